@@ -1,0 +1,148 @@
+// engine.h — internal declarations shared by the translation units of libibdgem_b200.so.
+// Nothing here is part of the ABI (that is include/ibdgem_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ibdgem_b200.h"
+
+namespace ibdgem {
+
+void set_error(const char *fmt, ...);
+
+#define IBD_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::ibdgem::set_error("[::] ERROR in %s (%s:%d): %s", #expr, __FILE__, __LINE__,      \
+                                cudaGetErrorString(_e));                                        \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+// Kernel ids for the per-kernel device timers / launch counters.
+enum KernelId {
+    K_SITE_TABLE = 0,   // A1 + M3/M4 per-site table
+    K_SCAN_COUNT,       // window map: per-block informative-site counts
+    K_SCAN_OFFSETS,     // window map: scan of block counts
+    K_SCAN_RANK,        // window map: ranks + window first/last sites
+    K_WINDOW_NONLD,     // W1/W2 non-LD window log-sums
+    K_COUNTERS,         // processed/skipped/final coverage distribution
+    K_EXPAND_SITES,     // expanded per-target tab values
+    K_LD_GENERAL,       // L1 general CUDA-core --LD window kernel
+    K_LD_FINALIZE,      // L2 merge of background-block partial log-sum-exps
+    K_LD_TRANSPOSE,     // tensor path: site-major bits -> window-padded haplotype-major bits
+    K_LD_EXPAND_BG,     // tensor path: background operand (0/1 int8, K-major)
+    K_LD_EXPAND_TGT,    // tensor path: target operand (depth-weighted int8, K-major)
+    K_LD_MARGINALS,     // tensor path: per-window per-haplotype linear terms + IBD0 chain
+    K_LD_IBD0,          // tensor path: IBD0 log-mean-exp with exclusion by omission
+    K_LD_MMA,           // tensor path: tcgen05 window GEMM + fused log-sum-exp epilogue
+    K_LD_COMBINE,       // tensor path: combine the two target haplotypes -> LIBD1
+    K_VITERBI,          // H1-H3 batched hiddengem
+    K_FILL,             // NaN fill of device score buffers
+    K_COUNT
+};
+
+extern const char *const kKernelNames[K_COUNT];
+
+struct PendingTimer {
+    int id;
+    cudaEvent_t a, b;
+};
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace ibdgem
+
+struct ibdgem_engine {
+    ibdgem_params prm{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int C = 21;  // max_cov + 1
+
+    // class tables: index = n_ref * C + n_alt
+    std::vector<double> h_P;    // [C*C][3]
+    std::vector<double> h_lnP;  // [C*C][3]
+    double *d_P = nullptr, *d_lnP = nullptr;
+    bool depth_linear = false;  // lnP2 - 2 lnP1 + lnP0 == n * kappa for every class
+    double kappa = 0, alpha = 0, beta = 0;
+
+    // uploaded inputs
+    int64_t S = 0;
+    int32_t N = 0;
+    int64_t Wh = 0;
+    uint64_t *d_pos = nullptr;
+    uint8_t *d_nref = nullptr, *d_nalt = nullptr, *d_hostkeep = nullptr;
+    double *d_afuser = nullptr;
+    uint32_t *d_bits = nullptr;
+    bool have_sites = false, have_panel = false, prepared = false;
+
+    // prepared, target-independent
+    double *d_f = nullptr;
+    uint8_t *d_keep = nullptr;    // passes every target-independent filter
+    uint8_t *d_status = nullptr;  // shared status (0/1/2)
+    double *d_lik7 = nullptr, *d_lnlik7 = nullptr;
+    uint32_t *d_rank = nullptr;   // shared exclusive rank of informative sites
+    int64_t *d_wfirst = nullptr, *d_wlast = nullptr;  // shared window first/last site
+    int32_t *d_nwin_shared = nullptr;  // device copy of nW_shared (window-map view)
+    int64_t *d_ktot_shared = nullptr;
+    int32_t nW_shared = 0;
+    int64_t K_shared = 0;
+
+    // tensor path caches (built lazily on first eligible score_ld)
+    struct LdCache *ld = nullptr;
+
+    // scratch
+    std::vector<ibdgem::DeviceBuf *> scratch;
+    int64_t device_bytes = 0;
+
+    // instrumentation
+    bool timing = false;
+    double k_ms[ibdgem::K_COUNT] = {0};
+    int64_t k_launches[ibdgem::K_COUNT] = {0};
+    std::vector<ibdgem::PendingTimer> pending;
+    std::vector<cudaEvent_t> event_pool;
+
+    int last_ld_path = -1;
+    int force_general = 0;
+};
+
+namespace ibdgem {
+
+// Timed launch helper: LAUNCH(e, K_ID) { kernel<<<...>>>(...); }
+struct LaunchScope {
+    ibdgem_engine *e;
+    int id;
+    cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(ibdgem_engine *e_, int id_);
+    ~LaunchScope();
+};
+int resolve_timers(ibdgem_engine *e);
+
+// grow-only scratch slots, kept across calls so steady-state scoring does not allocate
+enum ScratchSlot {
+    SC_TARGETS = 0, SC_BG, SC_TGT_COUNTS, SC_BLOCKCNT, SC_WFIRST, SC_WLAST, SC_NWIN, SC_KTOT, SC_WLL,
+    SC_WN, SC_WS, SC_WE, SC_COUNTERS, SC_SITE_STATUS, SC_SITE_LIK, SC_LD_PART, SC_NREFPANEL,
+    SC_HG_LIK, SC_HG_OFF, SC_HG_STATE, SC_HG_SCORE, SC_HG_COUNTS,
+    SC_MMA_TGT, SC_MMA_TROWS, SC_MMA_ROWLSE, SC_MMA_EXCL, SC_MMA_BGIDX, SC_MMA_MISC, SC_SLOTS
+};
+int scratch(ibdgem_engine *e, int slot, size_t bytes, void **out);
+
+int dev_alloc(ibdgem_engine *e, void **p, size_t bytes);
+void dev_free(ibdgem_engine *e, void *p, size_t bytes);
+
+// tensor-path entry points (ld_mma.cu)
+bool ld_tensor_eligible(ibdgem_engine *e, int32_t n_targets, int32_t n_bg, const uint8_t *tgt_counts);
+int ld_tensor_score(ibdgem_engine *e, int32_t n_targets, const int32_t *h_targets, int32_t n_bg,
+                    const int32_t *h_bg, int32_t pu_idx, double *d_wll /*[T][maxW][3]*/, int32_t maxW);
+void ld_tensor_release(ibdgem_engine *e);
+
+}  // namespace ibdgem
