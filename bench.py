@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native IBDGem engine.
+
+Metric (BASELINE.json): LD genotype-comparisons/s, one comparison = one
+site x target x background-individual x 1-of-4 haplotype pairing (the multiply at
+src/ibdgem.c:716-719 of the reference).  Workload at N=1: BASELINE.json configs[2] — `--LD`
+scoring of a synthetic chr20-scale panel, 1,000,000 sites x 2,504 phased samples, 1,000 targets,
+window 1,000 sites (SURVEY.md §8d "C3", depth >= 1 variant).  At N>1 every rank scores its own
+1,000 targets against the replicated panel (weak scaling) and the per-window scores are
+all-gathered over NCCL.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+    python bench.py --impl reference ...                     (the reference's CPU binary)
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "LD genotype-comparisons/s (site x target x bg x 4)"
+UNIT = "comparisons/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sites", type=int, default=1_000_000)
+    ap.add_argument("--samples", type=int, default=2504)
+    ap.add_argument("--targets", type=int, default=1000)
+    ap.add_argument("--window", type=int, default=1000)
+    ap.add_argument("--cpu-sites", type=int, default=10_000, help="site sample for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-general", action="store_true", help="A/B: CUDA-core --LD path")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU arm helpers
+def write_reference_sample(dirpath, bits_np, H, n_ref, n_alt, pos, n_sites):
+    """IMPUTE triple + pileup for the first n_sites of the workload (same seeded data)."""
+    from ibdgem_b200.synth import unpack_rows
+    os.makedirs(dirpath, exist_ok=True)
+    hap = unpack_rows(bits_np, H, np.arange(n_sites))
+    txt = np.full((n_sites, 2 * H), ord(" "), np.uint8)
+    txt[:, 0::2] = hap + ord("0")
+    txt[:, -1] = ord("\n")
+    txt.tofile(os.path.join(dirpath, "p.hap"))
+    with open(os.path.join(dirpath, "p.legend"), "w") as fh:
+        fh.write("ID pos allele0 allele1\n")
+        fh.write("".join("s%d %d A G\n" % (i, int(pos[i])) for i in range(n_sites)))
+    with open(os.path.join(dirpath, "p.indv"), "w") as fh:
+        fh.write("".join("i%d\n" % i for i in range(H // 2)))
+    with open(os.path.join(dirpath, "u.pileup"), "w") as fh:
+        for i in range(n_sites):
+            b = "A" * int(n_ref[i]) + "G" * int(n_alt[i])
+            c = len(b)
+            fh.write("20\t%d\tN\t%d\t%s\t%s\t%s\n" % (int(pos[i]), c, b or "*", "I" * c or "*", "]" * c or "*"))
+
+
+def run_reference_procs(binary, dirpath, targets, window):
+    """One process per target (the reference is single-threaded; independent processes sharded
+    with -s are how it uses more than one core).  Returns wall seconds."""
+    procs = []
+    t0 = time.perf_counter()
+    for t in targets:
+        out = os.path.join(dirpath, "out_%d" % t)
+        os.makedirs(out, exist_ok=True)
+        procs.append(subprocess.Popen([binary, "-H", "p.hap", "-L", "p.legend", "-I", "p.indv", "-P", "u.pileup",
+                                       "--LD", "-w", str(window), "-s", "i%d" % t, "-O", out], cwd=dirpath,
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("reference binary failed")
+    return time.perf_counter() - t0
+
+
+def host_sample(args, seed=1):
+    """The first cpu_sites sites of the synthetic workload, generated on the host with numpy."""
+    from ibdgem_b200.synth import synth_panel_numpy
+    return synth_panel_numpy(args.cpu_sites, args.samples, seed=seed)
+
+
+def cpu_baseline(args, sample=None, n_procs=1):
+    """Times the reference's own CPU implementation of the path on a bounded sample."""
+    d = sample if sample is not None else host_sample(args)
+    S1 = args.cpu_sites
+    H = 2 * args.samples
+    inf = int(((d["n_ref"][:S1].astype(int) + d["n_alt"][:S1]) >= 1).sum())
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ibdgem")
+    tmp = tempfile.mkdtemp(prefix="ibdgem_cpu_")
+    try:
+        if os.path.exists(ref_bin):
+            write_reference_sample(tmp, d["bits"], H, d["n_ref"], d["n_alt"], d["pos"], S1)
+            targets = list(range(n_procs))
+            wall = run_reference_procs(ref_bin, tmp, targets, args.window)
+            comps = len(targets) * inf * (args.samples - 1) * 4
+            kind = "reference"
+            note = "oracle/_ref/ibdgem (unmodified reference, as-shipped flags -ggdb3 = -O0)"
+        else:
+            import oracle
+            from ibdgem_b200.synth import unpack_rows
+            hap = unpack_rows(d["bits"], H, np.arange(S1))
+            prm = oracle.Params(window=args.window, ld_mode=1)
+            t0 = time.perf_counter()
+            comps = oracle.ld_loop_bench(prm, d["n_ref"][:S1], d["n_alt"][:S1], hap, np.arange(1, dtype=np.int32),
+                                         np.arange(args.samples, dtype=np.int32))
+            wall = time.perf_counter() - t0
+            kind = "port"
+            note = "oracle/liboracle.so orc_ld_loop_bench (C restatement of src/ibdgem.c:673-721, -O2)"
+            n_procs = 1
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return dict(value=comps / wall, unit=UNIT, cores=n_procs, kind=kind,
+                sample="%s; first %d sites x %d target(s) x %d background, --LD -w %d, %.2f s wall" % (
+                    note, S1, n_procs, args.samples - 1, args.window, wall)), comps, wall
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_procs = max(1, min(os.cpu_count() or 1, 64))
+    sample = host_sample(args)
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        cb, comps, wall = cpu_baseline(args, sample, n_procs)
+        if i >= args.warmup:
+            vals.append((comps, wall))
+        last = cb
+    comps = sum(c for c, _ in vals)
+    wall = sum(w for _, w in vals)
+    v = comps / wall
+    last["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / max(len(vals), 1) * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "--LD scoring, bounded CPU sample of C3: first %d sites x %d targets (one process "
+                               "per target on %d host cores) x %d background, window %d" % (
+                                   args.cpu_sites, n_procs, n_procs, args.samples - 1, args.window)},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ibdgem_b200 as ib
+    from ibdgem_b200.engine import _CScores
+    from ibdgem_b200.synth import synth_panel_torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, N, T, W = args.sites, args.samples, args.targets, args.window
+    d = synth_panel_torch(S, N, seed=1, device=dev)  # pinned host tensors, identical on every rank
+    bits = d["bits"].numpy().view(np.uint32)
+    pos = d["pos"].numpy().view(np.uint64)
+    n_ref, n_alt, keep = d["n_ref"].numpy(), d["n_alt"].numpy(), d["keep"].numpy()
+    # weak scaling: every rank scores its own T targets
+    targets = ((rank * T + np.arange(T)) % N).astype(np.int32)
+    bg = np.arange(N, dtype=np.int32)
+    inf_sites = int(((n_ref.astype(np.int64) + n_alt) >= 1).sum())
+    comps_rank = inf_sites * int(T) * (N - 1) * 4
+    maxW = S // W + 2
+
+    eng = ib.Engine(ib.Params(window_size=W, device=local_rank))
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.enable_timing(True)
+    if args.force_general:
+        eng.force_general_ld(True)
+
+    # pinned result buffers + a device tensor for the gather
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+    o_nw = pinned((T,), torch.int32)
+    o_ws, o_we = pinned((T, maxW), torch.int64), pinned((T, maxW), torch.int64)
+    o_wn = pinned((T, maxW), torch.int32)
+    o_ll = pinned((T, maxW, 3), torch.float64)
+    d_ll = torch.empty((T, maxW, 3), dtype=torch.float64, device=dev)
+    d_all = torch.empty((world * T, maxW, 3), dtype=torch.float64, device=dev) if world > 1 else None
+    cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr(), o_we.data_ptr(), o_wn.data_ptr(), o_ll.data_ptr(),
+                  None, None, None, None, None, None, d_ll.data_ptr())
+
+    def upload():
+        eng.upload_sites(pos, n_ref, n_alt, keep)
+        eng.upload_panel(bits, N)
+
+    def score():
+        eng.score_ld_raw(targets, bg, -1, cs)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all.view(-1), d_ll.view(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    upload()
+    eng.prepare()
+    for _ in range(max(args.warmup, 3)):
+        score()
+    eng.reset_stats()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = timed(score, args.steps)
+    clocks = sampler.stop() if sampler else None
+    stats = eng.kernel_stats()
+    ld_path = eng.last_ld_path()
+    ms_step = ms_total / args.steps
+    value = comps_rank * world / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers in, host results out, every step -------------------------------------
+    def e2e_step():
+        upload()
+        score()
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(2, min(args.steps, 3))
+    ms_e2e = timed(e2e_step, e2e_steps) / e2e_steps
+    h2d = bits.nbytes + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes
+    d2h = o_nw.numel() * 4 + o_ws.numel() * 8 * 2 + o_wn.numel() * 4 + o_ll.numel() * 8
+    e2e_value = comps_rank * world / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        launches = int(sum(n for _, n in stats.values()))
+        dom = "ld_mma" if ld_path == 1 else "ld_general"
+        dom_ms, dom_n = stats[dom]
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except OSError:
+            pass
+        # Algorithmic work of the dominant kernel: one multiply-accumulate of the
+        # weighted binary contraction sum_s n_s h_s k_s per comparison = 2 op / comparison; the int8
+        # tensor-core rate of sm_100a is 2x its bf16 rate, so the denominator is 2 x the measured dense
+        # bf16 figure.
+        flop_per_launch = 2.0 * comps_rank * args.steps / max(dom_n, 1)
+        avg_ms = dom_ms / max(dom_n, 1)
+        achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+        bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak = 2.0 * bf16 if ld_path == 1 else bf16
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "kernel": dom, "avg_launch_ms": avg_ms,
+                    "launches": dom_n,
+                    "peak_source": ("2 x bf16_tflops_sustained of measured MEASURED_PEAKS.json (int8 tcgen05 rate "
+                                    "= 2 x bf16)" if ld_path == 1 else "bf16_tflops_sustained of measured") if peaks
+                    else "fallback 1.4 PFLOP/s sustained bf16",
+                    "kernel_share_of_step": dom_ms / (ms_total) if ms_total > 0 else None,
+                    "kernels_ms_per_step": {k: v[0] / args.steps for k, v in stats.items() if v[1]}}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 --LD scoring: %d sites x %d-sample phased panel, %d targets per GPU, "
+                                   "window %d, depth Poisson(2)+1 (BASELINE.json configs[2])" % (S, N, T, W),
+                       "sites": S, "samples": N, "targets_per_gpu": T, "window": W,
+                       "parallelism": "targets sharded across %d GPU(s), panel replicated, one all_gather of "
+                                      "window scores" % world,
+                       "ld_path": "tensor (tcgen05 int8 window GEMM + fused LSE)" if ld_path == 1 else "general CUDA-core",
+                       "l2": "inputs larger than L2 (packed panel %.0f MB, operands %.1f GB)" % (
+                           bits.nbytes / 1e6, eng.device_bytes() / 1e9)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _, _ = cpu_baseline(args)
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
