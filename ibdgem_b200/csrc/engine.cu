@@ -26,8 +26,9 @@ void set_error(const char *fmt, ...) {
 
 const char *const kKernelNames[K_COUNT] = {
     "site_table",     "scan_count",    "scan_offsets",  "scan_rank",    "window_nonld", "counters",
-    "expand_sites",   "ld_general",    "ld_finalize",   "ld_transpose", "ld_expand_bg", "ld_expand_tgt",
-    "ld_marginals",   "ld_ibd0",       "ld_mma",        "ld_combine",   "viterbi",      "fill",
+    "expand_sites",   "ld_general",    "ld_finalize",   "ld_compact",   "ld_c0",        "ld_transpose",
+    "ld_marginals",   "ld_tables",     "ld_expand_bg",  "ld_expand_tgt", "ld_windows",  "ld_ibd0",
+    "ld_mma",         "viterbi",       "fill",
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1016,15 +1017,22 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     IBD_CUDA(cudaMemsetAsync(d_wn, 0, nWT * 4 + (size_t)T * 4, e->stream));
     IBD_CUDA(cudaMemsetAsync(d_ws, 0, nWT * 8, e->stream));
     IBD_CUDA(cudaMemsetAsync(d_we, 0, nWT * 8, e->stream));
-    {
-        LaunchScope ls(e, K_WINDOW_NONLD);
-        const int64_t warps = (int64_t)nWT;
-        window_nonld_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
-            v, m, d_targets, T, e->d_pos, e->d_f, e->d_lnlik7, e->d_P, C, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
+    const bool tensor = ld && !e->force_general && shared && ld_tensor_eligible(e, T, n_bg, tgt_counts);
+    if (tensor) {
+        // tensor path: fills window bookkeeping, LIBD0, LIBD1 and LIBD2 of every target
+        if (ld_tensor_score(e, T, targets, d_targets, n_bg, bg, pu_idx, outW, d_wll, d_wn, d_ws, d_we, d_nwout)) return 1;
+        e->last_ld_path = 1;
+    } else {
+        {
+            LaunchScope ls(e, K_WINDOW_NONLD);
+            const int64_t warps = (int64_t)nWT;
+            window_nonld_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
+                v, m, d_targets, T, e->d_pos, e->d_f, e->d_lnlik7, e->d_P, C, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
+        }
+        IBD_CUDA(cudaGetLastError());
     }
-    IBD_CUDA(cudaGetLastError());
 
-    if (ld) {
+    if (ld && !tensor) {
         std::vector<int32_t> h_nref(T);
         for (int t = 0; t < T; t++) {
             int c = 0;
@@ -1032,10 +1040,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
                 if (bg[n] != targets[t] && bg[n] != pu_idx) c++;
             h_nref[t] = c;
         }
-        if (!e->force_general && shared && ld_tensor_eligible(e, T, n_bg, tgt_counts)) {
-            if (ld_tensor_score(e, T, targets, n_bg, bg, pu_idx, d_wll, outW)) return 1;
-            e->last_ld_path = 1;
-        } else {
+        {
             int32_t *d_bg, *d_nrp;
             LdPartial *d_part;
             const int nz = std::max(1, (n_bg + LD_THREADS * LD_PER - 1) / (LD_THREADS * LD_PER));

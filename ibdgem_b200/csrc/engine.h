@@ -35,19 +35,24 @@ enum KernelId {
     K_EXPAND_SITES,     // expanded per-target tab values
     K_LD_GENERAL,       // L1 general CUDA-core --LD window kernel
     K_LD_FINALIZE,      // L2 merge of background-block partial log-sum-exps
+    K_LD_COMPACT,       // tensor path: informative sites -> window slots (depth, l1-l0, l0)
+    K_LD_C0,            // tensor path: per-window sum of l0
     K_LD_TRANSPOSE,     // tensor path: site-major bits -> window-padded haplotype-major bits
+    K_LD_MARGINALS,     // tensor path: per-window per-haplotype linear terms + per-individual chain
+    K_LD_TABLES,        // tensor path: screening keys / R' / Q' of the call's background columns
     K_LD_EXPAND_BG,     // tensor path: background operand (0/1 int8, K-major)
     K_LD_EXPAND_TGT,    // tensor path: target operand (depth-weighted int8, K-major)
-    K_LD_MARGINALS,     // tensor path: per-window per-haplotype linear terms + IBD0 chain
-    K_LD_IBD0,          // tensor path: IBD0 log-mean-exp with exclusion by omission
-    K_LD_MMA,           // tensor path: tcgen05 window GEMM + fused log-sum-exp epilogue
-    K_LD_COMBINE,       // tensor path: combine the two target haplotypes -> LIBD1
+    K_LD_WINDOWS,       // tensor path: window bookkeeping + LIBD2
+    K_LD_IBD0,          // tensor path: LIBD0 log-mean-exp with exclusion by omission
+    K_LD_MMA,           // tensor path: tcgen05 window GEMM + fused log-sum-exp epilogue -> LIBD1
     K_VITERBI,          // H1-H3 batched hiddengem
     K_FILL,             // NaN fill of device score buffers
     K_COUNT
 };
 
 extern const char *const kKernelNames[K_COUNT];
+
+struct LdCache;  // ld_mma.cu
 
 struct PendingTimer {
     int id;
@@ -98,7 +103,7 @@ struct ibdgem_engine {
     int64_t K_shared = 0;
 
     // tensor path caches (built lazily on first eligible score_ld)
-    struct LdCache *ld = nullptr;
+    ibdgem::LdCache *ld = nullptr;
 
     // scratch
     std::vector<ibdgem::DeviceBuf *> scratch;
@@ -132,7 +137,7 @@ enum ScratchSlot {
     SC_TARGETS = 0, SC_BG, SC_TGT_COUNTS, SC_BLOCKCNT, SC_WFIRST, SC_WLAST, SC_NWIN, SC_KTOT, SC_WLL,
     SC_WN, SC_WS, SC_WE, SC_COUNTERS, SC_SITE_STATUS, SC_SITE_LIK, SC_LD_PART, SC_NREFPANEL,
     SC_HG_LIK, SC_HG_OFF, SC_HG_STATE, SC_HG_SCORE, SC_HG_COUNTS,
-    SC_MMA_TGT, SC_MMA_TROWS, SC_MMA_ROWLSE, SC_MMA_EXCL, SC_MMA_BGIDX, SC_MMA_MISC, SC_SLOTS
+    SC_MMA_TGT, SC_MMA_BG, SC_MMA_ROWLSE, SC_MMA_BGIDX, SC_MMA_MISC, SC_SLOTS
 };
 int scratch(ibdgem_engine *e, int slot, size_t bytes, void **out);
 
@@ -141,8 +146,10 @@ void dev_free(ibdgem_engine *e, void *p, size_t bytes);
 
 // tensor-path entry points (ld_mma.cu)
 bool ld_tensor_eligible(ibdgem_engine *e, int32_t n_targets, int32_t n_bg, const uint8_t *tgt_counts);
-int ld_tensor_score(ibdgem_engine *e, int32_t n_targets, const int32_t *h_targets, int32_t n_bg,
-                    const int32_t *h_bg, int32_t pu_idx, double *d_wll /*[T][maxW][3]*/, int32_t maxW);
+int ld_tensor_prepare(ibdgem_engine *e);
+int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const int32_t *d_targets, int32_t n_bg,
+                    const int32_t *h_bg, int32_t pu_idx, int32_t outW, double *d_wll /*[T][outW][3]*/, int32_t *d_wn,
+                    uint64_t *d_ws, uint64_t *d_we, int32_t *d_nwout);
 void ld_tensor_release(ibdgem_engine *e);
 
 }  // namespace ibdgem

@@ -1,10 +1,912 @@
-// ld_mma.cu — tensor-core --LD path (placeholder until the tcgen05 kernel lands).
+// ld_mma.cu — tensor-core --LD window scoring (L1 + L2, src/ibdgem.c:673-753) for the common case
+// of shared windows (no -v, no -D) and a depth-linear class table.
+//
+// Algebra (DESIGN.md "tensor path").  With l_g(s) = ln P_s(D|G=g), d1 = l1 - l0 and
+// l2 - 2 l1 + l0 = n_s * kappa (kappa = ln 4 eps (1-eps), n_s = pileup depth), two haplotypes x, y
+// over a window w give
+//     ln prod_s P_s[x_s + y_s] = C0_w + R_w[x] + R_w[y] + kappa * M_w[x, y],
+//     C0 = sum l0,   R[x] = sum x_s d1_s,   M[x, y] = sum n_s x_s y_s   (an INTEGER).
+// So the 4 pseudo-diploid pairings of every target x background pair (the loop the reference
+// spends 78 % of its time in) are one exact int8 GEMM per window, [2T x W] . [W x 2B] -> int32,
+// on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), and
+//     LIBD1_w(t) = C0 + LSE_i ( R[a_i] + LSE_{k not own(t)} ( R'[k] + kappa M[a_i, k] ) ) - ln 4 nB
+// is evaluated in the epilogue straight out of TMEM in fp64.  Because M is an integer, the
+// epilogue first screens every element with an integer key (round(R'[k]/|kappa|) - M); only
+// elements within 32 nats of the running row maximum reach the fp64 exp — the dropped mass is
+// below 2N e^-32 ~ 1e-10 relative.  LIBD0 (the chain over background individuals) and LIBD2 are
+// target-independent per individual: Q_w[b] = C0 + R[r0] + R[r1] + kappa M[r0, r1].
+//
+// Kernels in this file: ld_compact, ld_c0, ld_transpose, ld_marginals (cached per prepared
+// panel); ld_tables, ld_expand_bg, ld_expand_tgt, ld_windows, ld_mma, ld_ibd0 (per call).
+#include <cuda.h>
+#include <math.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <map>
+#include <vector>
+
 #include "engine.h"
+
 namespace ibdgem {
-bool ld_tensor_eligible(ibdgem_engine *, int32_t, int32_t, const uint8_t *) { return false; }
-int ld_tensor_score(ibdgem_engine *, int32_t, const int32_t *, int32_t, const int32_t *, int32_t, double *, int32_t) {
-    set_error("[::] ERROR: tensor --LD path not built.");
-    return 1;
+
+// ---------------------------------------------------------------------------------------------
+// cached, target-independent operands
+struct LdCache {
+    bool valid = false;
+    int32_t nW = 0;
+    int64_t K = 0;
+    int W = 0, Wpad = 0, WP32 = 0, KB = 0;
+    int H = 0, N = 0;
+    int32_t *d_infsite = nullptr;  // [nW][Wpad] site index of each window slot, -1 = padding
+    uint8_t *d_nk = nullptr;       // [nW][Wpad] pileup depth n_s of the slot
+    double *d_d1 = nullptr;        // [nW][Wpad] l1 - l0
+    double *d_l0 = nullptr;        // [nW][Wpad] l0
+    double *d_C0 = nullptr;        // [nW]
+    uint32_t *d_tbits = nullptr;   // [nW][H][WP32] haplotype-major window-padded bits
+    double *d_Rw = nullptr;        // [nW][H]
+    double *d_Qw = nullptr;        // [nW][N]
+    size_t b_infsite = 0, b_nk = 0, b_d1 = 0, b_l0 = 0, b_C0 = 0, b_tbits = 0, b_Rw = 0, b_Qw = 0;
+};
+
+constexpr int KEY_PAD = -(1 << 30);   // key of padding / excluded columns
+constexpr int KEY_INIT = -(1 << 29);  // initial running maximum
+constexpr double SCREEN_NATS = 32.0;
+constexpr size_t LD_OPERAND_BUDGET = (size_t)12 << 30;  // bytes of expanded int8 operands per window batch
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-void ld_tensor_release(ibdgem_engine *) {}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand slab (rows of 128 bytes, 8-row groups 1024 bytes apart):
+// the tcgen05 shared-memory matrix descriptor.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+    return d;
+}
+
+// exp(x) for x <= 0 in fp64: Cody-Waite reduction, degree-12 Taylor polynomial on |r| <= ln2/2
+// (truncation 2e-16), exponent rebuilt by integer add.  Used only on screened elements.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    if (!(x > -700.0)) return 0.0;
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);  // round(x log2 e) in the low word
+    const int n = __double2loint(t);
+    const double nr = t - 6755399441055744.0;
+    double r = fma(nr, -6.93147180369123816490e-01, x);
+    r = fma(nr, -1.90821492927058770002e-10, r);
+    double p = 2.08767569878680989792e-09;  // 1/12!
+    p = fma(p, r, 2.50521083854417187751e-08);
+    p = fma(p, r, 2.75573192239858906526e-07);
+    p = fma(p, r, 2.75573192239858906526e-06);
+    p = fma(p, r, 2.48015873015873015873e-05);
+    p = fma(p, r, 1.98412698412698412698e-04);
+    p = fma(p, r, 1.38888888888888888889e-03);
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + n * 1048576, __double2loint(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// cached-operand kernels
+
+// one thread per panel line: informative kept sites go to their window slot
+__global__ void __launch_bounds__(256)
+ld_compact_kernel(int64_t S, const uint8_t *__restrict__ status, const uint32_t *__restrict__ rank,
+                  const uint8_t *__restrict__ nref, const uint8_t *__restrict__ nalt,
+                  const double *__restrict__ lnP, int C, int W, int Wpad, int32_t *__restrict__ infsite,
+                  uint8_t *__restrict__ nk, double *__restrict__ d1, double *__restrict__ l0) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= S || status[s] != 1) return;
+    const uint32_t r = rank[s];
+    const int64_t slot = (int64_t)(r / (uint32_t)W) * Wpad + (r % (uint32_t)W);
+    const int a = nref[s], b = nalt[s];
+    const double *L = lnP + (size_t)(a * C + b) * 3;
+    infsite[slot] = (int32_t)s;
+    nk[slot] = (uint8_t)(a + b);
+    d1[slot] = L[1] - L[0];
+    l0[slot] = L[0];
+}
+
+// C0_w = sum of l0 over the window, fixed-order tree so the value is reproducible
+__global__ void __launch_bounds__(256) ld_c0_kernel(const double *__restrict__ l0, int Wpad, double *__restrict__ C0) {
+    __shared__ double sh[256];
+    const double *p = l0 + (size_t)blockIdx.x * Wpad;
+    double a = 0;
+    for (int k = threadIdx.x; k < Wpad; k += 256) a += p[k];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) C0[blockIdx.x] = sh[0];
+}
+
+// site-major panel bits -> [window][haplotype][32-site words].  Block = (8 word columns = 256
+// haplotypes, one window); warp g transposes the 32x32 bit blocks of window slots 32g..32g+31
+// with ballots; the tile goes through shared memory so the stores are 128-byte rows.
+__global__ void __launch_bounds__(1024)
+ld_transpose_kernel(const uint32_t *__restrict__ bits, int64_t Wh, int H, const int32_t *__restrict__ infsite,
+                    int Wpad, int WP32, uint32_t *__restrict__ tbits) {
+    __shared__ uint32_t tile[256 * 33];
+    const int w = blockIdx.x, j0 = blockIdx.y * 8;
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    if (g < WP32) {
+        const int32_t s = infsite[(size_t)w * Wpad + g * 32 + lane];
+        const uint32_t *row = bits + (size_t)(s < 0 ? 0 : s) * Wh;
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            uint32_t word = 0;
+            if (s >= 0 && j0 + jj < Wh) word = __ldg(row + j0 + jj);
+            uint32_t out = 0;
+#pragma unroll
+            for (int b = 0; b < 32; b++) {
+                const uint32_t m = __ballot_sync(0xffffffffu, (word >> b) & 1u);
+                if (lane == b) out = m;
+            }
+            tile[(jj * 32 + lane) * 33 + g] = out;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * WP32; i += 1024) {
+        const int hl = i / WP32, gg = i % WP32;
+        const int hap = j0 * 32 + hl;
+        if (hap < H) tbits[((size_t)w * H + hap) * WP32 + gg] = tile[hl * 33 + gg];
+    }
+}
+
+// one thread per (window, haplotype): R_w[x] = sum_s x_s d1_s in site order, and for each
+// individual Q_w[b] = C0 + R[r0] + R[r1] + kappa * sum_s n_s r0_s r1_s.
+__global__ void __launch_bounds__(256)
+ld_marginals_kernel(const uint32_t *__restrict__ tbits, int H, int Wpad, int WP32, const double *__restrict__ d1,
+                    const uint8_t *__restrict__ nk, const double *__restrict__ C0, double kappa,
+                    double *__restrict__ Rw, double *__restrict__ Qw) {
+    extern __shared__ unsigned char shraw[];
+    double *sd = reinterpret_cast<double *>(shraw);
+    uint8_t *sn = shraw + (size_t)Wpad * 8;
+    const int w = blockIdx.x;
+    for (int k = threadIdx.x; k < Wpad; k += blockDim.x) {
+        sd[k] = d1[(size_t)w * Wpad + k];
+        sn[k] = nk[(size_t)w * Wpad + k];
+    }
+    __syncthreads();
+    const int hap = blockIdx.y * blockDim.x + threadIdx.x;  // pairs (2i, 2i+1) share a warp
+    const bool ok = hap < H;
+    const uint32_t *row = tbits + ((size_t)w * H + (ok ? hap : 0)) * WP32;
+    double R = 0;
+    int ms = 0;
+    for (int g = 0; g < WP32; g++) {
+        const uint32_t word = ok ? __ldg(row + g) : 0u;
+        const uint32_t both = word & __shfl_xor_sync(0xffffffffu, word, 1);
+#pragma unroll 8
+        for (int b = 0; b < 32; b++) {
+            const int k = g * 32 + b;
+            if ((word >> b) & 1u) R += sd[k];
+            if ((both >> b) & 1u) ms += sn[k];
+        }
+    }
+    const double Rp = __shfl_xor_sync(0xffffffffu, R, 1);
+    if (ok) {
+        Rw[(size_t)w * H + hap] = R;
+        if ((hap & 1) == 0) Qw[(size_t)w * (H / 2) + (hap >> 1)] = ((C0[w] + R) + Rp) + kappa * (double)ms;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-call kernels
+
+// screening keys and R'[k] = R[k] + ln(multiplicity) for every background haplotype column
+__global__ void __launch_bounds__(256)
+ld_tables_kernel(int nW, int ncols, int ncolpad, int H, const int32_t *__restrict__ bgU, const double *__restrict__ lnc,
+                 const double *__restrict__ Rw, const double *__restrict__ Qw, double inv_abs_kappa,
+                 int32_t *__restrict__ akey, double *__restrict__ Rp, double *__restrict__ Qp) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nW * ncolpad) return;
+    const int w = (int)(i / ncolpad), c = (int)(i % ncolpad);
+    if (c < ncols) {
+        const int u = c >> 1, ind = bgU[u];
+        const double rp = Rw[(size_t)w * H + 2 * ind + (c & 1)] + lnc[u];
+        Rp[i] = rp;
+        akey[i] = (int32_t)rint(rp * inv_abs_kappa);
+        if ((c & 1) == 0) Qp[(size_t)w * (ncols / 2) + u] = Qw[(size_t)w * (H / 2) + ind] + lnc[u];
+    } else {
+        Rp[i] = -INFINITY;
+        akey[i] = KEY_PAD;
+    }
+}
+
+__device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+// background operand: [window][column][Wpad] bytes, 0/1, K-major
+__global__ void __launch_bounds__(256)
+ld_expand_bg_kernel(int64_t total, int w0, int ncols, int H, int WP32, const int32_t *__restrict__ bgU,
+                    const uint32_t *__restrict__ tbits, uint4 *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % WP32);
+    const int64_t wc = i / WP32;
+    const int c = (int)(wc % ncols), w = w0 + (int)(wc / ncols);
+    const int hap = 2 * bgU[c >> 1] + (c & 1);
+    const uint32_t word = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
+    uint4 lo, hi;
+    lo.x = spread4(word & 15u); lo.y = spread4((word >> 4) & 15u); lo.z = spread4((word >> 8) & 15u); lo.w = spread4((word >> 12) & 15u);
+    hi.x = spread4((word >> 16) & 15u); hi.y = spread4((word >> 20) & 15u); hi.z = spread4((word >> 24) & 15u); hi.w = spread4(word >> 28);
+    out[i * 2] = lo;
+    out[i * 2 + 1] = hi;
+}
+
+// target operand: [window][row][Wpad] bytes, n_s * h_s, K-major
+__global__ void __launch_bounds__(256)
+ld_expand_tgt_kernel(int64_t total, int w0, int nrows, int H, int Wpad, int WP32, const int32_t *__restrict__ targets,
+                     const uint32_t *__restrict__ tbits, const uint8_t *__restrict__ nk, uint4 *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % WP32);
+    const int64_t wr = i / WP32;
+    const int r = (int)(wr % nrows), w = w0 + (int)(wr / nrows);
+    const int hap = 2 * targets[r >> 1] + (r & 1);
+    const uint32_t word = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
+    const uint4 *nv = reinterpret_cast<const uint4 *>(nk + (size_t)w * Wpad + g * 32);
+    const uint4 n0 = __ldg(nv), n1 = __ldg(nv + 1);
+    uint4 lo, hi;
+    lo.x = (spread4(word & 15u) * 0xFFu) & n0.x; lo.y = (spread4((word >> 4) & 15u) * 0xFFu) & n0.y;
+    lo.z = (spread4((word >> 8) & 15u) * 0xFFu) & n0.z; lo.w = (spread4((word >> 12) & 15u) * 0xFFu) & n0.w;
+    hi.x = (spread4((word >> 16) & 15u) * 0xFFu) & n1.x; hi.y = (spread4((word >> 20) & 15u) * 0xFFu) & n1.y;
+    hi.z = (spread4((word >> 24) & 15u) * 0xFFu) & n1.z; hi.w = (spread4(word >> 28) * 0xFFu) & n1.w;
+    out[i * 2] = lo;
+    out[i * 2 + 1] = hi;
+}
+
+// window bookkeeping (W2) and LIBD2 = Q_w[target] for every (target, window)
+__global__ void __launch_bounds__(256)
+ld_windows_kernel(int T, int nW, int outW, int W, int64_t K, const int32_t *__restrict__ targets, int Nind,
+                  const int64_t *__restrict__ wfirst, const int64_t *__restrict__ wlast, const uint64_t *__restrict__ pos,
+                  const double *__restrict__ Qw, double *__restrict__ wll, int32_t *__restrict__ wn,
+                  uint64_t *__restrict__ ws, uint64_t *__restrict__ we, int32_t *__restrict__ nwout) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T * outW) return;
+    const int t = (int)(i / outW), w = (int)(i % outW);
+    if (w == 0) nwout[t] = nW;
+    if (w >= nW) return;
+    wll[i * 3 + 2] = Qw[(size_t)w * Nind + targets[t]];
+    const int64_t left = K - (int64_t)w * W;
+    wn[i] = (int32_t)(left < W ? left : W);
+    ws[i] = pos[wfirst[w]];
+    we[i] = pos[wlast[w]];
+}
+
+// LIBD0: log-mean-exp of Q'_w over the background, the target's own entry omitted (never
+// subtracted).  One block per window; 64 chunk partials so an omission re-scans one chunk only.
+constexpr int IBD0_CHUNKS = 64;
+__global__ void __launch_bounds__(256)
+ld_ibd0_kernel(int T, int nU, int outW, const double *__restrict__ Qp, const int32_t *__restrict__ ownU,
+               const double *__restrict__ lognb, double *__restrict__ wll) {
+    __shared__ double cm[IBD0_CHUNKS], cs[IBD0_CHUNKS];
+    __shared__ double tot_m, tot_s;
+    const int w = blockIdx.x;
+    const double *q = Qp + (size_t)w * nU;
+    const int clen = (nU + IBD0_CHUNKS - 1) / IBD0_CHUNKS;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c = wid; c < IBD0_CHUNKS; c += 8) {
+        const int u0 = c * clen, u1 = min(nU, u0 + clen);
+        double m = -INFINITY;
+        for (int u = u0 + lane; u < u1; u += 32) m = fmax(m, q[u]);
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        double s = 0;
+        if (m > -INFINITY)
+            for (int u = u0 + lane; u < u1; u += 32) s += exp(q[u] - m);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) { cm[c] = m; cs[c] = s; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = -INFINITY;
+        for (int c = 0; c < IBD0_CHUNKS; c++) m = fmax(m, cm[c]);
+        double s = 0;
+        for (int c = 0; c < IBD0_CHUNKS; c++)
+            if (cs[c] > 0) s += cs[c] * exp(cm[c] - m);
+        tot_m = m; tot_s = s;
+    }
+    __syncthreads();
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const double lnb = lognb[t];
+        double r;
+        if (!(lnb == lnb)) {
+            r = nan;  // n_refpanel = 0: 0/0 in the reference
+        } else {
+            const int own = ownU[t];
+            if (own < 0 || q[own] < tot_m - 60.0) {
+                r = tot_m + log(tot_s) - lnb;
+            } else {
+                const int oc = own / clen;
+                double m = -INFINITY;
+                for (int c = 0; c < IBD0_CHUNKS; c++)
+                    if (c != oc) m = fmax(m, cm[c]);
+                const int u0 = oc * clen, u1 = min(nU, u0 + clen);
+                for (int u = u0; u < u1; u++)
+                    if (u != own) m = fmax(m, q[u]);
+                double s = 0;
+                for (int c = 0; c < IBD0_CHUNKS; c++)
+                    if (c != oc && cs[c] > 0) s += cs[c] * exp(cm[c] - m);
+                for (int u = u0; u < u1; u++)
+                    if (u != own) s += exp(q[u] - m);
+                r = m + log(s) - lnb;
+            }
+        }
+        wll[((size_t)t * outW + w) * 3 + 0] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_LD_MMA: persistent, warp-specialised window GEMM with the fused log-sum-exp epilogue.
+//   unit = (window w, block of 128 target haplotypes); the unit's A tile (128 rows x Wpad bytes)
+//   stays resident in shared memory while the background tiles (128 columns x 128 bytes per
+//   stage) stream through a TMA ring; accumulators (128 x 128 int32) rotate through 4 TMEM
+//   slots; two sets of 4 epilogue warps alternate tiles, each thread owning one target
+//   haplotype row, so the reduction over background columns needs no cross-thread traffic.
+namespace mma {
+constexpr int BM = 128, BN = 128, KBYTES = 128, UK = 32;
+constexpr int MAXKB = 8;        // Wpad <= 1024
+constexpr int NSTAGE = 5;       // background ring
+constexpr int NACC = 4;         // TMEM accumulator slots (4 x 128 columns = all 512)
+constexpr int A_SLAB = BM * KBYTES;   // 16 KB
+constexpr int B_SLAB = BN * KBYTES;   // 16 KB
+constexpr int THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+// shared memory map (offsets from the 1024-aligned base)
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + MAXKB * A_SLAB;
+constexpr int OFF_KEYS = OFF_B + NSTAGE * B_SLAB;      // 8 warps x 128 int32
+constexpr int OFF_MERGE = OFF_KEYS + 8 * BN * 4;       // 2 x 128 x double2
+constexpr int OFF_BAR = OFF_MERGE + 2 * BM * 16;
+constexpr int NBAR = 2 + 2 * NSTAGE + 2 * NACC;
+constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;       // + alignment slack
+constexpr uint32_t IDESC = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (0u << 10) /* B = u8 */ |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct Params {
+    int w0;                  // first window of this batch (operands hold windows w0 .. w0 + nW - 1)
+    int nW, MB, NT, KB;      // windows, row blocks per window, column tiles, 128-byte k blocks
+    int n_units;
+    int nrows, ncolpad;      // 2T, NT * 128
+    int H, outW;
+    int delta;               // screening distance in key units
+    double kappa;
+    const int32_t *akey;     // [nW][ncolpad]
+    const double *Rp;        // [nW][ncolpad]
+    const double *Rw;        // [nW][H]
+    const int32_t *row_hap;  // [nrows] panel haplotype of each row
+    const int32_t *row_own;  // [nrows] first excluded column of the row, or -1
+    const double *C0;        // [nW]
+    const double *lognb4;    // [T] ln(4 n_refpanel) or NaN
+    double *wll;             // [T][outW][3]
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
+    uint64_t *a_full = bars, *a_empty = bars + 1;
+    uint64_t *b_full = bars + 2, *b_empty = bars + 2 + NSTAGE;
+    uint64_t *acc_full = bars + 2 + 2 * NSTAGE, *acc_empty = acc_full + NACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++) {
+                const int w = u / p.MB, mb = u % p.MB;
+                mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
+                mbar_expect_tx(a_full, (uint32_t)(p.KB * A_SLAB));
+                for (int kb = 0; kb < p.KB; kb++)
+                    tma_load_3d(smem + OFF_A + kb * A_SLAB, &tmapA, a_full, kb * KBYTES, mb * BM, w);
+                for (int n = 0; n < p.NT; n++)
+                    for (int kb = 0; kb < p.KB; kb++) {
+                        mbar_wait(b_empty + st, ph ^ 1u);
+                        mbar_expect_tx(b_full + st, (uint32_t)B_SLAB);
+                        tma_load_3d(smem + OFF_B + st * B_SLAB, &tmapB, b_full + st, kb * KBYTES, n * BN, w);
+                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            uint32_t g = 0;  // accumulator tile counter
+            const uint32_t a_base = smem_u32(smem + OFF_A), b_base = smem_u32(smem + OFF_B);
+            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++) {
+                mbar_wait(a_full, (uint32_t)(it & 1));
+                for (int n = 0; n < p.NT; n++, g++) {
+                    const uint32_t acc = g % NACC, use = g / NACC;
+                    mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kb = 0; kb < p.KB; kb++) {
+                        mbar_wait(b_full + st, ph);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < KBYTES / UK; k++) {
+                            const uint64_t ad = umma_desc_sw128(a_base + kb * A_SLAB + k * UK);
+                            const uint64_t bd = umma_desc_sw128(b_base + st * B_SLAB + k * UK);
+                            umma_i8(d_tmem, ad, bd, IDESC, (uint32_t)((kb | k) != 0));
+                        }
+                        tc_commit(b_empty + st);
+                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+                    }
+                    tc_commit(acc_full + acc);
+                }
+                tc_commit(a_empty);
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue: TMEM -> integer screen -> fp64 log-sum-exp =====
+        const int ew = warp - EPI_WARP0, set = ew >> 2, quarter = warp & 3;
+        const int rloc = quarter * 32 + lane;
+        int *skeys = reinterpret_cast<int *>(smem + OFF_KEYS) + ew * BN;
+        double2 *merge = reinterpret_cast<double2 *>(smem + OFF_MERGE);
+        uint32_t g0 = 0;  // tile counter at the start of the unit
+        int it = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++, g0 += (uint32_t)p.NT) {
+            const int w = p.w0 + u / p.MB, mb = u % p.MB;
+            const int row = mb * BM + rloc;
+            const bool row_ok = row < p.nrows;
+            const int own0 = row_ok ? p.row_own[row] : -1;
+            const int32_t *akw = p.akey + (size_t)w * p.ncolpad;
+            const double *rpw = p.Rp + (size_t)w * p.ncolpad;
+            int kmax = row_ok ? KEY_INIT : (1 << 30);  // padding rows never reach the fp64 path
+            double m = -INFINITY, s = 0.0;
+            for (int n = 0; n < p.NT; n++) {
+                const uint32_t g = g0 + (uint32_t)n;
+                if ((int)(g & 1u) != set) continue;
+                const uint32_t acc = g % NACC, use = g / NACC;
+                // this tile's screening keys -> this warp's shared slot
+                {
+                    const int4 kv = __ldg(reinterpret_cast<const int4 *>(akw + n * BN) + lane);
+                    __syncwarp();
+                    reinterpret_cast<int4 *>(skeys)[lane] = kv;
+                    __syncwarp();
+                }
+                // does any row of this warp exclude a column of this tile?
+                const bool own_here = own0 >= n * BN && own0 < (n + 1) * BN;
+                const bool any_own = __any_sync(0xffffffffu, own_here);
+                mbar_wait(acc_full + acc, use & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c++) {
+                    int v[32];
+                    __syncwarp();
+                    tmem_ld32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    int cm = KEY_PAD;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int4 a4 = *reinterpret_cast<const int4 *>(skeys + c * 32 + j);
+                        v[j] = a4.x - v[j];
+                        v[j + 1] = a4.y - v[j + 1];
+                        v[j + 2] = a4.z - v[j + 2];
+                        v[j + 3] = a4.w - v[j + 3];
+                    }
+                    if (any_own) {
+                        const int jo = own0 - (n * BN + c * 32);  // own columns jo, jo+1 (jo even)
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if ((j & ~1) == jo) v[j] = KEY_PAD;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) cm = max(cm, v[j]);
+                    kmax = max(kmax, cm);
+                    const int thr = kmax - p.delta;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        if (v[j] > thr) {
+                            const int col = n * BN + c * 32 + j;
+                            const int M = skeys[c * 32 + j] - v[j];
+                            const double x = fma(p.kappa, (double)M, __ldg(rpw + col));
+                            if (x > m) {
+                                s = fma(s, exp_nonpos(m - x), 1.0);
+                                m = x;
+                            } else {
+                                s += exp_nonpos(x - m);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + acc);
+            }
+            // merge the two sets' partial (max, sum) per row, then the two haplotypes of a target
+            double2 *mb_buf = merge + (it & 1) * BM;
+            if (set == 1) mb_buf[rloc] = make_double2(m, s);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (set == 0) {
+                const double2 o = mb_buf[rloc];
+                double M2 = fmax(m, o.x), S2 = 0.0;
+                if (s > 0.0) S2 += s * exp_nonpos(m - M2);
+                if (o.y > 0.0) S2 += o.y * exp_nonpos(o.x - M2);
+                double e = -INFINITY;
+                if (S2 > 0.0) e = M2 + log(S2);
+                if (row_ok) e += p.Rw[(size_t)w * p.H + p.row_hap[row]];
+                const double eo = __shfl_xor_sync(0xffffffffu, e, 1);
+                if (row_ok && (lane & 1) == 0) {
+                    const int t = row >> 1;
+                    const double lnb = p.lognb4[t];
+                    double r;
+                    if (!(lnb == lnb)) {
+                        r = __longlong_as_double(0x7ff8000000000000LL);
+                    } else {
+                        const double mm = fmax(e, eo);
+                        r = (mm == -INFINITY) ? -INFINITY : mm + log(exp_nonpos(e - mm) + exp_nonpos(eo - mm));
+                        r = (p.C0[w] + r) - lnb;
+                    }
+                    p.wll[((size_t)t * p.outW + w) * 3 + 1] = r;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+}  // namespace mma
+
+// ---------------------------------------------------------------------------------------------
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// [windows][rows][Wpad] bytes, box = 128 bytes x 128 rows, 128-byte swizzle, zero fill outside
+static int make_operand_map(CUtensorMap *m, void *base, int Wpad, int rows, int nW) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("[::] ERROR: cuTensorMapEncodeTiled is not available from the CUDA driver.");
+        return 1;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)Wpad, (cuuint64_t)rows, (cuuint64_t)nW};
+    const cuuint64_t strides[2] = {(cuuint64_t)Wpad, (cuuint64_t)Wpad * (cuuint64_t)rows};
+    const cuuint32_t box[3] = {(cuuint32_t)mma::KBYTES, (cuuint32_t)mma::BM, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("[::] ERROR: cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d operand.", (int)r, Wpad, rows, nW);
+        return 1;
+    }
+    return 0;
+}
+
+bool ld_tensor_eligible(ibdgem_engine *e, int32_t n_targets, int32_t n_bg, const uint8_t *tgt_counts) {
+    if (tgt_counts || e->prm.variable_sites_only) return false;
+    if (!e->depth_linear || !(e->kappa < -1e-3)) return false;
+    if (e->nW_shared <= 0 || e->K_shared <= 0) return false;
+    const int Wpad = (e->prm.window_size + 127) / 128 * 128;
+    if (Wpad > mma::MAXKB * mma::KBYTES) return false;
+    if ((int64_t)e->prm.max_cov * Wpad >= (1 << 24)) return false;
+    if (n_targets <= 0 || n_bg <= 0) return false;
+    if (ceil(SCREEN_NATS / -e->kappa) > 1e6) return false;
+    return true;
+}
+
+void ld_tensor_release(ibdgem_engine *e) {
+    LdCache *c = e->ld;
+    if (!c) return;
+    dev_free(e, c->d_infsite, c->b_infsite);
+    dev_free(e, c->d_nk, c->b_nk);
+    dev_free(e, c->d_d1, c->b_d1);
+    dev_free(e, c->d_l0, c->b_l0);
+    dev_free(e, c->d_C0, c->b_C0);
+    dev_free(e, c->d_tbits, c->b_tbits);
+    dev_free(e, c->d_Rw, c->b_Rw);
+    dev_free(e, c->d_Qw, c->b_Qw);
+    delete c;
+    e->ld = nullptr;
+}
+
+static int build_cache(ibdgem_engine *e) {
+    if (e->ld && e->ld->valid) return 0;
+    ld_tensor_release(e);
+    LdCache *c = new LdCache();
+    e->ld = c;
+    c->nW = e->nW_shared;
+    c->K = e->K_shared;
+    c->W = e->prm.window_size;
+    c->Wpad = (c->W + 127) / 128 * 128;
+    c->WP32 = c->Wpad / 32;
+    c->KB = c->Wpad / 128;
+    c->N = e->N;
+    c->H = 2 * e->N;
+    const size_t slots = (size_t)c->nW * c->Wpad;
+    c->b_infsite = slots * 4; c->b_nk = slots; c->b_d1 = slots * 8; c->b_l0 = slots * 8; c->b_C0 = (size_t)c->nW * 8;
+    c->b_tbits = (size_t)c->nW * c->H * c->WP32 * 4;
+    c->b_Rw = (size_t)c->nW * c->H * 8;
+    c->b_Qw = (size_t)c->nW * c->N * 8;
+    if (dev_alloc(e, (void **)&c->d_infsite, c->b_infsite) || dev_alloc(e, (void **)&c->d_nk, c->b_nk) ||
+        dev_alloc(e, (void **)&c->d_d1, c->b_d1) || dev_alloc(e, (void **)&c->d_l0, c->b_l0) ||
+        dev_alloc(e, (void **)&c->d_C0, c->b_C0) || dev_alloc(e, (void **)&c->d_tbits, c->b_tbits) ||
+        dev_alloc(e, (void **)&c->d_Rw, c->b_Rw) || dev_alloc(e, (void **)&c->d_Qw, c->b_Qw))
+        return 1;
+    IBD_CUDA(cudaMemsetAsync(c->d_infsite, 0xFF, c->b_infsite, e->stream));
+    IBD_CUDA(cudaMemsetAsync(c->d_nk, 0, c->b_nk, e->stream));
+    IBD_CUDA(cudaMemsetAsync(c->d_d1, 0, c->b_d1, e->stream));
+    IBD_CUDA(cudaMemsetAsync(c->d_l0, 0, c->b_l0, e->stream));
+    {
+        LaunchScope ls(e, K_LD_COMPACT);
+        ld_compact_kernel<<<(unsigned)((e->S + 255) / 256), 256, 0, e->stream>>>(
+            e->S, e->d_status, e->d_rank, e->d_nref, e->d_nalt, e->d_lnP, e->C, c->W, c->Wpad, c->d_infsite, c->d_nk,
+            c->d_d1, c->d_l0);
+    }
+    {
+        LaunchScope ls(e, K_LD_C0);
+        ld_c0_kernel<<<c->nW, 256, 0, e->stream>>>(c->d_l0, c->Wpad, c->d_C0);
+    }
+    {
+        LaunchScope ls(e, K_LD_TRANSPOSE);
+        const int words = (c->H + 31) / 32;
+        ld_transpose_kernel<<<dim3(c->nW, (words + 7) / 8), 1024, 0, e->stream>>>(e->d_bits, e->Wh, c->H, c->d_infsite,
+                                                                                 c->Wpad, c->WP32, c->d_tbits);
+    }
+    {
+        LaunchScope ls(e, K_LD_MARGINALS);
+        ld_marginals_kernel<<<dim3(c->nW, (c->H + 255) / 256), 256, (size_t)c->Wpad * 9, e->stream>>>(
+            c->d_tbits, c->H, c->Wpad, c->WP32, c->d_d1, c->d_nk, c->d_C0, e->kappa, c->d_Rw, c->d_Qw);
+    }
+    IBD_CUDA(cudaGetLastError());
+    c->valid = true;
+    return 0;
+}
+
+int ld_tensor_prepare(ibdgem_engine *e) { return build_cache(e); }
+
+// Fills every window output of the call: d_wll [T][outW][3], d_wn, d_ws, d_we [T][outW], d_nwout [T].
+int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const int32_t *d_targets, int32_t n_bg,
+                    const int32_t *h_bg, int32_t pu_idx, int32_t outW, double *d_wll, int32_t *d_wn, uint64_t *d_ws,
+                    uint64_t *d_we, int32_t *d_nwout) {
+    if (build_cache(e)) return 1;
+    LdCache *c = e->ld;
+    // unique background individuals with multiplicities; the pileup's own individual never
+    // contributes (src/ibdgem.c:714), duplicates become a ln(multiplicity) weight
+    std::map<int32_t, int32_t> mult;
+    for (int n = 0; n < n_bg; n++)
+        if (h_bg[n] != pu_idx) mult[h_bg[n]]++;
+    std::vector<int32_t> bgU;
+    std::vector<double> lnc;
+    std::map<int32_t, int32_t> where;
+    int64_t total_bg = 0;
+    for (auto &kv : mult) {
+        where[kv.first] = (int32_t)bgU.size();
+        bgU.push_back(kv.first);
+        lnc.push_back(log((double)kv.second));
+        total_bg += kv.second;
+    }
+    const int nU = (int)bgU.size();
+    const double nan = (double)NAN;
+    std::vector<int32_t> ownU(T), row_hap(2 * (size_t)T), row_own(2 * (size_t)T);
+    std::vector<double> lognb(T), lognb4(T);
+    for (int t = 0; t < T; t++) {
+        auto itw = where.find(h_targets[t]);
+        const int own = itw == where.end() ? -1 : itw->second;
+        const int64_t nb = total_bg - (own >= 0 ? mult[h_targets[t]] : 0);
+        ownU[t] = own;
+        lognb[t] = nb > 0 ? log((double)nb) : nan;
+        lognb4[t] = nb > 0 ? log(4.0 * (double)nb) : nan;
+        for (int i = 0; i < 2; i++) {
+            row_hap[2 * t + i] = 2 * h_targets[t] + i;
+            row_own[2 * t + i] = own >= 0 ? 2 * own : -1;
+        }
+    }
+    const int nW = c->nW;
+    {
+        LaunchScope ls(e, K_LD_WINDOWS);
+        const int64_t n = (int64_t)T * outW;
+        ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+            T, nW, outW, c->W, c->K, d_targets, c->N, e->d_wfirst, e->d_wlast, e->d_pos, c->d_Qw, d_wll, d_wn, d_ws, d_we,
+            d_nwout);
+    }
+    if (nU == 0) {  // every background member excluded: LIBD0 = LIBD1 = 0/0 (d_wll is NaN-filled)
+        IBD_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const int ncols = 2 * nU;
+    const int NT = (ncols + mma::BN - 1) / mma::BN;
+    const int ncolpad = NT * mma::BN;
+    const int nrows = 2 * T;
+    const int MB = (nrows + mma::BM - 1) / mma::BM;
+
+    const size_t per_window = (size_t)(ncols + nrows) * c->Wpad;
+    const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, LD_OPERAND_BUDGET / per_window));
+    int32_t *d_bgU, *d_ownU, *d_rowhap, *d_rowown, *d_akey;
+    double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp;
+    unsigned char *d_A, *d_B;
+    const size_t misc_i = (size_t)nU + T + 4 * (size_t)T;
+    const size_t misc_d = (size_t)nU + 2 * (size_t)T;
+    if (scratch(e, SC_MMA_MISC, misc_i * 4 + misc_d * 8 + 64, (void **)&d_lnc) ||
+        scratch(e, SC_MMA_BGIDX, (size_t)nW * ncolpad * 4, (void **)&d_akey) ||
+        scratch(e, SC_MMA_ROWLSE, (size_t)nW * ncolpad * 8 + (size_t)nW * nU * 8, (void **)&d_Rp) ||
+        scratch(e, SC_MMA_TGT, (size_t)nWb * nrows * c->Wpad, (void **)&d_A) ||
+        scratch(e, SC_MMA_BG, (size_t)nWb * ncols * c->Wpad, (void **)&d_B))
+        return 1;
+    d_lognb = d_lnc + nU;
+    d_lognb4 = d_lognb + T;
+    d_bgU = reinterpret_cast<int32_t *>(d_lognb4 + T);
+    d_ownU = d_bgU + nU;
+    d_rowhap = d_ownU + T;
+    d_rowown = d_rowhap + 2 * (size_t)T;
+    d_Qp = d_Rp + (size_t)nW * ncolpad;
+    IBD_CUDA(cudaMemcpyAsync(d_lnc, lnc.data(), (size_t)nU * 8, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_lognb, lognb.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_lognb4, lognb4.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_bgU, bgU.data(), (size_t)nU * 4, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_ownU, ownU.data(), (size_t)T * 4, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_rowhap, row_hap.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_rowown, row_own.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
+    // the host vectors above are pageable: the copies are staged before these calls return
+
+    {
+        LaunchScope ls(e, K_LD_TABLES);
+        const int64_t n = (int64_t)nW * ncolpad;
+        ld_tables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(nW, ncols, ncolpad, c->H, d_bgU, d_lnc, c->d_Rw,
+                                                                             c->d_Qw, 1.0 / -e->kappa, d_akey, d_Rp, d_Qp);
+    }
+    {
+        LaunchScope ls(e, K_LD_IBD0);
+        ld_ibd0_kernel<<<nW, 256, 0, e->stream>>>(T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll);
+    }
+    IBD_CUDA(cudaGetLastError());
+    static bool attr_set = false;
+    if (!attr_set) {
+        IBD_CUDA(cudaFuncSetAttribute(mma::ld_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mma::SMEM_BYTES));
+        attr_set = true;
+    }
+    // windows are processed in batches so the expanded int8 operands stay within a fixed budget
+    for (int w0 = 0; w0 < nW; w0 += nWb) {
+        const int nw = std::min(nWb, nW - w0);
+        {
+            LaunchScope ls(e, K_LD_EXPAND_BG);
+            const int64_t n = (int64_t)nw * ncols * c->WP32;
+            ld_expand_bg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(n, w0, ncols, c->H, c->WP32, d_bgU, c->d_tbits,
+                                                                                    reinterpret_cast<uint4 *>(d_B));
+        }
+        {
+            LaunchScope ls(e, K_LD_EXPAND_TGT);
+            const int64_t n = (int64_t)nw * nrows * c->WP32;
+            ld_expand_tgt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+                n, w0, nrows, c->H, c->Wpad, c->WP32, d_targets, c->d_tbits, c->d_nk, reinterpret_cast<uint4 *>(d_A));
+        }
+        IBD_CUDA(cudaGetLastError());
+        CUtensorMap mapA, mapB;
+        if (make_operand_map(&mapA, d_A, c->Wpad, nrows, nw) || make_operand_map(&mapB, d_B, c->Wpad, ncols, nw)) return 1;
+        mma::Params p;
+        p.w0 = w0;
+        p.nW = nw; p.MB = MB; p.NT = NT; p.KB = c->KB;
+        p.n_units = nw * MB;
+        p.nrows = nrows; p.ncolpad = ncolpad;
+        p.H = c->H; p.outW = outW;
+        p.delta = (int)ceil(SCREEN_NATS / -e->kappa) + 2;
+        p.kappa = e->kappa;
+        p.akey = d_akey; p.Rp = d_Rp; p.Rw = c->d_Rw;
+        p.row_hap = d_rowhap; p.row_own = d_rowown;
+        p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
+        {
+            LaunchScope ls(e, K_LD_MMA);
+            const int grid = std::min(p.n_units, e->sm_count);
+            mma::ld_mma_kernel<<<grid, mma::THREADS, mma::SMEM_BYTES, e->stream>>>(mapA, mapB, p);
+        }
+        IBD_CUDA(cudaGetLastError());
+    }
+    IBD_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace ibdgem
