@@ -417,14 +417,15 @@ constexpr int NSTAGE = 5;       // background ring
 constexpr int NACC = 4;         // TMEM accumulator slots (4 x 128 columns = all 512)
 constexpr int A_SLAB = BM * KBYTES;   // 16 KB
 constexpr int B_SLAB = BN * KBYTES;   // 16 KB
-constexpr int THREADS = 384;
+constexpr int NSETS = 2;        // epilogue warp sets (4 warps each), tiles dealt round-robin
+constexpr int THREADS = 128 + NSETS * 128;
 constexpr int EPI_WARP0 = 4;
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + MAXKB * A_SLAB;
-constexpr int OFF_KEYS = OFF_B + NSTAGE * B_SLAB;      // 8 warps x 128 int32
-constexpr int OFF_MERGE = OFF_KEYS + 8 * BN * 4;       // 2 x 128 x double2
-constexpr int OFF_BAR = OFF_MERGE + 2 * BM * 16;
+constexpr int OFF_KEYS = OFF_B + NSTAGE * B_SLAB;      // per epilogue warp: 128 int32
+constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * BN * 4;   // 2 x (NSETS - 1) x 128 x double2
+constexpr int OFF_BAR = OFF_MERGE + 2 * (NSETS - 1) * BM * 16;
 constexpr int NBAR = 2 + 2 * NSTAGE + 2 * NACC;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;       // + alignment slack
@@ -553,7 +554,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             double m = -INFINITY, s = 0.0;
             for (int n = 0; n < p.NT; n++) {
                 const uint32_t g = g0 + (uint32_t)n;
-                if ((int)(g & 1u) != set) continue;
+                if ((int)(g % NSETS) != set) continue;
                 const uint32_t acc = g % NACC, use = g / NACC;
                 // this tile's screening keys -> this warp's shared slot
                 {
@@ -574,7 +575,6 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                     __syncwarp();
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
-                    int cm = KEY_PAD;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const int4 a4 = *reinterpret_cast<const int4 *>(skeys + c * 32 + j);
@@ -589,16 +589,26 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         for (int j = 0; j < 32; j++)
                             if ((j & ~1) == jo) v[j] = KEY_PAD;
                     }
+                    int cm = KEY_PAD;
 #pragma unroll
                     for (int j = 0; j < 32; j++) cm = max(cm, v[j]);
                     kmax = max(kmax, cm);
                     const int thr = kmax - p.delta;
+                    uint32_t mask = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        if (v[j] > thr) {
-                            const int col = n * BN + c * 32 + j;
-                            const int M = skeys[c * 32 + j] - v[j];
-                            const double x = fma(p.kappa, (double)M, __ldg(rpw + col));
+                    for (int j = 0; j < 32; j++)
+                        if (v[j] > thr) mask |= 1u << j;
+                    // columns some row of this warp still cares about: one shared copy of the fp64
+                    // path, the element re-read from TMEM (registers cannot be indexed dynamically)
+                    uint32_t todo = __reduce_or_sync(0xffffffffu, mask);
+                    while (todo) {
+                        const int j = __ffs((int)todo) - 1;
+                        todo &= todo - 1;
+                        int M;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(M) : "r"(taddr + c * 32 + j) : "memory");
+                        tmem_ld_wait();
+                        if ((mask >> j) & 1u) {
+                            const double x = fma(p.kappa, (double)M, __ldg(rpw + n * BN + c * 32 + j));
                             if (x > m) {
                                 s = fma(s, exp_nonpos(m - x), 1.0);
                                 m = x;
@@ -606,6 +616,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                                 s += exp_nonpos(x - m);
                             }
                         }
+                        __syncwarp();
                     }
                 }
                 tc_fence_before();
@@ -613,14 +624,20 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 if (lane == 0) mbar_arrive(acc_empty + acc);
             }
             // merge the two sets' partial (max, sum) per row, then the two haplotypes of a target
-            double2 *mb_buf = merge + (it & 1) * BM;
-            if (set == 1) mb_buf[rloc] = make_double2(m, s);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            double2 *mb_buf = merge + (it & 1) * (NSETS - 1) * BM;
+            if (set > 0) mb_buf[(set - 1) * BM + rloc] = make_double2(m, s);
+            asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128) : "memory");
             if (set == 0) {
-                const double2 o = mb_buf[rloc];
-                double M2 = fmax(m, o.x), S2 = 0.0;
+                double M2 = m;
+#pragma unroll
+                for (int q = 0; q < NSETS - 1; q++) M2 = fmax(M2, mb_buf[q * BM + rloc].x);
+                double S2 = 0.0;
                 if (s > 0.0) S2 += s * exp_nonpos(m - M2);
-                if (o.y > 0.0) S2 += o.y * exp_nonpos(o.x - M2);
+#pragma unroll
+                for (int q = 0; q < NSETS - 1; q++) {
+                    const double2 o = mb_buf[q * BM + rloc];
+                    if (o.y > 0.0) S2 += o.y * exp_nonpos(o.x - M2);
+                }
                 double e = -INFINITY;
                 if (S2 > 0.0) e = M2 + log(S2);
                 if (row_ok) e += p.Rw[(size_t)w * p.H + p.row_hap[row]];
