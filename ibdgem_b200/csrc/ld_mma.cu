@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -78,11 +79,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// wait used by the many epilogue warps: backs off so the spinning does not steal issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -413,22 +442,27 @@ ld_ibd0_kernel(int T, int nU, int outW, const double *__restrict__ Qp, const int
 namespace mma {
 constexpr int BM = 128, BN = 128, KBYTES = 128, UK = 32;
 constexpr int MAXKB = 8;        // Wpad <= 1024
-constexpr int NSTAGE = 5;       // background ring
 constexpr int NACC = 4;         // TMEM accumulator slots (4 x 128 columns = all 512)
 constexpr int A_SLAB = BM * KBYTES;   // 16 KB
 constexpr int B_SLAB = BN * KBYTES;   // 16 KB
-constexpr int NSETS = 2;        // epilogue warp sets (4 warps each), tiles dealt round-robin
-constexpr int THREADS = 128 + NSETS * 128;
 constexpr int EPI_WARP0 = 4;
-// shared memory map (offsets from the 1024-aligned base)
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + MAXKB * A_SLAB;
-constexpr int OFF_KEYS = OFF_B + NSTAGE * B_SLAB;      // per epilogue warp: 128 int32
-constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * BN * 4;   // 2 x (NSETS - 1) x 128 x double2
-constexpr int OFF_BAR = OFF_MERGE + 2 * (NSETS - 1) * BM * 16;
-constexpr int NBAR = 2 + 2 * NSTAGE + 2 * NACC;
-constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;       // + alignment slack
+// NSETS epilogue warp sets (4 warps each, tiles dealt round-robin), NSTAGE-deep background ring;
+// shared memory map as offsets from the 1024-aligned base
+template <int NSETS_, int NSTAGE_>
+struct Cfg {
+    static constexpr int NSETS = NSETS_, NSTAGE = NSTAGE_;
+    static constexpr int THREADS = 128 + NSETS * 128;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = OFF_A + MAXKB * A_SLAB;
+    static constexpr int OFF_KEYS = OFF_B + NSTAGE * B_SLAB;             // per epilogue warp: 128 int32
+    static constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * BN * 4;      // 2 x (NSETS - 1) x 128 x double2
+    static constexpr int OFF_KMAX = OFF_MERGE + 2 * (NSETS - 1) * BM * 16;  // 2 x 128 int32, shared by the sets
+    static constexpr int OFF_BAR = OFF_KMAX + 2 * BM * 4;
+    static constexpr int NBAR = 2 + 2 * NSTAGE + 2 * NACC;
+    static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+    static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
+    static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
+};
 constexpr uint32_t IDESC = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (0u << 10) /* B = u8 */ |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -450,8 +484,12 @@ struct Params {
     double *wll;             // [T][outW][3]
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+template <class CF>
+__global__ void __launch_bounds__(CF::THREADS, 1)
 ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const Params p) {
+    constexpr int NSETS = CF::NSETS, NSTAGE = CF::NSTAGE;
+    constexpr int OFF_A = CF::OFF_A, OFF_B = CF::OFF_B, OFF_KEYS = CF::OFF_KEYS, OFF_MERGE = CF::OFF_MERGE;
+    constexpr int OFF_BAR = CF::OFF_BAR, OFF_TMEM = CF::OFF_TMEM, OFF_KMAX = CF::OFF_KMAX;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
@@ -473,6 +511,8 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 3)
+        for (int i = lane; i < 2 * BM; i += 32) reinterpret_cast<int *>(smem + OFF_KMAX)[i] = KEY_INIT;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -504,36 +544,39 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            int it = 0;
-            uint32_t g = 0;  // accumulator tile counter
-            const uint32_t a_base = smem_u32(smem + OFF_A), b_base = smem_u32(smem + OFF_B);
-            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++) {
-                mbar_wait(a_full, (uint32_t)(it & 1));
-                for (int n = 0; n < p.NT; n++, g++) {
-                    const uint32_t acc = g % NACC, use = g / NACC;
-                    mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
+        // ===== MMA issuer: the whole warp walks the loop convergently (so every operand stays in
+        // uniform registers); one elected lane issues the tcgen05 instructions =====
+        int st = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        uint32_t g = 0;  // accumulator tile counter
+        const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + OFF_A));
+        const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem + OFF_B));
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++) {
+            mbar_wait(a_full, (uint32_t)(it & 1));
+            for (int n = 0; n < p.NT; n++, g++) {
+                const uint32_t acc = g % NACC, use = g / NACC;
+                mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < p.KB; kb++) {
+                    mbar_wait(b_full + st, ph);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * BN;
-                    for (int kb = 0; kb < p.KB; kb++) {
-                        mbar_wait(b_full + st, ph);
-                        tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad = adesc0 + (uint64_t)((kb * A_SLAB) >> 4);
+                        const uint64_t bd = bdesc0 + (uint64_t)((st * B_SLAB) >> 4);
 #pragma unroll
-                        for (int k = 0; k < KBYTES / UK; k++) {
-                            const uint64_t ad = umma_desc_sw128(a_base + kb * A_SLAB + k * UK);
-                            const uint64_t bd = umma_desc_sw128(b_base + st * B_SLAB + k * UK);
-                            umma_i8(d_tmem, ad, bd, IDESC, (uint32_t)((kb | k) != 0));
-                        }
+                        for (int k = 0; k < KBYTES / UK; k++)
+                            umma_i8(d_tmem, ad + (uint64_t)(k * (UK >> 4)), bd + (uint64_t)(k * (UK >> 4)), IDESC,
+                                    (uint32_t)((kb | k) != 0));
                         tc_commit(b_empty + st);
-                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+                        if (kb == p.KB - 1) tc_commit(acc_full + acc);
                     }
-                    tc_commit(acc_full + acc);
+                    __syncwarp();
+                    if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                 }
-                tc_commit(a_empty);
             }
+            if (elect_one()) tc_commit(a_empty);
+            __syncwarp();
         }
     } else if (warp >= EPI_WARP0) {
         // ===== epilogue: TMEM -> integer screen -> fp64 log-sum-exp =====
@@ -541,6 +584,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         const int rloc = quarter * 32 + lane;
         int *skeys = reinterpret_cast<int *>(smem + OFF_KEYS) + ew * BN;
         double2 *merge = reinterpret_cast<double2 *>(smem + OFF_MERGE);
+        int *skmax_all = reinterpret_cast<int *>(smem + OFF_KMAX);
         uint32_t g0 = 0;  // tile counter at the start of the unit
         int it = 0;
         for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++, g0 += (uint32_t)p.NT) {
@@ -551,6 +595,9 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             const int32_t *akw = p.akey + (size_t)w * p.ncolpad;
             const double *rpw = p.Rp + (size_t)w * p.ncolpad;
             int kmax = row_ok ? KEY_INIT : (1 << 30);  // padding rows never reach the fp64 path
+            // the sets see disjoint tiles: they share the row's running maximum key through shared
+            // memory (monotone, so a stale read only lets more elements through the screen)
+            int *skmax = skmax_all + (it & 1) * BM + rloc;
             double m = -INFINITY, s = 0.0;
             for (int n = 0; n < p.NT; n++) {
                 const uint32_t g = g0 + (uint32_t)n;
@@ -566,7 +613,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 // does any row of this warp exclude a column of this tile?
                 const bool own_here = own0 >= n * BN && own0 < (n + 1) * BN;
                 const bool any_own = __any_sync(0xffffffffu, own_here);
-                mbar_wait(acc_full + acc, use & 1u);
+                mbar_wait_relaxed(acc_full + acc, use & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
@@ -592,7 +639,11 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                     int cm = KEY_PAD;
 #pragma unroll
                     for (int j = 0; j < 32; j++) cm = max(cm, v[j]);
-                    kmax = max(kmax, cm);
+                    kmax = max(kmax, *skmax);
+                    if (cm > kmax) {
+                        kmax = cm;
+                        if (row_ok) atomicMax(skmax, cm);
+                    }
                     const int thr = kmax - p.delta;
                     uint32_t mask = 0;
 #pragma unroll
@@ -624,6 +675,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 if (lane == 0) mbar_arrive(acc_empty + acc);
             }
             // merge the two sets' partial (max, sum) per row, then the two haplotypes of a target
+            if (set == 0) skmax_all[((it + 1) & 1) * BM + rloc] = KEY_INIT;  // next unit's slot (idle since unit it - 1)
             double2 *mb_buf = merge + (it & 1) * (NSETS - 1) * BM;
             if (set > 0) mb_buf[(set - 1) * BM + rloc] = make_double2(m, s);
             asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128) : "memory");
@@ -702,6 +754,41 @@ static int make_operand_map(CUtensorMap *m, void *base, int Wpad, int rows, int 
         return 1;
     }
     return 0;
+}
+
+template <class CF>
+static int launch_mma_cfg(int grid, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b, const mma::Params &p) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        IBD_CUDA(cudaFuncSetAttribute(mma::ld_mma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
+        attr_set = true;
+    }
+    mma::ld_mma_kernel<CF><<<grid, CF::THREADS, CF::SMEM_BYTES, st>>>(a, b, p);
+    return 0;
+}
+// tuning variants (IBDGEM_MMA_VARIANT): 0 = 4 epilogue sets / 4 stages (default), 1 = 2 sets / 5 stages
+static int mma_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *s = getenv("IBDGEM_MMA_VARIANT");
+        v = s ? atoi(s) : 0;
+    }
+    return v;
+}
+static int launch_mma(int variant, int grid, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b, const mma::Params &p) {
+    switch (variant) {
+        case 1: return launch_mma_cfg<mma::Cfg<2, 5>>(grid, st, a, b, p);
+        default: return launch_mma_cfg<mma::Cfg<4, 4>>(grid, st, a, b, p);
+    }
+}
+static double screen_nats() {
+    static double v = -1;
+    if (v < 0) {
+        const char *s = getenv("IBDGEM_SCREEN_NATS");
+        v = s ? atof(s) : SCREEN_NATS;
+        if (!(v >= 8.0 && v <= 700.0)) v = SCREEN_NATS;
+    }
+    return v;
 }
 
 bool ld_tensor_eligible(ibdgem_engine *e, int32_t n_targets, int32_t n_bg, const uint8_t *tgt_counts) {
@@ -881,11 +968,6 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         ld_ibd0_kernel<<<nW, 256, 0, e->stream>>>(T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll);
     }
     IBD_CUDA(cudaGetLastError());
-    static bool attr_set = false;
-    if (!attr_set) {
-        IBD_CUDA(cudaFuncSetAttribute(mma::ld_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mma::SMEM_BYTES));
-        attr_set = true;
-    }
     // windows are processed in batches so the expanded int8 operands stay within a fixed budget
     for (int w0 = 0; w0 < nW; w0 += nWb) {
         const int nw = std::min(nWb, nW - w0);
@@ -910,7 +992,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.n_units = nw * MB;
         p.nrows = nrows; p.ncolpad = ncolpad;
         p.H = c->H; p.outW = outW;
-        p.delta = (int)ceil(SCREEN_NATS / -e->kappa) + 2;
+        p.delta = (int)ceil(screen_nats() / -e->kappa) + 2;
         p.kappa = e->kappa;
         p.akey = d_akey; p.Rp = d_Rp; p.Rw = c->d_Rw;
         p.row_hap = d_rowhap; p.row_own = d_rowown;
@@ -918,7 +1000,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         {
             LaunchScope ls(e, K_LD_MMA);
             const int grid = std::min(p.n_units, e->sm_count);
-            mma::ld_mma_kernel<<<grid, mma::THREADS, mma::SMEM_BYTES, e->stream>>>(mapA, mapB, p);
+            if (launch_mma(mma_variant(), grid, e->stream, mapA, mapB, p)) return 1;
         }
         IBD_CUDA(cudaGetLastError());
     }
