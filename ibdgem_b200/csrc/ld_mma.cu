@@ -79,6 +79,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// non-blocking probe: lets the issue loop overlap the latency of several barrier tests
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 // wait used by the many epilogue warps: backs off so the spinning does not steal issue slots
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -441,16 +455,21 @@ ld_ibd0_kernel(int T, int nU, int outW, const double *__restrict__ Qp, const int
 //   haplotype row, so the reduction over background columns needs no cross-thread traffic.
 namespace mma {
 constexpr int BM = 128, BN = 128, KBYTES = 128, UK = 32;
-constexpr int MAXKB = 8;        // Wpad <= 1024
-constexpr int NACC = 4;         // TMEM accumulator slots (4 x 128 columns = all 512)
+constexpr int MAXKB = 8;              // Wpad <= 1024
 constexpr int A_SLAB = BM * KBYTES;   // 16 KB
 constexpr int B_SLAB = BN * KBYTES;   // 16 KB
 constexpr int EPI_WARP0 = 4;
-// NSETS epilogue warp sets (4 warps each, tiles dealt round-robin), NSTAGE-deep background ring;
-// shared memory map as offsets from the 1024-aligned base
-template <int NSETS_, int NSTAGE_>
+constexpr int NSETS = 4;              // epilogue warp sets of 4 warps (one warp per TMEM lane quarter)
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+
+// CG = CTAs per MMA (tcgen05 cta_group).  CG = 2 pairs two SMs on one 256 x 256 tile: each CTA keeps
+// its own 128 target rows resident and streams HALF of every background tile, which halves the
+// shared-memory traffic per MMA — the resource ncu showed saturated with CG = 1.
+template <int CG_, int NSTAGE_>
 struct Cfg {
-    static constexpr int NSETS = NSETS_, NSTAGE = NSTAGE_;
+    static constexpr int CG = CG_, NSTAGE = NSTAGE_;
+    static constexpr int TILE_N = BN * CG;          // accumulator tile columns
+    static constexpr int NACC = 512 / TILE_N;       // TMEM accumulator slots
     static constexpr int THREADS = 128 + NSETS * 128;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + MAXKB * A_SLAB;
@@ -461,16 +480,17 @@ struct Cfg {
     static constexpr int NBAR = 2 + 2 * NSTAGE + 2 * NACC;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
+    static constexpr uint32_t IDESC = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (0u << 10) /* B = u8 */ |
+                                      ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
+    static_assert(NSETS == NACC * CG, "one epilogue set per (accumulator slot, 128-column group)");
 };
-constexpr uint32_t IDESC = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (0u << 10) /* B = u8 */ |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 struct Params {
     int w0;                  // first window of this batch (operands hold windows w0 .. w0 + nW - 1)
-    int nW, MB, NT, KB;      // windows, row blocks per window, column tiles, 128-byte k blocks
+    int nW, MB, NT, KB;      // windows, row blocks (of 128 * CG) per window, column tiles (of 128 * CG), 128-byte k blocks
     int n_units;
-    int nrows, ncolpad;      // 2T, NT * 128
+    int nrows, ncolpad;      // 2T, padded column count of the key tables
     int H, outW;
     int delta;               // screening distance in key units
     double kappa;
@@ -484,10 +504,62 @@ struct Params {
     double *wll;             // [T][outW][3]
 };
 
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_cg(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    if constexpr (CG == 1) {
+        tma_load_3d(dst, map, bar, c0, c1, c2);
+    } else {  // executed by both CTAs of the pair; the bytes are counted on CTA 0's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                smem_u32(dst)),
+            "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tc_commit_cg(uint64_t *bar) {
+    if constexpr (CG == 1) {
+        tc_commit(bar);
+    } else {  // arrives on the barrier at this offset in BOTH CTAs once the pair's MMAs retire
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void umma_i8_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        umma_i8(tmem_d, adesc, bdesc, idesc, accumulate);
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// arrive on CTA 0's copy of a barrier (CTA 0 itself: a plain local arrive)
+template <int CG>
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+    if constexpr (CG == 1) {
+        mbar_arrive(bar);
+    } else {
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+    }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 template <class CF>
 __global__ void __launch_bounds__(CF::THREADS, 1)
 ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const Params p) {
-    constexpr int NSETS = CF::NSETS, NSTAGE = CF::NSTAGE;
+    constexpr int CG = CF::CG, NSTAGE = CF::NSTAGE, NACC = CF::NACC, TILE_N = CF::TILE_N;
     constexpr int OFF_A = CF::OFF_A, OFF_B = CF::OFF_B, OFF_KEYS = CF::OFF_KEYS, OFF_MERGE = CF::OFF_MERGE;
     constexpr int OFF_BAR = CF::OFF_BAR, OFF_TMEM = CF::OFF_TMEM, OFF_KMAX = CF::OFF_KMAX;
     extern __shared__ unsigned char smem_raw[];
@@ -499,6 +571,9 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank = 0;  // CTA rank in the pair; rank 0 issues the MMAs
+    if constexpr (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int group0 = (int)(blockIdx.x / CG), ngroups = (int)(gridDim.x / CG);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
@@ -508,114 +583,143 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < NSTAGE; i++) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * CG * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3)
         for (int i = lane; i < 2 * BM; i += 32) reinterpret_cast<int *>(smem + OFF_KMAX)[i] = KEY_INIT;
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // peer barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (both CTAs of a pair: own A rows, own half of every background tile) =====
         if (lane == 0) {
             int st = 0;
             uint32_t ph = 0;
             int it = 0;
-            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++) {
+            for (int u = group0; u < p.n_units; u += ngroups, it++) {
                 const int w = u / p.MB, mb = u % p.MB;
                 mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
-                mbar_expect_tx(a_full, (uint32_t)(p.KB * A_SLAB));
+                if (rank == 0) mbar_expect_tx(a_full, (uint32_t)(CG * p.KB * A_SLAB));
                 for (int kb = 0; kb < p.KB; kb++)
-                    tma_load_3d(smem + OFF_A + kb * A_SLAB, &tmapA, a_full, kb * KBYTES, mb * BM, w);
+                    tma_load_3d_cg<CG>(smem + OFF_A + kb * A_SLAB, &tmapA, a_full, kb * KBYTES, (mb * CG + (int)rank) * BM, w);
                 for (int n = 0; n < p.NT; n++)
                     for (int kb = 0; kb < p.KB; kb++) {
                         mbar_wait(b_empty + st, ph ^ 1u);
-                        mbar_expect_tx(b_full + st, (uint32_t)B_SLAB);
-                        tma_load_3d(smem + OFF_B + st * B_SLAB, &tmapB, b_full + st, kb * KBYTES, n * BN, w);
+                        if (rank == 0) mbar_expect_tx(b_full + st, (uint32_t)(CG * B_SLAB));
+                        tma_load_3d_cg<CG>(smem + OFF_B + st * B_SLAB, &tmapB, b_full + st, kb * KBYTES,
+                                           (n * CG + (int)rank) * BN, w);
                         if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                     }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp walks the loop convergently (so every operand stays in
-        // uniform registers); one elected lane issues the tcgen05 instructions =====
-        int st = 0;
-        uint32_t ph = 0;
-        int it = 0;
-        uint32_t g = 0;  // accumulator tile counter
-        const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + OFF_A));
-        const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem + OFF_B));
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++) {
-            mbar_wait(a_full, (uint32_t)(it & 1));
-            for (int n = 0; n < p.NT; n++, g++) {
-                const uint32_t acc = g % NACC, use = g / NACC;
-                mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < p.KB; kb++) {
-                    mbar_wait(b_full + st, ph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t ad = adesc0 + (uint64_t)((kb * A_SLAB) >> 4);
-                        const uint64_t bd = bdesc0 + (uint64_t)((st * B_SLAB) >> 4);
+        // ===== MMA issuer (CTA 0 of the pair): the whole warp walks the loop convergently so every
+        // operand stays in uniform registers; one elected lane issues the tcgen05 instructions =====
+        if (rank == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            uint32_t g = 0;  // accumulator tile counter
+            const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + OFF_A));
+            const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem + OFF_B));
+            for (int u = group0; u < p.n_units; u += ngroups, it++) {
+                mbar_wait(a_full, (uint32_t)(it & 1));
+                for (int n = 0; n < p.NT; n++, g++) {
+                    const uint32_t acc = g % NACC, use = g / NACC;
+                    mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
+                    const uint32_t d_tmem = tmem_base + acc * TILE_N;
+                    // two k-blocks per trip: both barrier probes are in flight together
+                    for (int kb = 0; kb < p.KB; kb += 2) {
+                        const bool two = kb + 1 < p.KB;
+                        int st2 = st + 1;
+                        uint32_t ph2 = ph;
+                        if (st2 == NSTAGE) { st2 = 0; ph2 ^= 1u; }
+                        const bool r1 = mbar_test(b_full + st, ph);
+                        const bool r2 = two ? mbar_test(b_full + st2, ph2) : true;
+                        if (!r1) mbar_wait(b_full + st, ph);
+                        if (!r2) mbar_wait(b_full + st2, ph2);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t ad = adesc0 + (uint64_t)((kb * A_SLAB) >> 4);
+                            const uint64_t bd = bdesc0 + (uint64_t)((st * B_SLAB) >> 4);
 #pragma unroll
-                        for (int k = 0; k < KBYTES / UK; k++)
-                            umma_i8(d_tmem, ad + (uint64_t)(k * (UK >> 4)), bd + (uint64_t)(k * (UK >> 4)), IDESC,
-                                    (uint32_t)((kb | k) != 0));
-                        tc_commit(b_empty + st);
-                        if (kb == p.KB - 1) tc_commit(acc_full + acc);
+                            for (int k = 0; k < KBYTES / UK; k++)
+                                umma_i8_cg<CG>(d_tmem, ad + (uint64_t)(k * (UK >> 4)), bd + (uint64_t)(k * (UK >> 4)), CF::IDESC,
+                                               (uint32_t)((kb | k) != 0));
+                            tc_commit_cg<CG>(b_empty + st);
+                            if (two) {
+                                const uint64_t ad2 = ad + (uint64_t)(A_SLAB >> 4);
+                                const uint64_t bd2 = bdesc0 + (uint64_t)((st2 * B_SLAB) >> 4);
+#pragma unroll
+                                for (int k = 0; k < KBYTES / UK; k++)
+                                    umma_i8_cg<CG>(d_tmem, ad2 + (uint64_t)(k * (UK >> 4)), bd2 + (uint64_t)(k * (UK >> 4)), CF::IDESC, 1u);
+                                tc_commit_cg<CG>(b_empty + st2);
+                            }
+                            if (kb + 2 >= p.KB) tc_commit_cg<CG>(acc_full + acc);
+                        }
+                        __syncwarp();
+                        if (two) { st = st2; ph = ph2; }
+                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                 }
+                if (elect_one()) tc_commit_cg<CG>(a_empty);
+                __syncwarp();
             }
-            if (elect_one()) tc_commit(a_empty);
-            __syncwarp();
         }
     } else if (warp >= EPI_WARP0) {
         // ===== epilogue: TMEM -> integer screen -> fp64 log-sum-exp =====
+        // set -> (accumulator slot, 128-column group of the tile); each thread owns one target row
         const int ew = warp - EPI_WARP0, set = ew >> 2, quarter = warp & 3;
+        const int slot = set % NACC, cgroup = set / NACC;
         const int rloc = quarter * 32 + lane;
         int *skeys = reinterpret_cast<int *>(smem + OFF_KEYS) + ew * BN;
         double2 *merge = reinterpret_cast<double2 *>(smem + OFF_MERGE);
         int *skmax_all = reinterpret_cast<int *>(smem + OFF_KMAX);
         uint32_t g0 = 0;  // tile counter at the start of the unit
         int it = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it++, g0 += (uint32_t)p.NT) {
+        for (int u = group0; u < p.n_units; u += ngroups, it++, g0 += (uint32_t)p.NT) {
             const int w = p.w0 + u / p.MB, mb = u % p.MB;
-            const int row = mb * BM + rloc;
+            const int row = (mb * CG + (int)rank) * BM + rloc;
             const bool row_ok = row < p.nrows;
             const int own0 = row_ok ? p.row_own[row] : -1;
             const int32_t *akw = p.akey + (size_t)w * p.ncolpad;
             const double *rpw = p.Rp + (size_t)w * p.ncolpad;
             int kmax = row_ok ? KEY_INIT : (1 << 30);  // padding rows never reach the fp64 path
-            // the sets see disjoint tiles: they share the row's running maximum key through shared
+            // the sets see disjoint columns: they share the row's running maximum key through shared
             // memory (monotone, so a stale read only lets more elements through the screen)
             int *skmax = skmax_all + (it & 1) * BM + rloc;
             double m = -INFINITY, s = 0.0;
             for (int n = 0; n < p.NT; n++) {
                 const uint32_t g = g0 + (uint32_t)n;
-                if ((int)(g % NSETS) != set) continue;
-                const uint32_t acc = g % NACC, use = g / NACC;
+                if ((int)(g % NACC) != slot) continue;
+                const uint32_t use = g / NACC;
+                const int col0 = n * TILE_N + cgroup * BN;  // first column this warp handles
                 // this tile's screening keys -> this warp's shared slot
                 {
-                    const int4 kv = __ldg(reinterpret_cast<const int4 *>(akw + n * BN) + lane);
+                    const int4 kv = __ldg(reinterpret_cast<const int4 *>(akw + col0) + lane);
                     __syncwarp();
                     reinterpret_cast<int4 *>(skeys)[lane] = kv;
                     __syncwarp();
                 }
                 // does any row of this warp exclude a column of this tile?
-                const bool own_here = own0 >= n * BN && own0 < (n + 1) * BN;
+                const bool own_here = own0 >= col0 && own0 < col0 + BN;
                 const bool any_own = __any_sync(0xffffffffu, own_here);
-                mbar_wait_relaxed(acc_full + acc, use & 1u);
+                mbar_wait_relaxed(acc_full + slot, use & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+                const uint32_t taddr = tmem_base + slot * TILE_N + cgroup * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; c++) {
                     int v[32];
@@ -631,7 +735,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         v[j + 3] = a4.w - v[j + 3];
                     }
                     if (any_own) {
-                        const int jo = own0 - (n * BN + c * 32);  // own columns jo, jo+1 (jo even)
+                        const int jo = own0 - (col0 + c * 32);  // own columns jo, jo+1 (jo even)
 #pragma unroll
                         for (int j = 0; j < 32; j++)
                             if ((j & ~1) == jo) v[j] = KEY_PAD;
@@ -659,7 +763,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(M) : "r"(taddr + c * 32 + j) : "memory");
                         tmem_ld_wait();
                         if ((mask >> j) & 1u) {
-                            const double x = fma(p.kappa, (double)M, __ldg(rpw + n * BN + c * 32 + j));
+                            const double x = fma(p.kappa, (double)M, __ldg(rpw + col0 + c * 32 + j));
                             if (x > m) {
                                 s = fma(s, exp_nonpos(m - x), 1.0);
                                 m = x;
@@ -672,9 +776,9 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty + acc);
+                if (lane == 0) mbar_arrive_leader<CG>(acc_empty + slot);
             }
-            // merge the two sets' partial (max, sum) per row, then the two haplotypes of a target
+            // merge the sets' partial (max, sum) per row, then the two haplotypes of a target
             if (set == 0) skmax_all[((it + 1) & 1) * BM + rloc] = KEY_INIT;  // next unit's slot (idle since unit it - 1)
             double2 *mb_buf = merge + (it & 1) * (NSETS - 1) * BM;
             if (set > 0) mb_buf[(set - 1) * BM + rloc] = make_double2(m, s);
@@ -713,9 +817,13 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all();  // the peer's shared memory and barriers stay alive until both are done
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if constexpr (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 }  // namespace mma
@@ -757,16 +865,30 @@ static int make_operand_map(CUtensorMap *m, void *base, int Wpad, int rows, int 
 }
 
 template <class CF>
-static int launch_mma_cfg(int grid, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b, const mma::Params &p) {
+static int launch_mma_cfg(int n_units, int sm_count, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b,
+                          const mma::Params &p) {
     static bool attr_set = false;
     if (!attr_set) {
         IBD_CUDA(cudaFuncSetAttribute(mma::ld_mma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
         attr_set = true;
     }
-    mma::ld_mma_kernel<CF><<<grid, CF::THREADS, CF::SMEM_BYTES, st>>>(a, b, p);
+    const int groups = std::max(1, std::min(n_units, sm_count / CF::CG));  // persistent: one CTA (pair) per SM (pair)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(groups * CF::CG));
+    cfg.blockDim = dim3((unsigned)CF::THREADS);
+    cfg.dynamicSmemBytes = CF::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CF::CG;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    IBD_CUDA(cudaLaunchKernelEx(&cfg, mma::ld_mma_kernel<CF>, a, b, p));
     return 0;
 }
-// tuning variants (IBDGEM_MMA_VARIANT): 0 = 4 epilogue sets / 4 stages (default), 1 = 2 sets / 5 stages
+// IBDGEM_MMA_VARIANT: 0 = CTA pairs (cta_group::2, 256 x 256 tiles; default), 1 = single CTA (128 x 128 tiles)
 static int mma_variant() {
     static int v = -1;
     if (v < 0) {
@@ -775,10 +897,12 @@ static int mma_variant() {
     }
     return v;
 }
-static int launch_mma(int variant, int grid, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b, const mma::Params &p) {
+static int mma_cg(int variant) { return variant == 1 ? 1 : 2; }
+static int launch_mma(int variant, int n_units, int sm_count, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b,
+                      const mma::Params &p) {
     switch (variant) {
-        case 1: return launch_mma_cfg<mma::Cfg<2, 5>>(grid, st, a, b, p);
-        default: return launch_mma_cfg<mma::Cfg<4, 4>>(grid, st, a, b, p);
+        case 1: return launch_mma_cfg<mma::Cfg<1, 4>>(n_units, sm_count, st, a, b, p);
+        default: return launch_mma_cfg<mma::Cfg<2, 4>>(n_units, sm_count, st, a, b, p);
     }
 }
 static double screen_nats() {
@@ -923,10 +1047,12 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         return 0;
     }
     const int ncols = 2 * nU;
-    const int NT = (ncols + mma::BN - 1) / mma::BN;
-    const int ncolpad = NT * mma::BN;
+    const int variant = mma_variant();
+    const int CG = mma_cg(variant);
+    const int NT = (ncols + mma::BN * CG - 1) / (mma::BN * CG);
+    const int ncolpad = NT * mma::BN * CG;
     const int nrows = 2 * T;
-    const int MB = (nrows + mma::BM - 1) / mma::BM;
+    const int MB = (nrows + mma::BM * CG - 1) / (mma::BM * CG);
 
     const size_t per_window = (size_t)(ncols + nrows) * c->Wpad;
     const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, LD_OPERAND_BUDGET / per_window));
@@ -999,8 +1125,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
         {
             LaunchScope ls(e, K_LD_MMA);
-            const int grid = std::min(p.n_units, e->sm_count);
-            if (launch_mma(mma_variant(), grid, e->stream, mapA, mapB, p)) return 1;
+            if (launch_mma(variant, p.n_units, e->sm_count, e->stream, mapA, mapB, p)) return 1;
         }
         IBD_CUDA(cudaGetLastError());
     }
