@@ -269,6 +269,11 @@ def main():
         eng.upload_panel(bits, N)
 
     def score():
+        # one step = the whole path from the packed inputs resident in HBM: allele-frequency popcount
+        # + per-site table + window map (prepare), the cached window operands, then --LD scoring.
+        # invalidate() discards every derived device array of the previous step (nothing is cached
+        # across steps except the allocations).
+        eng.invalidate()
         eng.score_ld_raw(targets, bg, -1, cs)
         if world > 1:
             dist.all_gather_into_tensor(d_all.view(-1), d_ll.view(-1))

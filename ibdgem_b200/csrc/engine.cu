@@ -833,7 +833,7 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
                              e->stream));
     e->have_panel = true;
     e->prepared = false;
-    ld_tensor_release(e);
+    ld_tensor_invalidate(e);
     return 0;
 }
 
@@ -913,8 +913,15 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     e->nW_shared = nwin;
     e->K_shared = ktot;
     e->prepared = true;
-    ld_tensor_release(e);
+    ld_tensor_invalidate(e);
     resolve_timers(e);
+    return 0;
+}
+
+int ibdgem_engine_invalidate(ibdgem_engine *e) {
+    if (!e) return 1;
+    e->prepared = false;
+    ld_tensor_invalidate(e);
     return 0;
 }
 

@@ -151,5 +151,6 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
                     const int32_t *h_bg, int32_t pu_idx, int32_t outW, double *d_wll /*[T][outW][3]*/, int32_t *d_wn,
                     uint64_t *d_ws, uint64_t *d_we, int32_t *d_nwout);
 void ld_tensor_release(ibdgem_engine *e);
+void ld_tensor_invalidate(ibdgem_engine *e);
 
 }  // namespace ibdgem

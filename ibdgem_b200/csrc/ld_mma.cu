@@ -465,17 +465,21 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a sha
 // CG = CTAs per MMA (tcgen05 cta_group).  CG = 2 pairs two SMs on one 256 x 256 tile: each CTA keeps
 // its own 128 target rows resident and streams HALF of every background tile, which halves the
 // shared-memory traffic per MMA — the resource ncu showed saturated with CG = 1.
-template <int CG_, int NSTAGE_>
+template <int CG_, int NSTAGE_, bool EXPAND_>
 struct Cfg {
     static constexpr int CG = CG_, NSTAGE = NSTAGE_;
+    // EXPAND: the background operand is never materialised in HBM; four expander warps turn the
+    // bit-packed haplotype rows into the swizzled int8 stage layout in shared memory
+    static constexpr bool EXPAND = EXPAND_;
+    static constexpr int EXP_WARP0 = EPI_WARP0 + NSETS * 4;
     static constexpr int TILE_N = BN * CG;          // accumulator tile columns
     static constexpr int NACC = 512 / TILE_N;       // TMEM accumulator slots
-    static constexpr int THREADS = 128 + NSETS * 128;
+    static constexpr int THREADS = 128 + NSETS * 128 + (EXPAND ? 128 : 0);
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + MAXKB * A_SLAB;
     static constexpr int OFF_KEYS = OFF_B + NSTAGE * B_SLAB;             // per epilogue warp: 128 int32
-    static constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * BN * 4;      // 2 x (NSETS - 1) x 128 x double2
-    static constexpr int OFF_KMAX = OFF_MERGE + 2 * (NSETS - 1) * BM * 16;  // 2 x 128 int32, shared by the sets
+    static constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * BN * 4;      // (NSETS - 1) x 128 x double2
+    static constexpr int OFF_KMAX = OFF_MERGE + (NSETS - 1) * BM * 16;   // 2 x 128 int32, shared by the sets
     static constexpr int OFF_BAR = OFF_KMAX + 2 * BM * 4;
     static constexpr int NBAR = 2 + 2 * NSTAGE + 2 * NACC;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
@@ -502,6 +506,9 @@ struct Params {
     const double *C0;        // [nW]
     const double *lognb4;    // [T] ln(4 n_refpanel) or NaN
     double *wll;             // [T][outW][3]
+    const uint32_t *tbits;   // [windows][H][WP32] haplotype-major bits (EXPAND)
+    const int32_t *colhap;   // [ncolpad] panel haplotype of each background column, -1 = padding (EXPAND)
+    int WP32;
 };
 
 template <int CG>
@@ -516,6 +523,10 @@ __device__ __forceinline__ void tma_load_3d_cg(void *dst, const CUtensorMap *map
             : "memory");
     }
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+constexpr int PF_TILES = 2;
 template <int CG>
 __device__ __forceinline__ void tc_commit_cg(uint64_t *bar) {
     if constexpr (CG == 1) {
@@ -582,7 +593,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     if (warp == 1 && lane == 0) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int i = 0; i < NSTAGE; i++) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(b_full + i, CF::EXPAND ? 4 * CG : 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * CG * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -603,6 +614,11 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register budget per role (EXPAND runs 24 warps, 80 registers each at launch = the CTA's whole
+    // pool): control 32 + expander 64 release exactly what the four epilogue warpgroups claim (96).
+    // Each role branch starts with its setmaxnreg so ptxas allocates per region.
+    if (warp < EPI_WARP0) {
+    if constexpr (CF::EXPAND) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
         // ===== TMA producer (both CTAs of a pair: own A rows, own half of every background tile) =====
         if (lane == 0) {
@@ -615,8 +631,11 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 if (rank == 0) mbar_expect_tx(a_full, (uint32_t)(CG * p.KB * A_SLAB));
                 for (int kb = 0; kb < p.KB; kb++)
                     tma_load_3d_cg<CG>(smem + OFF_A + kb * A_SLAB, &tmapA, a_full, kb * KBYTES, (mb * CG + (int)rank) * BM, w);
+                if constexpr (!CF::EXPAND)
                 for (int n = 0; n < p.NT; n++)
                     for (int kb = 0; kb < p.KB; kb++) {
+                        if (n + PF_TILES < p.NT)  // pull the same k-block of a later tile into L2
+                            tma_prefetch_3d(&tmapB, kb * KBYTES, ((n + PF_TILES) * CG + (int)rank) * BN, w);
                         mbar_wait(b_empty + st, ph ^ 1u);
                         if (rank == 0) mbar_expect_tx(b_full + st, (uint32_t)(CG * B_SLAB));
                         tma_load_3d_cg<CG>(smem + OFF_B + st * B_SLAB, &tmapB, b_full + st, kb * KBYTES,
@@ -679,7 +698,68 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 __syncwarp();
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    }
+    } else if (CF::EXPAND && warp >= CF::EXP_WARP0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // ===== expander: bit-packed background rows -> 0/1 bytes in the 128-byte-swizzled K-major
+        // stage layout the MMA reads.  One thread per background column of the stage; the row's
+        // window bits (16 bytes per k-block) are fetched one tile ahead and held in registers. =====
+        const int t = (int)threadIdx.x - CF::EXP_WARP0 * 32;  // column within this CTA's half tile
+        unsigned char *srow = smem + OFF_B + (t >> 3) * 1024 + (t & 7) * 128;
+        const uint32_t sw = (uint32_t)(t & 7);
+        int st = 0;
+        uint32_t ph = 0;
+        uint4 cur[MAXKB];
+        // window bits of this thread's column for tile (w, n); a consumed k-block is at once
+        // refilled with the same k-block of the NEXT tile, so loads run a full tile ahead
+        auto row_ptr = [&](int w, int n) -> const uint4 * {
+            const int hap = __ldg(p.colhap + (n * CG + (int)rank) * BN + t);
+            return hap < 0 ? nullptr
+                           : reinterpret_cast<const uint4 *>(p.tbits + ((size_t)(p.w0 + w) * p.H + hap) * p.WP32);
+        };
+        if (group0 < p.n_units) {
+            const uint4 *src = row_ptr(group0 / p.MB, 0);
+#pragma unroll
+            for (int kb = 0; kb < MAXKB; kb++) {
+                cur[kb] = make_uint4(0u, 0u, 0u, 0u);
+                if (kb < p.KB && src) cur[kb] = __ldg(src + kb);
+            }
+        }
+        for (int u = group0; u < p.n_units; u += ngroups) {
+            const int w = u / p.MB;
+            for (int n = 0; n < p.NT; n++) {
+                // next tile of this CTA: same window, or the first tile of its next unit
+                int w2 = w, n2 = n + 1;
+                if (n2 == p.NT) { n2 = 0; w2 = (u + ngroups < p.n_units) ? (u + ngroups) / p.MB : -1; }
+                const uint4 *nsrc = w2 >= 0 ? row_ptr(w2, n2) : nullptr;
+#pragma unroll
+                for (int kb = 0; kb < MAXKB; kb++) {
+                    if (kb < p.KB) {
+                        mbar_wait(b_empty + st, ph ^ 1u);
+                        unsigned char *dst = srow + st * B_SLAB;
+                        const uint32_t wd[4] = {cur[kb].x, cur[kb].y, cur[kb].z, cur[kb].w};
+                        cur[kb] = make_uint4(0u, 0u, 0u, 0u);
+                        if (nsrc) cur[kb] = __ldg(nsrc + kb);
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {  // 16 sites -> one 16-byte chunk
+                            const uint32_t hw = (wd[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+                            uint4 o;
+                            o.x = spread4(hw & 15u);
+                            o.y = spread4((hw >> 4) & 15u);
+                            o.z = spread4((hw >> 8) & 15u);
+                            o.w = spread4(hw >> 12);
+                            *reinterpret_cast<uint4 *>(dst + (((uint32_t)c ^ sw) << 4)) = o;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader<CG>(b_full + st);
+                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else {
+        if constexpr (CF::EXPAND) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         // ===== epilogue: TMEM -> integer screen -> fp64 log-sum-exp =====
         // set -> (accumulator slot, 128-column group of the tile); each thread owns one target row
         const int ew = warp - EPI_WARP0, set = ew >> 2, quarter = warp & 3;
@@ -780,7 +860,8 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             }
             // merge the sets' partial (max, sum) per row, then the two haplotypes of a target
             if (set == 0) skmax_all[((it + 1) & 1) * BM + rloc] = KEY_INIT;  // next unit's slot (idle since unit it - 1)
-            double2 *mb_buf = merge + (it & 1) * (NSETS - 1) * BM;
+            double2 *mb_buf = merge;
+            asm volatile("bar.sync 2, %0;" ::"n"(NSETS * 128) : "memory");  // set 0 is done reading the previous unit's partials
             if (set > 0) mb_buf[(set - 1) * BM + rloc] = make_double2(m, s);
             asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128) : "memory");
             if (set == 0) {
@@ -888,21 +969,26 @@ static int launch_mma_cfg(int n_units, int sm_count, cudaStream_t st, const CUte
     IBD_CUDA(cudaLaunchKernelEx(&cfg, mma::ld_mma_kernel<CF>, a, b, p));
     return 0;
 }
-// IBDGEM_MMA_VARIANT: 0 = CTA pairs (cta_group::2, 256 x 256 tiles; default), 1 = single CTA (128 x 128 tiles)
+// IBDGEM_MMA_VARIANT: 2 = CTA pairs (cta_group::2, 256 x 256 tiles), background operand expanded to
+// HBM and fetched by TMA (default: 7.1 ms + 1.2 ms expansion at C3); 0 = CTA pairs with in-kernel
+// expansion of the bit-packed background (9.2 ms at C3, but 5 GB less HBM and no expansion pass);
+// 1 = single CTA (128 x 128 tiles), TMA-fed
 static int mma_variant() {
     static int v = -1;
     if (v < 0) {
         const char *s = getenv("IBDGEM_MMA_VARIANT");
-        v = s ? atoi(s) : 0;
+        v = s ? atoi(s) : 2;
     }
     return v;
 }
 static int mma_cg(int variant) { return variant == 1 ? 1 : 2; }
+static bool mma_expand(int variant) { return variant == 0; }
 static int launch_mma(int variant, int n_units, int sm_count, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b,
                       const mma::Params &p) {
     switch (variant) {
-        case 1: return launch_mma_cfg<mma::Cfg<1, 4>>(n_units, sm_count, st, a, b, p);
-        default: return launch_mma_cfg<mma::Cfg<2, 4>>(n_units, sm_count, st, a, b, p);
+        case 1: return launch_mma_cfg<mma::Cfg<1, 5, false>>(n_units, sm_count, st, a, b, p);
+        case 2: return launch_mma_cfg<mma::Cfg<2, 5, false>>(n_units, sm_count, st, a, b, p);
+        default: return launch_mma_cfg<mma::Cfg<2, 5, true>>(n_units, sm_count, st, a, b, p);
     }
 }
 static double screen_nats() {
@@ -942,29 +1028,39 @@ void ld_tensor_release(ibdgem_engine *e) {
     e->ld = nullptr;
 }
 
+// New inputs: the cached operands are stale, but the buffers are kept — a re-upload of the same
+// shape (every end-to-end step) then rebuilds in place without cudaFree / cudaMalloc.
+void ld_tensor_invalidate(ibdgem_engine *e) {
+    if (e->ld) e->ld->valid = false;
+}
+
 static int build_cache(ibdgem_engine *e) {
     if (e->ld && e->ld->valid) return 0;
-    ld_tensor_release(e);
-    LdCache *c = new LdCache();
-    e->ld = c;
-    c->nW = e->nW_shared;
+    const int Wpad = (e->prm.window_size + 127) / 128 * 128;
+    if (e->ld && (e->ld->nW != e->nW_shared || e->ld->N != e->N || e->ld->Wpad != Wpad)) ld_tensor_release(e);
+    LdCache *c = e->ld;
+    if (!c) {
+        c = new LdCache();
+        e->ld = c;
+        c->nW = e->nW_shared;
+        c->W = e->prm.window_size;
+        c->Wpad = Wpad;
+        c->WP32 = c->Wpad / 32;
+        c->KB = c->Wpad / 128;
+        c->N = e->N;
+        c->H = 2 * e->N;
+        const size_t slots = (size_t)c->nW * c->Wpad;
+        c->b_infsite = slots * 4; c->b_nk = slots; c->b_d1 = slots * 8; c->b_l0 = slots * 8; c->b_C0 = (size_t)c->nW * 8;
+        c->b_tbits = (size_t)c->nW * c->H * c->WP32 * 4;
+        c->b_Rw = (size_t)c->nW * c->H * 8;
+        c->b_Qw = (size_t)c->nW * c->N * 8;
+        if (dev_alloc(e, (void **)&c->d_infsite, c->b_infsite) || dev_alloc(e, (void **)&c->d_nk, c->b_nk) ||
+            dev_alloc(e, (void **)&c->d_d1, c->b_d1) || dev_alloc(e, (void **)&c->d_l0, c->b_l0) ||
+            dev_alloc(e, (void **)&c->d_C0, c->b_C0) || dev_alloc(e, (void **)&c->d_tbits, c->b_tbits) ||
+            dev_alloc(e, (void **)&c->d_Rw, c->b_Rw) || dev_alloc(e, (void **)&c->d_Qw, c->b_Qw))
+            return 1;
+    }
     c->K = e->K_shared;
-    c->W = e->prm.window_size;
-    c->Wpad = (c->W + 127) / 128 * 128;
-    c->WP32 = c->Wpad / 32;
-    c->KB = c->Wpad / 128;
-    c->N = e->N;
-    c->H = 2 * e->N;
-    const size_t slots = (size_t)c->nW * c->Wpad;
-    c->b_infsite = slots * 4; c->b_nk = slots; c->b_d1 = slots * 8; c->b_l0 = slots * 8; c->b_C0 = (size_t)c->nW * 8;
-    c->b_tbits = (size_t)c->nW * c->H * c->WP32 * 4;
-    c->b_Rw = (size_t)c->nW * c->H * 8;
-    c->b_Qw = (size_t)c->nW * c->N * 8;
-    if (dev_alloc(e, (void **)&c->d_infsite, c->b_infsite) || dev_alloc(e, (void **)&c->d_nk, c->b_nk) ||
-        dev_alloc(e, (void **)&c->d_d1, c->b_d1) || dev_alloc(e, (void **)&c->d_l0, c->b_l0) ||
-        dev_alloc(e, (void **)&c->d_C0, c->b_C0) || dev_alloc(e, (void **)&c->d_tbits, c->b_tbits) ||
-        dev_alloc(e, (void **)&c->d_Rw, c->b_Rw) || dev_alloc(e, (void **)&c->d_Qw, c->b_Qw))
-        return 1;
     IBD_CUDA(cudaMemsetAsync(c->d_infsite, 0xFF, c->b_infsite, e->stream));
     IBD_CUDA(cudaMemsetAsync(c->d_nk, 0, c->b_nk, e->stream));
     IBD_CUDA(cudaMemsetAsync(c->d_d1, 0, c->b_d1, e->stream));
@@ -1054,18 +1150,19 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     const int nrows = 2 * T;
     const int MB = (nrows + mma::BM * CG - 1) / (mma::BM * CG);
 
-    const size_t per_window = (size_t)(ncols + nrows) * c->Wpad;
+    const bool fused = mma_expand(variant);  // background expanded inside the MMA kernel
+    const size_t per_window = (size_t)((fused ? 0 : ncols) + nrows) * c->Wpad;
     const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, LD_OPERAND_BUDGET / per_window));
-    int32_t *d_bgU, *d_ownU, *d_rowhap, *d_rowown, *d_akey;
+    int32_t *d_bgU, *d_ownU, *d_rowhap, *d_rowown, *d_akey, *d_colhap;
     double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp;
     unsigned char *d_A, *d_B;
-    const size_t misc_i = (size_t)nU + T + 4 * (size_t)T;
+    const size_t misc_i = (size_t)nU + T + 4 * (size_t)T + (size_t)ncolpad;
     const size_t misc_d = (size_t)nU + 2 * (size_t)T;
     if (scratch(e, SC_MMA_MISC, misc_i * 4 + misc_d * 8 + 64, (void **)&d_lnc) ||
         scratch(e, SC_MMA_BGIDX, (size_t)nW * ncolpad * 4, (void **)&d_akey) ||
         scratch(e, SC_MMA_ROWLSE, (size_t)nW * ncolpad * 8 + (size_t)nW * nU * 8, (void **)&d_Rp) ||
         scratch(e, SC_MMA_TGT, (size_t)nWb * nrows * c->Wpad, (void **)&d_A) ||
-        scratch(e, SC_MMA_BG, (size_t)nWb * ncols * c->Wpad, (void **)&d_B))
+        scratch(e, SC_MMA_BG, fused ? 16 : (size_t)nWb * ncols * c->Wpad, (void **)&d_B))
         return 1;
     d_lognb = d_lnc + nU;
     d_lognb4 = d_lognb + T;
@@ -1073,7 +1170,11 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     d_ownU = d_bgU + nU;
     d_rowhap = d_ownU + T;
     d_rowown = d_rowhap + 2 * (size_t)T;
+    d_colhap = d_rowown + 2 * (size_t)T;
     d_Qp = d_Rp + (size_t)nW * ncolpad;
+    std::vector<int32_t> colhap((size_t)ncolpad, -1);
+    for (int cidx = 0; cidx < ncols; cidx++) colhap[cidx] = 2 * bgU[cidx >> 1] + (cidx & 1);
+    IBD_CUDA(cudaMemcpyAsync(d_colhap, colhap.data(), (size_t)ncolpad * 4, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lnc, lnc.data(), (size_t)nU * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lognb, lognb.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lognb4, lognb4.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
@@ -1097,7 +1198,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     // windows are processed in batches so the expanded int8 operands stay within a fixed budget
     for (int w0 = 0; w0 < nW; w0 += nWb) {
         const int nw = std::min(nWb, nW - w0);
-        {
+        if (!fused) {
             LaunchScope ls(e, K_LD_EXPAND_BG);
             const int64_t n = (int64_t)nw * ncols * c->WP32;
             ld_expand_bg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(n, w0, ncols, c->H, c->WP32, d_bgU, c->d_tbits,
@@ -1111,7 +1212,9 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         }
         IBD_CUDA(cudaGetLastError());
         CUtensorMap mapA, mapB;
-        if (make_operand_map(&mapA, d_A, c->Wpad, nrows, nw) || make_operand_map(&mapB, d_B, c->Wpad, ncols, nw)) return 1;
+        if (make_operand_map(&mapA, d_A, c->Wpad, nrows, nw)) return 1;
+        if (fused) mapB = mapA;
+        else if (make_operand_map(&mapB, d_B, c->Wpad, ncols, nw)) return 1;
         mma::Params p;
         p.w0 = w0;
         p.nW = nw; p.MB = MB; p.NT = NT; p.KB = c->KB;
@@ -1123,6 +1226,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.akey = d_akey; p.Rp = d_Rp; p.Rw = c->d_Rw;
         p.row_hap = d_rowhap; p.row_own = d_rowown;
         p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
+        p.tbits = c->d_tbits; p.colhap = d_colhap; p.WP32 = c->WP32;
         {
             LaunchScope ls(e, K_LD_MMA);
             if (launch_mma(variant, p.n_units, e->sm_count, e->stream, mapA, mapB, p)) return 1;

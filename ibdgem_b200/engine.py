@@ -117,6 +117,9 @@ class Engine:
     def prepare(self):
         self._check(self._lib.ibdgem_engine_prepare(self._h))
 
+    def invalidate(self):
+        self._check(self._lib.ibdgem_engine_invalidate(self._h))
+
     def get_site_table(self):
         f = np.zeros(self.S)
         st = np.zeros(self.S, np.uint8)

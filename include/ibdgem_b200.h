@@ -105,6 +105,10 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
  * per-site IBD0 / IBD1[g] / IBD2[g] (find_pDgf, find_pDgIBD1, src/ibd-math.c:84-142) and the
  * shared window map.  Called implicitly by the score functions when inputs changed. */
 int ibdgem_engine_prepare(ibdgem_engine *e);
+/* Marks the prepared state stale without touching the uploaded inputs, so the next prepare() /
+ * score_*() recomputes the whole target-independent stage from the packed arrays resident in
+ * HBM (what one reference run does per invocation).  Device buffers are kept. */
+int ibdgem_engine_invalidate(ibdgem_engine *e);
 
 /* Compact per-site table after prepare() (any pointer may be NULL):
  *   f[S]; status[S] (for a target that is not filtered by -v/-D);
