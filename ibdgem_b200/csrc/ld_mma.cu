@@ -194,6 +194,26 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     return __hiloint2double(__double2hiint(p) + n * 1048576, __double2loint(p));
 }
 
+// running log-sum-exp (max m, scaled sum s) += e^x
+__device__ __forceinline__ void lse_add(double &m, double &s, double x) {
+    const bool up = x > m;
+    const double e = exp_nonpos(up ? m - x : x - m);  // one exp whichever way the maximum moves
+    s = up ? fma(s, e, 1.0) : s + e;
+    m = up ? x : m;
+}
+
+// v[j] for a per-lane j in 0..31: binary select tree (registers cannot be indexed dynamically)
+template <int N>
+__device__ __forceinline__ int pick_tree(const int *v, int j) {
+    if constexpr (N == 1) {
+        return v[0];
+    } else {
+        const int lo = pick_tree<N / 2>(v, j), hi = pick_tree<N / 2>(v + N / 2, j);
+        return (j & (N / 2)) ? hi : lo;
+    }
+}
+__device__ __forceinline__ int pick32(const int (&v)[32], int j) { return pick_tree<32>(v, j); }
+
 // ---------------------------------------------------------------------------------------------
 // cached-operand kernels
 
@@ -465,29 +485,26 @@ constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a sha
 // CG = CTAs per MMA (tcgen05 cta_group).  CG = 2 pairs two SMs on one 256 x 256 tile: each CTA keeps
 // its own 128 target rows resident and streams HALF of every background tile, which halves the
 // shared-memory traffic per MMA — the resource ncu showed saturated with CG = 1.
-template <int CG_, int NSTAGE_, bool EXPAND_>
+template <int CG_, int NSTAGE_>
 struct Cfg {
     static constexpr int CG = CG_, NSTAGE = NSTAGE_;
-    // EXPAND: the background operand is never materialised in HBM; four expander warps turn the
-    // bit-packed haplotype rows into the swizzled int8 stage layout in shared memory
-    static constexpr bool EXPAND = EXPAND_;
-    static constexpr int EXP_WARP0 = EPI_WARP0 + NSETS * 4;
     static constexpr int TILE_N = BN * CG;          // accumulator tile columns
     static constexpr int NACC = 512 / TILE_N;       // TMEM accumulator slots
-    static constexpr int THREADS = 128 + NSETS * 128 + (EXPAND ? 128 : 0);
+    static constexpr int SETCOLS = TILE_N / NSETS;  // accumulator columns per epilogue set
+    static constexpr int THREADS = 128 + NSETS * 128;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + MAXKB * A_SLAB;
     static constexpr int OFF_KEYS = OFF_B + NSTAGE * B_SLAB;             // per epilogue warp: 128 int32
-    static constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * BN * 4;      // (NSETS - 1) x 128 x double2
-    static constexpr int OFF_KMAX = OFF_MERGE + (NSETS - 1) * BM * 16;   // 2 x 128 int32, shared by the sets
+    static constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * SETCOLS * 4;  // NSETS x 128 x double2: the sets' (max, sum) per row
+    static constexpr int OFF_KMAX = OFF_MERGE + NSETS * BM * 16;          // 2 x 128 int32, shared by the sets
     static constexpr int OFF_BAR = OFF_KMAX + 2 * BM * 4;
-    static constexpr int NBAR = 2 + 2 * NSTAGE + 2 * NACC;
+    static constexpr int NBAR = 2 * MAXKB + 2 * NSTAGE + 2 * NACC;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
     static constexpr uint32_t IDESC = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (0u << 10) /* B = u8 */ |
                                       ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
-    static_assert(NSETS == NACC * CG, "one epilogue set per (accumulator slot, 128-column group)");
+    static_assert(SETCOLS % 32 == 0 && SETCOLS <= BN, "epilogue sets split the tile into 32-column chunks");
 };
 
 struct Params {
@@ -506,10 +523,16 @@ struct Params {
     const double *C0;        // [nW]
     const double *lognb4;    // [T] ln(4 n_refpanel) or NaN
     double *wll;             // [T][outW][3]
-    const uint32_t *tbits;   // [windows][H][WP32] haplotype-major bits (EXPAND)
-    const int32_t *colhap;   // [ncolpad] panel haplotype of each background column, -1 = padding (EXPAND)
-    int WP32;
+    int debug;               // IBDGEM_MMA_DEBUG experiments (0 = product behaviour)
+    int warm_tiles;          // leading tiles of a unit whose maximum is taken before they are screened
+    unsigned long long *trace;  // IBDGEM_MMA_TRACE: [4][1024] event log of CTA 0 (nullptr = off)
 };
+// event log entry: clock64 << 16 | event << 12 | tile; one lane per traced warp writes
+#define IBD_TRACE(role, ev, tile)                                                                          \
+    do {                                                                                                   \
+        if (p.trace && blockIdx.x == 0 && lane == 0 && tr_n < 1024)                                        \
+            p.trace[(role) * 1024 + tr_n++] = ((unsigned long long)clock64() << 16) | ((ev) << 12) | ((tile) & 0xfff); \
+    } while (0)
 
 template <int CG>
 __device__ __forceinline__ void tma_load_3d_cg(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
@@ -576,9 +599,11 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);
-    uint64_t *a_full = bars, *a_empty = bars + 1;
-    uint64_t *b_full = bars + 2, *b_empty = bars + 2 + NSTAGE;
-    uint64_t *acc_full = bars + 2 + 2 * NSTAGE, *acc_empty = acc_full + NACC;
+    // the resident target tile has one (full, empty) pair per 128-byte k-block: the next unit's
+    // k-block is fetched as soon as the last tile of this unit has consumed it
+    uint64_t *a_full = bars, *a_empty = bars + MAXKB;
+    uint64_t *b_full = bars + 2 * MAXKB, *b_empty = b_full + NSTAGE;
+    uint64_t *acc_full = b_empty + NSTAGE, *acc_empty = acc_full + NACC;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -591,10 +616,9 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
-        for (int i = 0; i < NSTAGE; i++) { mbar_init(b_full + i, CF::EXPAND ? 4 * CG : 1); mbar_init(b_empty + i, 1); }
-        for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * CG * CG); }
+        for (int i = 0; i < MAXKB; i++) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * NSETS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3)
@@ -614,11 +638,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Register budget per role (EXPAND runs 24 warps, 80 registers each at launch = the CTA's whole
-    // pool): control 32 + expander 64 release exactly what the four epilogue warpgroups claim (96).
-    // Each role branch starts with its setmaxnreg so ptxas allocates per region.
     if (warp < EPI_WARP0) {
-    if constexpr (CF::EXPAND) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 0) {
         // ===== TMA producer (both CTAs of a pair: own A rows, own half of every background tile) =====
         if (lane == 0) {
@@ -627,13 +647,16 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             int it = 0;
             for (int u = group0; u < p.n_units; u += ngroups, it++) {
                 const int w = u / p.MB, mb = u % p.MB;
-                mbar_wait(a_empty, (uint32_t)((it & 1) ^ 1));
-                if (rank == 0) mbar_expect_tx(a_full, (uint32_t)(CG * p.KB * A_SLAB));
-                for (int kb = 0; kb < p.KB; kb++)
-                    tma_load_3d_cg<CG>(smem + OFF_A + kb * A_SLAB, &tmapA, a_full, kb * KBYTES, (mb * CG + (int)rank) * BM, w);
-                if constexpr (!CF::EXPAND)
+                auto load_a = [&](int kb) {
+                    mbar_wait(a_empty + kb, (uint32_t)((it & 1) ^ 1));
+                    if (rank == 0) mbar_expect_tx(a_full + kb, (uint32_t)(CG * A_SLAB));
+                    tma_load_3d_cg<CG>(smem + OFF_A + kb * A_SLAB, &tmapA, a_full + kb, kb * KBYTES, (mb * CG + (int)rank) * BM, w);
+                };
                 for (int n = 0; n < p.NT; n++)
                     for (int kb = 0; kb < p.KB; kb++) {
+                        // the unit's target k-blocks are interleaved with its first background tile, in
+                        // the order the MMA issuer needs them
+                        if (n == 0) load_a(kb);
                         if (n + PF_TILES < p.NT)  // pull the same k-block of a later tile into L2
                             tma_prefetch_3d(&tmapB, kb * KBYTES, ((n + PF_TILES) * CG + (int)rank) * BN, w);
                         mbar_wait(b_empty + st, ph ^ 1u);
@@ -652,13 +675,16 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             uint32_t ph = 0;
             int it = 0;
             uint32_t g = 0;  // accumulator tile counter
+            int tr_n = 0;
             const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + OFF_A));
             const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem + OFF_B));
             for (int u = group0; u < p.n_units; u += ngroups, it++) {
-                mbar_wait(a_full, (uint32_t)(it & 1));
                 for (int n = 0; n < p.NT; n++, g++) {
+                    const bool first = n == 0, last = n == p.NT - 1;
                     const uint32_t acc = g % NACC, use = g / NACC;
+                    IBD_TRACE(0, 1, g);
                     mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
+                    IBD_TRACE(0, 2, g);
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     // two k-blocks per trip: both barrier probes are in flight together
                     for (int kb = 0; kb < p.KB; kb += 2) {
@@ -668,8 +694,14 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         if (st2 == NSTAGE) { st2 = 0; ph2 ^= 1u; }
                         const bool r1 = mbar_test(b_full + st, ph);
                         const bool r2 = two ? mbar_test(b_full + st2, ph2) : true;
+                        if (!r1 || !r2) IBD_TRACE(0, 3, g);
                         if (!r1) mbar_wait(b_full + st, ph);
                         if (!r2) mbar_wait(b_full + st2, ph2);
+                        if (!r1 || !r2) IBD_TRACE(0, 4, g);
+                        if (first) {  // the unit's target k-blocks arrive one by one
+                            mbar_wait(a_full + kb, (uint32_t)(it & 1));
+                            if (two) mbar_wait(a_full + kb + 1, (uint32_t)(it & 1));
+                        }
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t ad = adesc0 + (uint64_t)((kb * A_SLAB) >> 4);
@@ -679,6 +711,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                                 umma_i8_cg<CG>(d_tmem, ad + (uint64_t)(k * (UK >> 4)), bd + (uint64_t)(k * (UK >> 4)), CF::IDESC,
                                                (uint32_t)((kb | k) != 0));
                             tc_commit_cg<CG>(b_empty + st);
+                            if (last) tc_commit_cg<CG>(a_empty + kb);
                             if (two) {
                                 const uint64_t ad2 = ad + (uint64_t)(A_SLAB >> 4);
                                 const uint64_t bd2 = bdesc0 + (uint64_t)((st2 * B_SLAB) >> 4);
@@ -686,6 +719,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                                 for (int k = 0; k < KBYTES / UK; k++)
                                     umma_i8_cg<CG>(d_tmem, ad2 + (uint64_t)(k * (UK >> 4)), bd2 + (uint64_t)(k * (UK >> 4)), CF::IDESC, 1u);
                                 tc_commit_cg<CG>(b_empty + st2);
+                                if (last) tc_commit_cg<CG>(a_empty + kb + 1);
                             }
                             if (kb + 2 >= p.KB) tc_commit_cg<CG>(acc_full + acc);
                         }
@@ -694,82 +728,69 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                     }
                 }
-                if (elect_one()) tc_commit_cg<CG>(a_empty);
-                __syncwarp();
-            }
-        }
-    }
-    } else if (CF::EXPAND && warp >= CF::EXP_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        // ===== expander: bit-packed background rows -> 0/1 bytes in the 128-byte-swizzled K-major
-        // stage layout the MMA reads.  One thread per background column of the stage; the row's
-        // window bits (16 bytes per k-block) are fetched one tile ahead and held in registers. =====
-        const int t = (int)threadIdx.x - CF::EXP_WARP0 * 32;  // column within this CTA's half tile
-        unsigned char *srow = smem + OFF_B + (t >> 3) * 1024 + (t & 7) * 128;
-        const uint32_t sw = (uint32_t)(t & 7);
-        int st = 0;
-        uint32_t ph = 0;
-        uint4 cur[MAXKB];
-        // window bits of this thread's column for tile (w, n); a consumed k-block is at once
-        // refilled with the same k-block of the NEXT tile, so loads run a full tile ahead
-        auto row_ptr = [&](int w, int n) -> const uint4 * {
-            const int hap = __ldg(p.colhap + (n * CG + (int)rank) * BN + t);
-            return hap < 0 ? nullptr
-                           : reinterpret_cast<const uint4 *>(p.tbits + ((size_t)(p.w0 + w) * p.H + hap) * p.WP32);
-        };
-        if (group0 < p.n_units) {
-            const uint4 *src = row_ptr(group0 / p.MB, 0);
-#pragma unroll
-            for (int kb = 0; kb < MAXKB; kb++) {
-                cur[kb] = make_uint4(0u, 0u, 0u, 0u);
-                if (kb < p.KB && src) cur[kb] = __ldg(src + kb);
-            }
-        }
-        for (int u = group0; u < p.n_units; u += ngroups) {
-            const int w = u / p.MB;
-            for (int n = 0; n < p.NT; n++) {
-                // next tile of this CTA: same window, or the first tile of its next unit
-                int w2 = w, n2 = n + 1;
-                if (n2 == p.NT) { n2 = 0; w2 = (u + ngroups < p.n_units) ? (u + ngroups) / p.MB : -1; }
-                const uint4 *nsrc = w2 >= 0 ? row_ptr(w2, n2) : nullptr;
-#pragma unroll
-                for (int kb = 0; kb < MAXKB; kb++) {
-                    if (kb < p.KB) {
-                        mbar_wait(b_empty + st, ph ^ 1u);
-                        unsigned char *dst = srow + st * B_SLAB;
-                        const uint32_t wd[4] = {cur[kb].x, cur[kb].y, cur[kb].z, cur[kb].w};
-                        cur[kb] = make_uint4(0u, 0u, 0u, 0u);
-                        if (nsrc) cur[kb] = __ldg(nsrc + kb);
-#pragma unroll
-                        for (int c = 0; c < 8; c++) {  // 16 sites -> one 16-byte chunk
-                            const uint32_t hw = (wd[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
-                            uint4 o;
-                            o.x = spread4(hw & 15u);
-                            o.y = spread4((hw >> 4) & 15u);
-                            o.z = spread4((hw >> 8) & 15u);
-                            o.w = spread4(hw >> 12);
-                            *reinterpret_cast<uint4 *>(dst + (((uint32_t)c ^ sw) << 4)) = o;
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_leader<CG>(b_full + st);
-                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
-                    }
-                }
+                IBD_TRACE(0, 5, g);
             }
         }
     } else {
-        if constexpr (CF::EXPAND) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        // ===== merge warps (2, 3): at the end of every unit the four epilogue sets leave their partial
+        // (max, scaled sum) per row in shared memory and move on; these two warps join them, add the
+        // rows' own terms and write LIBD1.  One thread per target (both haplotype rows), so the fp64
+        // exp / log chains (~8k cycles per unit) are off the accumulator hand-back path. =====
+        const double2 *mb_buf = reinterpret_cast<const double2 *>(smem + OFF_MERGE);
+        const int r0 = (warp - 2) * 64 + lane * 2;  // first of the target's two rows within the CTA's 128
+        asm volatile("bar.arrive 2, %0;" ::"n"(NSETS * 128 + 64) : "memory");  // buffer free for unit 0
+        for (int u = group0; u < p.n_units; u += ngroups) {
+            const int w = p.w0 + u / p.MB, mb = u % p.MB;
+            const int row = (mb * CG + (int)rank) * BM + r0;
+            const bool ok = row < p.nrows;  // nrows is even: both rows or neither
+            double rw0 = 0.0, rw1 = 0.0, lnb = 0.0;
+            if (ok) {
+                rw0 = __ldg(p.Rw + (size_t)w * p.H + __ldg(p.row_hap + row));
+                rw1 = __ldg(p.Rw + (size_t)w * p.H + __ldg(p.row_hap + row + 1));
+                lnb = __ldg(p.lognb4 + (row >> 1));
+            }
+            const double c0w = __ldg(p.C0 + w);
+            asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128 + 64) : "memory");  // the sets' partials are in place
+            double A[2], S[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double2 o[NSETS];
+#pragma unroll
+                for (int q = 0; q < NSETS; q++) o[q] = mb_buf[q * BM + r0 + h];
+                double M2 = o[0].x;
+#pragma unroll
+                for (int q = 1; q < NSETS; q++) M2 = fmax(M2, o[q].x);
+                double S2 = 0.0;
+#pragma unroll
+                for (int q = 0; q < NSETS; q++) S2 = fma(o[q].y, exp_nonpos(o[q].x - M2), S2);
+                S[h] = S2;
+                A[h] = (S2 > 0.0) ? M2 + (h ? rw1 : rw0) : -INFINITY;
+            }
+            asm volatile("bar.arrive 2, %0;" ::"n"(NSETS * 128 + 64) : "memory");  // partials consumed
+            // a row is A + ln S; the two haplotypes of the target are joined under one logarithm
+            const double mm = fmax(A[0], A[1]);
+            double r = mm + log(fma(S[0], exp_nonpos(A[0] - mm), S[1] * exp_nonpos(A[1] - mm)));
+            if (mm == -INFINITY) r = -INFINITY;
+            r = (c0w + r) - lnb;
+            if (!(lnb == lnb)) r = __longlong_as_double(0x7ff8000000000000LL);  // n_refpanel = 0: 0/0 in the reference
+            if (ok) p.wll[((size_t)(row >> 1) * p.outW + w) * 3 + 1] = r;
+        }
+    }
+    } else {
         // ===== epilogue: TMEM -> integer screen -> fp64 log-sum-exp =====
-        // set -> (accumulator slot, 128-column group of the tile); each thread owns one target row
+        // every set works on every tile: set q owns columns [q * SETCOLS, (q + 1) * SETCOLS) of the
+        // accumulator, so all four epilogue warps of a scheduler drain the slot together and the
+        // slot is handed back to the MMA issuer in half the time; each thread owns one target row
+        constexpr int SETCOLS = CF::SETCOLS;
         const int ew = warp - EPI_WARP0, set = ew >> 2, quarter = warp & 3;
-        const int slot = set % NACC, cgroup = set / NACC;
         const int rloc = quarter * 32 + lane;
-        int *skeys = reinterpret_cast<int *>(smem + OFF_KEYS) + ew * BN;
+        int *skeys = reinterpret_cast<int *>(smem + OFF_KEYS) + ew * SETCOLS;
         double2 *merge = reinterpret_cast<double2 *>(smem + OFF_MERGE);
         int *skmax_all = reinterpret_cast<int *>(smem + OFF_KMAX);
         uint32_t g0 = 0;  // tile counter at the start of the unit
         int it = 0;
+        int tr_n = 0;
+        const int tr_role = ew == 0 ? 1 : (ew == 15 ? 2 : 3);
         for (int u = group0; u < p.n_units; u += ngroups, it++, g0 += (uint32_t)p.NT) {
             const int w = p.w0 + u / p.MB, mb = u % p.MB;
             const int row = (mb * CG + (int)rank) * BM + rloc;
@@ -782,27 +803,41 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             // memory (monotone, so a stale read only lets more elements through the screen)
             int *skmax = skmax_all + (it & 1) * BM + rloc;
             double m = -INFINITY, s = 0.0;
+            // screening keys and R'[k] of the NEXT tile are fetched while the current one is processed,
+            // so no global-load latency sits between acc_full and the hand-back of the slot
+            constexpr int NCH = SETCOLS / 32;
+            int4 kv_next = make_int4(0, 0, 0, 0);
+            double rp_next[NCH];
+            auto fetch = [&](int n) {
+                const int col = n * TILE_N + set * SETCOLS;
+                if (lane < SETCOLS / 4) kv_next = __ldg(reinterpret_cast<const int4 *>(akw + col) + lane);
+#pragma unroll
+                for (int c = 0; c < NCH; c++) rp_next[c] = __ldg(rpw + col + c * 32 + lane);
+            };
+            fetch(0);
             for (int n = 0; n < p.NT; n++) {
                 const uint32_t g = g0 + (uint32_t)n;
-                if ((int)(g % NACC) != slot) continue;
+                const int slot = (int)(g % NACC);
                 const uint32_t use = g / NACC;
-                const int col0 = n * TILE_N + cgroup * BN;  // first column this warp handles
-                // this tile's screening keys -> this warp's shared slot
-                {
-                    const int4 kv = __ldg(reinterpret_cast<const int4 *>(akw + col0) + lane);
-                    __syncwarp();
-                    reinterpret_cast<int4 *>(skeys)[lane] = kv;
-                    __syncwarp();
-                }
+                const int col0 = n * TILE_N + set * SETCOLS;  // first column this warp handles
+                double rp_cur[NCH];  // lane l holds R' of column col0 + 32 c + l
+#pragma unroll
+                for (int c = 0; c < NCH; c++) rp_cur[c] = rp_next[c];
+                __syncwarp();
+                if (lane < SETCOLS / 4) reinterpret_cast<int4 *>(skeys)[lane] = kv_next;
+                __syncwarp();
+                if (n + 1 < p.NT) fetch(n + 1);
                 // does any row of this warp exclude a column of this tile?
-                const bool own_here = own0 >= col0 && own0 < col0 + BN;
+                const bool own_here = own0 >= col0 && own0 < col0 + SETCOLS;
                 const bool any_own = __any_sync(0xffffffffu, own_here);
+                kmax = max(kmax, *skmax);
+                if (tr_role < 3) IBD_TRACE(tr_role, 1, g);
                 mbar_wait_relaxed(acc_full + slot, use & 1u);
+                if (tr_role < 3) IBD_TRACE(tr_role, 2, g);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + slot * TILE_N + cgroup * BN + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; c++) {
-                    int v[32];
+                const uint32_t taddr = tmem_base + slot * TILE_N + set * SETCOLS + ((uint32_t)(quarter * 32) << 16);
+                // chunk c of this warp's columns: v[j] = key[j] - M[row, j], returns the chunk maximum
+                auto load_chunk = [&](int c, int (&v)[32]) -> int {
                     __syncwarp();
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
@@ -820,79 +855,81 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         for (int j = 0; j < 32; j++)
                             if ((j & ~1) == jo) v[j] = KEY_PAD;
                     }
-                    int cm = KEY_PAD;
+                    // 3-input max, four independent chains
+                    int c0 = __vimax3_s32(v[0], v[1], v[2]), c1 = __vimax3_s32(v[8], v[9], v[10]);
+                    int c2 = __vimax3_s32(v[16], v[17], v[18]), c3 = __vimax3_s32(v[24], v[25], v[26]);
+                    c0 = __vimax3_s32(c0, v[3], v[4]); c1 = __vimax3_s32(c1, v[11], v[12]);
+                    c2 = __vimax3_s32(c2, v[19], v[20]); c3 = __vimax3_s32(c3, v[27], v[28]);
+                    c0 = __vimax3_s32(c0, v[5], v[6]); c1 = __vimax3_s32(c1, v[13], v[14]);
+                    c2 = __vimax3_s32(c2, v[21], v[22]); c3 = __vimax3_s32(c3, v[29], v[30]);
+                    c0 = __vimax3_s32(c0, v[7], c1); c2 = __vimax3_s32(c2, v[15], c3);
+                    return __vimax3_s32(c0, c2, max(v[23], v[31]));
+                };
+                if (n < p.warm_tiles && p.debug != 1) {
+                    // The screen is relative to the RUNNING row maximum, which starts at -inf: without
+                    // help the first tile of a unit sends nearly every element down the fp64 path
+                    // (measured: ~40k cycles per unit, 1/3 of the kernel).  So the first tile is read
+                    // twice: once for the maximum over all its 256 columns (shared by the four sets
+                    // through skmax), then screened against that.
+                    int tm = KEY_PAD;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) cm = max(cm, v[j]);
+                    for (int c = 0; c < NCH; c++) {
+                        int v[32];
+                        tm = max(tm, load_chunk(c, v));
+                    }
+                    if (tm > kmax) {
+                        kmax = tm;
+                        if (row_ok) atomicMax(skmax, tm);
+                    }
+                    asm volatile("bar.sync 3, %0;" ::"n"(NSETS * 128) : "memory");
                     kmax = max(kmax, *skmax);
+                }
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    if (p.debug == 1) break;  // roofline experiment: MMA + operand feed only
+                    int v[32];
+                    const int cm = load_chunk(c, v);
                     if (cm > kmax) {
                         kmax = cm;
                         if (row_ok) atomicMax(skmax, cm);
                     }
                     const int thr = kmax - p.delta;
+                    // an element passes the screen only if the chunk maximum does: the per-element
+                    // mask is built only when some row of the warp has a candidate in this chunk
                     uint32_t mask = 0;
+                    if (__any_sync(0xffffffffu, cm > thr)) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (v[j] > thr) mask |= 1u << j;
-                    // columns some row of this warp still cares about: one shared copy of the fp64
-                    // path, the element re-read from TMEM (registers cannot be indexed dynamically)
-                    uint32_t todo = __reduce_or_sync(0xffffffffu, mask);
-                    while (todo) {
-                        const int j = __ffs((int)todo) - 1;
-                        todo &= todo - 1;
-                        int M;
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(M) : "r"(taddr + c * 32 + j) : "memory");
-                        tmem_ld_wait();
-                        if ((mask >> j) & 1u) {
-                            const double x = fma(p.kappa, (double)M, __ldg(rpw + col0 + c * 32 + j));
-                            if (x > m) {
-                                s = fma(s, exp_nonpos(m - x), 1.0);
-                                m = x;
-                            } else {
-                                s += exp_nonpos(x - m);
-                            }
-                        }
-                        __syncwarp();
+                        for (int j = 0; j < 32; j++)
+                            if (v[j] > thr) mask |= 1u << j;
+                    }
+                    // Candidates are rare and scattered over rows and columns, so each lane walks ITS
+                    // OWN candidate columns: trip count = the largest number of candidates any row of
+                    // the warp has in this chunk (usually 1), one convergent exp per trip.  v[j] for
+                    // the lane's own j is a 31-select tree over the registers.
+                    uint32_t mk = mask;
+                    const int trips = __reduce_max_sync(0xffffffffu, (unsigned)__popc(mk));
+                    for (int q = 0; q < trips; q++) {
+                        const bool act = mk != 0u;
+                        const int j = act ? __ffs((int)mk) - 1 : 0;
+                        mk &= mk - 1u;
+                        const int vj = pick32(v, j);
+                        const int M = skeys[c * 32 + j] - vj;  // v = key - M
+                        const double rp = __shfl_sync(0xffffffffu, rp_cur[c], j);
+                        if (act) lse_add(m, s, fma(p.kappa, (double)M, rp));
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader<CG>(acc_empty + slot);
+                if (tr_role < 3) IBD_TRACE(tr_role, 3, g);
             }
-            // merge the sets' partial (max, sum) per row, then the two haplotypes of a target
+            // hand the partial (max, sum) of this set's columns to the merge warps and move on
             if (set == 0) skmax_all[((it + 1) & 1) * BM + rloc] = KEY_INIT;  // next unit's slot (idle since unit it - 1)
-            double2 *mb_buf = merge;
-            asm volatile("bar.sync 2, %0;" ::"n"(NSETS * 128) : "memory");  // set 0 is done reading the previous unit's partials
-            if (set > 0) mb_buf[(set - 1) * BM + rloc] = make_double2(m, s);
-            asm volatile("bar.sync 1, %0;" ::"n"(NSETS * 128) : "memory");
-            if (set == 0) {
-                double M2 = m;
-#pragma unroll
-                for (int q = 0; q < NSETS - 1; q++) M2 = fmax(M2, mb_buf[q * BM + rloc].x);
-                double S2 = 0.0;
-                if (s > 0.0) S2 += s * exp_nonpos(m - M2);
-#pragma unroll
-                for (int q = 0; q < NSETS - 1; q++) {
-                    const double2 o = mb_buf[q * BM + rloc];
-                    if (o.y > 0.0) S2 += o.y * exp_nonpos(o.x - M2);
-                }
-                double e = -INFINITY;
-                if (S2 > 0.0) e = M2 + log(S2);
-                if (row_ok) e += p.Rw[(size_t)w * p.H + p.row_hap[row]];
-                const double eo = __shfl_xor_sync(0xffffffffu, e, 1);
-                if (row_ok && (lane & 1) == 0) {
-                    const int t = row >> 1;
-                    const double lnb = p.lognb4[t];
-                    double r;
-                    if (!(lnb == lnb)) {
-                        r = __longlong_as_double(0x7ff8000000000000LL);
-                    } else {
-                        const double mm = fmax(e, eo);
-                        r = (mm == -INFINITY) ? -INFINITY : mm + log(exp_nonpos(e - mm) + exp_nonpos(eo - mm));
-                        r = (p.C0[w] + r) - lnb;
-                    }
-                    p.wll[((size_t)t * p.outW + w) * 3 + 1] = r;
-                }
-            }
+            if (tr_role < 3) IBD_TRACE(tr_role, 4, g0);
+            asm volatile("bar.sync 2, %0;" ::"n"(NSETS * 128 + 64) : "memory");  // previous unit's partials consumed
+            merge[set * BM + rloc] = make_double2(m, s);
+            asm volatile("bar.arrive 1, %0;" ::"n"(NSETS * 128 + 64) : "memory");
+            if (tr_role < 3) IBD_TRACE(tr_role, 7, g0);
         }
     }
 
@@ -969,10 +1006,8 @@ static int launch_mma_cfg(int n_units, int sm_count, cudaStream_t st, const CUte
     IBD_CUDA(cudaLaunchKernelEx(&cfg, mma::ld_mma_kernel<CF>, a, b, p));
     return 0;
 }
-// IBDGEM_MMA_VARIANT: 2 = CTA pairs (cta_group::2, 256 x 256 tiles), background operand expanded to
-// HBM and fetched by TMA (default: 7.1 ms + 1.2 ms expansion at C3); 0 = CTA pairs with in-kernel
-// expansion of the bit-packed background (9.2 ms at C3, but 5 GB less HBM and no expansion pass);
-// 1 = single CTA (128 x 128 tiles), TMA-fed
+// IBDGEM_MMA_VARIANT: 2 = CTA pairs (cta_group::2, 256 x 256 tiles; default), 1 = single CTA
+// (128 x 128 tiles; shared-memory bound, kept for A/B measurement)
 static int mma_variant() {
     static int v = -1;
     if (v < 0) {
@@ -982,14 +1017,10 @@ static int mma_variant() {
     return v;
 }
 static int mma_cg(int variant) { return variant == 1 ? 1 : 2; }
-static bool mma_expand(int variant) { return variant == 0; }
 static int launch_mma(int variant, int n_units, int sm_count, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b,
                       const mma::Params &p) {
-    switch (variant) {
-        case 1: return launch_mma_cfg<mma::Cfg<1, 5, false>>(n_units, sm_count, st, a, b, p);
-        case 2: return launch_mma_cfg<mma::Cfg<2, 5, false>>(n_units, sm_count, st, a, b, p);
-        default: return launch_mma_cfg<mma::Cfg<2, 5, true>>(n_units, sm_count, st, a, b, p);
-    }
+    if (variant == 1) return launch_mma_cfg<mma::Cfg<1, 5>>(n_units, sm_count, st, a, b, p);
+    return launch_mma_cfg<mma::Cfg<2, 5>>(n_units, sm_count, st, a, b, p);
 }
 static double screen_nats() {
     static double v = -1;
@@ -1150,19 +1181,18 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     const int nrows = 2 * T;
     const int MB = (nrows + mma::BM * CG - 1) / (mma::BM * CG);
 
-    const bool fused = mma_expand(variant);  // background expanded inside the MMA kernel
-    const size_t per_window = (size_t)((fused ? 0 : ncols) + nrows) * c->Wpad;
+    const size_t per_window = (size_t)(ncols + nrows) * c->Wpad;
     const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, LD_OPERAND_BUDGET / per_window));
-    int32_t *d_bgU, *d_ownU, *d_rowhap, *d_rowown, *d_akey, *d_colhap;
+    int32_t *d_bgU, *d_ownU, *d_rowhap, *d_rowown, *d_akey;
     double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp;
     unsigned char *d_A, *d_B;
-    const size_t misc_i = (size_t)nU + T + 4 * (size_t)T + (size_t)ncolpad;
+    const size_t misc_i = (size_t)nU + T + 4 * (size_t)T;
     const size_t misc_d = (size_t)nU + 2 * (size_t)T;
     if (scratch(e, SC_MMA_MISC, misc_i * 4 + misc_d * 8 + 64, (void **)&d_lnc) ||
         scratch(e, SC_MMA_BGIDX, (size_t)nW * ncolpad * 4, (void **)&d_akey) ||
         scratch(e, SC_MMA_ROWLSE, (size_t)nW * ncolpad * 8 + (size_t)nW * nU * 8, (void **)&d_Rp) ||
         scratch(e, SC_MMA_TGT, (size_t)nWb * nrows * c->Wpad, (void **)&d_A) ||
-        scratch(e, SC_MMA_BG, fused ? 16 : (size_t)nWb * ncols * c->Wpad, (void **)&d_B))
+        scratch(e, SC_MMA_BG, (size_t)nWb * ncols * c->Wpad, (void **)&d_B))
         return 1;
     d_lognb = d_lnc + nU;
     d_lognb4 = d_lognb + T;
@@ -1170,11 +1200,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     d_ownU = d_bgU + nU;
     d_rowhap = d_ownU + T;
     d_rowown = d_rowhap + 2 * (size_t)T;
-    d_colhap = d_rowown + 2 * (size_t)T;
     d_Qp = d_Rp + (size_t)nW * ncolpad;
-    std::vector<int32_t> colhap((size_t)ncolpad, -1);
-    for (int cidx = 0; cidx < ncols; cidx++) colhap[cidx] = 2 * bgU[cidx >> 1] + (cidx & 1);
-    IBD_CUDA(cudaMemcpyAsync(d_colhap, colhap.data(), (size_t)ncolpad * 4, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lnc, lnc.data(), (size_t)nU * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lognb, lognb.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lognb4, lognb4.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
@@ -1198,7 +1224,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     // windows are processed in batches so the expanded int8 operands stay within a fixed budget
     for (int w0 = 0; w0 < nW; w0 += nWb) {
         const int nw = std::min(nWb, nW - w0);
-        if (!fused) {
+        {
             LaunchScope ls(e, K_LD_EXPAND_BG);
             const int64_t n = (int64_t)nw * ncols * c->WP32;
             ld_expand_bg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(n, w0, ncols, c->H, c->WP32, d_bgU, c->d_tbits,
@@ -1213,8 +1239,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         IBD_CUDA(cudaGetLastError());
         CUtensorMap mapA, mapB;
         if (make_operand_map(&mapA, d_A, c->Wpad, nrows, nw)) return 1;
-        if (fused) mapB = mapA;
-        else if (make_operand_map(&mapB, d_B, c->Wpad, ncols, nw)) return 1;
+        if (make_operand_map(&mapB, d_B, c->Wpad, ncols, nw)) return 1;
         mma::Params p;
         p.w0 = w0;
         p.nW = nw; p.MB = MB; p.NT = NT; p.KB = c->KB;
@@ -1226,12 +1251,39 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.akey = d_akey; p.Rp = d_Rp; p.Rw = c->d_Rw;
         p.row_hap = d_rowhap; p.row_own = d_rowown;
         p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
-        p.tbits = c->d_tbits; p.colhap = d_colhap; p.WP32 = c->WP32;
+        {
+            static int dbg = -1;
+            if (dbg < 0) { const char *sdbg = getenv("IBDGEM_MMA_DEBUG"); dbg = sdbg ? atoi(sdbg) : 0; }
+            p.debug = dbg;
+        }
+        {
+            static int wt = -1;
+            if (wt < 0) { const char *sw = getenv("IBDGEM_MMA_WARM_TILES"); wt = sw ? atoi(sw) : 1; }
+            p.warm_tiles = wt;
+        }
+        p.trace = nullptr;
+        const char *trace_path = getenv("IBDGEM_MMA_TRACE");
+        unsigned long long *d_trace = nullptr;
+        if (trace_path) {
+            IBD_CUDA(cudaMalloc(&d_trace, 4 * 1024 * 8));
+            IBD_CUDA(cudaMemsetAsync(d_trace, 0, 4 * 1024 * 8, e->stream));
+            p.trace = d_trace;
+        }
         {
             LaunchScope ls(e, K_LD_MMA);
             if (launch_mma(variant, p.n_units, e->sm_count, e->stream, mapA, mapB, p)) return 1;
         }
         IBD_CUDA(cudaGetLastError());
+        if (d_trace) {
+            std::vector<unsigned long long> h(4 * 1024);
+            IBD_CUDA(cudaMemcpyAsync(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+            IBD_CUDA(cudaStreamSynchronize(e->stream));
+            if (FILE *fh = fopen(trace_path, "wb")) {
+                fwrite(h.data(), 8, h.size(), fh);
+                fclose(fh);
+            }
+            cudaFree(d_trace);
+        }
     }
     IBD_CUDA(cudaGetLastError());
     return 0;
