@@ -27,7 +27,7 @@ void set_error(const char *fmt, ...) {
 const char *const kKernelNames[K_COUNT] = {
     "site_table",     "scan_count",    "scan_offsets",  "scan_rank",    "window_nonld", "counters",
     "expand_sites",   "ld_general",    "ld_finalize",   "ld_compact",   "ld_c0",        "ld_transpose",
-    "ld_marginals",   "ld_tables",     "ld_expand_bg",  "ld_expand_tgt", "ld_windows",  "ld_ibd0",
+    "ld_tables",     "ld_expand_bg",  "ld_expand_tgt", "ld_windows",  "ld_ibd0",
     "ld_mma",         "viterbi",       "fill",
 };
 
@@ -121,10 +121,11 @@ __global__ void fill_nan_kernel(double *p, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K_SITE_TABLE: one warp per panel line.  Streams the packed row once (coalesced), popcounts it
-// for the allele frequency (find_f_impute, src/ibd-parse.c:91-99), applies the AF-range and
-// max-cov filters (src/ibdgem.c:616-626) and evaluates IBD0, IBD1|g, IBD2|g (src/ibd-math.c:84-142,
-// src/ibdgem.c:632-651) plus their logs.
+// K_SITE_TABLE: a warp takes 32 consecutive panel lines.  Phase 1 streams each packed row with
+// coalesced 128-bit loads and popcounts it for the allele frequency (find_f_impute,
+// src/ibd-parse.c:91-99); lane r keeps row r's count.  Phase 2 is lane-parallel, one site per
+// lane: the AF-range and max-cov filters (src/ibdgem.c:616-626), IBD0, IBD1|g, IBD2|g
+// (src/ibd-math.c:84-142, src/ibdgem.c:632-651) and their logs.
 __global__ void __launch_bounds__(256)
 site_table_kernel(int64_t S, int32_t N, int64_t Wh, const uint32_t *__restrict__ bits,
                   const uint8_t *__restrict__ hostkeep, const uint8_t *__restrict__ nref,
@@ -138,45 +139,53 @@ site_table_kernel(int64_t S, int32_t N, int64_t Wh, const uint32_t *__restrict__
     const int H = 2 * N;
     const int nfull = H >> 5, rem = H & 31;
     const bool vec4 = ((Wh & 3) == 0);
-    for (int64_t s = warp0; s < S; s += nwarps) {
-        const uint32_t *row = bits + s * Wh;
-        int cnt = 0;
-        if (vec4) {  // 128-bit loads when rows are 16-byte aligned
+    const int n4 = vec4 ? (nfull >> 2) : 0;
+    for (int64_t s0 = warp0 * 32; s0 < S; s0 += nwarps * 32) {
+        const int rows = (int)min((int64_t)32, S - s0);
+        int mycnt = 0;
+        for (int r = 0; r < rows; r++) {
+            const uint32_t *row = bits + (s0 + r) * Wh;
             const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
-            const int n4 = nfull >> 2;
+            int cnt = 0;
             for (int w = lane; w < n4; w += 32) {
                 const uint4 q = __ldg(row4 + w);
                 cnt += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
             }
             for (int w = (n4 << 2) + lane; w < nfull; w += 32) cnt += __popc(__ldg(row + w));
-        } else {
-            for (int w = lane; w < nfull; w += 32) cnt += __popc(__ldg(row + w));
+            if (lane == 0 && rem) cnt += __popc(__ldg(row + nfull) & ((1u << rem) - 1u));
+            cnt = warp_sum_i(cnt);
+            if (lane == r) mycnt = cnt;
         }
-        if (lane == 0 && rem) cnt += __popc(__ldg(row + nfull) & ((1u << rem) - 1u));
-        cnt = warp_sum_i(cnt);
-        if (lane < 7) {
-            double f = __ddiv_rn((double)cnt, (double)H);
+        const int64_t s = s0 + lane;
+        if (lane < rows) {
+            double f = __ddiv_rn((double)mycnt, (double)H);
             if (afuser) {
                 const double u = afuser[s];
                 if (u == u) f = u;  // src/ibdgem.c:609-614
             }
             const int r = nref[s], a = nalt[s];
             const bool k = hostkeep[s] && !(f > max_af || f < min_af) && (r + a <= max_cov);
-            double v = __longlong_as_double(0x7ff8000000000000LL);
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            double v[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) v[i] = nan;
             if (k) {
                 const double *P = Ptab + (size_t)(r * C + a) * 3;
                 const double P0 = P[0], P1 = P[1], P2 = P[2];
-                if (lane == 0) v = lik_ibd0(f, P0, P1, P2);
-                else if (lane < 4) v = lik_ibd1(lane - 1, f, P0, P1, P2);
-                else v = P[lane - 4];
+                v[0] = lik_ibd0(f, P0, P1, P2);
+                v[1] = lik_ibd1(0, f, P0, P1, P2);
+                v[2] = lik_ibd1(1, f, P0, P1, P2);
+                v[3] = lik_ibd1(2, f, P0, P1, P2);
+                v[4] = P0; v[5] = P1; v[6] = P2;
             }
-            lik7[s * 7 + lane] = v;
-            lnlik7[s * 7 + lane] = k ? log(v) : v;
-            if (lane == 0) {
-                f_out[s] = f;
-                keep[s] = k ? 1 : 0;
-                status[s] = k ? ((r + a >= 1) ? 1 : 2) : 0;
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                lik7[s * 7 + i] = v[i];
+                lnlik7[s * 7 + i] = k ? log(v[i]) : v[i];
             }
+            f_out[s] = f;
+            keep[s] = k ? 1 : 0;
+            status[s] = k ? ((r + a >= 1) ? 1 : 2) : 0;
         }
     }
 }
@@ -894,7 +903,7 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     }
     {
         LaunchScope ls(e, K_SITE_TABLE);
-        const int blocks = (int)std::min<int64_t>((S + 7) / 8, (int64_t)e->sm_count * 16);
+        const int blocks = (int)((S + 255) / 256);  // one batch of 32 panel lines per warp
         site_table_kernel<<<blocks, 256, 0, e->stream>>>(
             S, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C,
             e->prm.min_af, e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7,

@@ -16,7 +16,7 @@
 // below 2N e^-32 ~ 1e-10 relative.  LIBD0 (the chain over background individuals) and LIBD2 are
 // target-independent per individual: Q_w[b] = C0 + R[r0] + R[r1] + kappa M[r0, r1].
 //
-// Kernels in this file: ld_compact, ld_c0, ld_transpose, ld_marginals (cached per prepared
+// Kernels in this file: ld_compact, ld_c0, ld_transpose (+ marginals) (cached per prepared
 // panel); ld_tables, ld_expand_bg, ld_expand_tgt, ld_windows, ld_mma, ld_ibd0 (per call).
 #include <cuda.h>
 #include <math.h>
@@ -250,73 +250,86 @@ __global__ void __launch_bounds__(256) ld_c0_kernel(const double *__restrict__ l
     if (threadIdx.x == 0) C0[blockIdx.x] = sh[0];
 }
 
-// site-major panel bits -> [window][haplotype][32-site words].  Block = (8 word columns = 256
-// haplotypes, one window); warp g transposes the 32x32 bit blocks of window slots 32g..32g+31
-// with ballots; the tile goes through shared memory so the stores are 128-byte rows.
+// 32 x 32 bit transpose across a warp: lane i holds row i on entry, column i on exit.  Five
+// butterfly exchanges of half-blocks, each one shuffle + one funnel rotate + one bitwise select:
+// a lane in the lower half keeps its bits under m and takes the partner's bits under m moved up
+// by j (a left rotate puts them there), a lane in the upper half the mirror image.
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int j = 16 >> k;
+        const uint32_t m = k == 0 ? 0x0000FFFFu : k == 1 ? 0x00FF00FFu : k == 2 ? 0x0F0F0F0Fu : k == 3 ? 0x33333333u : 0x55555555u;
+        const bool hi = (lane & j) != 0;
+        const uint32_t keep = hi ? ~m : m;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        const uint32_t t = __funnelshift_l(y, y, hi ? 32 - j : j);
+        x = (x & keep) | (t & ~keep);
+    }
+    return x;
+}
+
+// K_LD_TRANSPOSE: site-major panel bits -> [window][haplotype][32-site words], fused with the
+// per-window marginals.  Block = (one window, 8 word columns = 256 haplotypes).  Warp g transposes
+// the 32 x 32 bit blocks of window slots 32g .. 32g+31 in registers and builds the bit planes of
+// n_ref, n_alt and n of those slots; the tile goes through shared memory so the stores are whole
+// rows.  Then 4 threads per haplotype turn its rows into integers by AND + popcount against the
+// planes:  A = sum x n_ref, B = sum x n_alt  ->  R_w[x] = alpha A + beta B  (l1 - l0 is linear in
+// the counts), and for each individual  Q_w[b] = C0 + R[r0] + R[r1] + kappa sum n r0 r1.
+constexpr int LD_PLANES = 7;  // counts are <= 127 (IBDGEM_MAX_COV_LIMIT)
 __global__ void __launch_bounds__(1024)
 ld_transpose_kernel(const uint32_t *__restrict__ bits, int64_t Wh, int H, const int32_t *__restrict__ infsite,
-                    int Wpad, int WP32, uint32_t *__restrict__ tbits) {
+                    const uint8_t *__restrict__ nref, const uint8_t *__restrict__ nalt, int Wpad, int WP32, int nbits,
+                    const double *__restrict__ C0, double alpha, double beta, double kappa, uint32_t *__restrict__ tbits,
+                    double *__restrict__ Rw, double *__restrict__ Qw) {
     __shared__ uint32_t tile[256 * 33];
-    const int w = blockIdx.x, j0 = blockIdx.y * 8;
+    __shared__ uint32_t planes[3][LD_PLANES][32];
+    // the word-column group is the fastest grid dimension: the blocks that share a window's panel rows
+    // run together, so every 32-byte piece of a row is fetched from HBM once
+    const int w = blockIdx.y, j0 = blockIdx.x * 8;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     if (g < WP32) {
         const int32_t s = infsite[(size_t)w * Wpad + g * 32 + lane];
+        const int r = s >= 0 ? nref[s] : 0, a = s >= 0 ? nalt[s] : 0;
+        for (int b = 0; b < nbits; b++) {
+            const uint32_t pr = __ballot_sync(0xffffffffu, (r >> b) & 1);
+            const uint32_t pa = __ballot_sync(0xffffffffu, (a >> b) & 1);
+            const uint32_t pn = __ballot_sync(0xffffffffu, ((r + a) >> b) & 1);
+            if (lane == 0) { planes[0][b][g] = pr; planes[1][b][g] = pa; planes[2][b][g] = pn; }
+        }
         const uint32_t *row = bits + (size_t)(s < 0 ? 0 : s) * Wh;
+        uint32_t word[8];
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-            uint32_t word = 0;
-            if (s >= 0 && j0 + jj < Wh) word = __ldg(row + j0 + jj);
-            uint32_t out = 0;
+        for (int jj = 0; jj < 8; jj++) word[jj] = (s >= 0 && j0 + jj < Wh) ? __ldg(row + j0 + jj) : 0u;
 #pragma unroll
-            for (int b = 0; b < 32; b++) {
-                const uint32_t m = __ballot_sync(0xffffffffu, (word >> b) & 1u);
-                if (lane == b) out = m;
-            }
-            tile[(jj * 32 + lane) * 33 + g] = out;
-        }
+        for (int jj = 0; jj < 8; jj++) tile[(jj * 32 + lane) * 33 + g] = transpose32(word[jj], lane);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 256 * WP32; i += 1024) {
-        const int hl = i / WP32, gg = i % WP32;
-        const int hap = j0 * 32 + hl;
-        if (hap < H) tbits[((size_t)w * H + hap) * WP32 + gg] = tile[hl * 33 + gg];
-    }
-}
-
-// one thread per (window, haplotype): R_w[x] = sum_s x_s d1_s in site order, and for each
-// individual Q_w[b] = C0 + R[r0] + R[r1] + kappa * sum_s n_s r0_s r1_s.
-__global__ void __launch_bounds__(256)
-ld_marginals_kernel(const uint32_t *__restrict__ tbits, int H, int Wpad, int WP32, const double *__restrict__ d1,
-                    const uint8_t *__restrict__ nk, const double *__restrict__ C0, double kappa,
-                    double *__restrict__ Rw, double *__restrict__ Qw) {
-    extern __shared__ unsigned char shraw[];
-    double *sd = reinterpret_cast<double *>(shraw);
-    uint8_t *sn = shraw + (size_t)Wpad * 8;
-    const int w = blockIdx.x;
-    for (int k = threadIdx.x; k < Wpad; k += blockDim.x) {
-        sd[k] = d1[(size_t)w * Wpad + k];
-        sn[k] = nk[(size_t)w * Wpad + k];
-    }
-    __syncthreads();
-    const int hap = blockIdx.y * blockDim.x + threadIdx.x;  // pairs (2i, 2i+1) share a warp
-    const bool ok = hap < H;
-    const uint32_t *row = tbits + ((size_t)w * H + (ok ? hap : 0)) * WP32;
-    double R = 0;
-    int ms = 0;
-    for (int g = 0; g < WP32; g++) {
-        const uint32_t word = ok ? __ldg(row + g) : 0u;
-        const uint32_t both = word & __shfl_xor_sync(0xffffffffu, word, 1);
-#pragma unroll 8
-        for (int b = 0; b < 32; b++) {
-            const int k = g * 32 + b;
-            if ((word >> b) & 1u) R += sd[k];
-            if ((both >> b) & 1u) ms += sn[k];
+    if (lane < WP32)  // a warp stores one haplotype row of the tile per pass
+        for (int hl = g; hl < 256; hl += 32) {
+            const int hap = j0 * 32 + hl;
+            if (hap < H) tbits[((size_t)w * H + hap) * WP32 + lane] = tile[hl * 33 + lane];
+        }
+    // marginals: threads 4h .. 4h+3 share haplotype h of the tile (its partner 2i <-> 2i+1 is the next row)
+    const int hl = threadIdx.x >> 2, sub = threadIdx.x & 3;
+    const int hap = j0 * 32 + hl;
+    int A = 0, B = 0, Mq = 0;
+    for (int gg = sub; gg < WP32; gg += 4) {
+        const uint32_t x = tile[hl * 33 + gg];
+        const uint32_t both = x & tile[(hl ^ 1) * 33 + gg];
+        for (int b = 0; b < nbits; b++) {
+            A += __popc(x & planes[0][b][gg]) << b;
+            B += __popc(x & planes[1][b][gg]) << b;
+            Mq += __popc(both & planes[2][b][gg]) << b;
         }
     }
-    const double Rp = __shfl_xor_sync(0xffffffffu, R, 1);
-    if (ok) {
+    A += __shfl_xor_sync(0xffffffffu, A, 1); A += __shfl_xor_sync(0xffffffffu, A, 2);
+    B += __shfl_xor_sync(0xffffffffu, B, 1); B += __shfl_xor_sync(0xffffffffu, B, 2);
+    Mq += __shfl_xor_sync(0xffffffffu, Mq, 1); Mq += __shfl_xor_sync(0xffffffffu, Mq, 2);
+    const double R = fma(alpha, (double)A, beta * (double)B);
+    const double Rp = __shfl_xor_sync(0xffffffffu, R, 4);
+    if (sub == 0 && hap < H) {
         Rw[(size_t)w * H + hap] = R;
-        if ((hap & 1) == 0) Qw[(size_t)w * (H / 2) + (hap >> 1)] = ((C0[w] + R) + Rp) + kappa * (double)ms;
+        if ((hap & 1) == 0) Qw[(size_t)w * (H / 2) + (hap >> 1)] = ((C0[w] + R) + Rp) + kappa * (double)Mq;
     }
 }
 
@@ -422,18 +435,19 @@ ld_ibd0_kernel(int T, int nU, int outW, const double *__restrict__ Qp, const int
         for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
         double s = 0;
         if (m > -INFINITY)
-            for (int u = u0 + lane; u < u1; u += 32) s += exp(q[u] - m);
+            for (int u = u0 + lane; u < u1; u += 32) s += exp_nonpos(q[u] - m);
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) { cm[c] = m; cs[c] = s; }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double m = -INFINITY;
-        for (int c = 0; c < IBD0_CHUNKS; c++) m = fmax(m, cm[c]);
+    if (wid == 0) {  // combine the chunk partials across the lanes of one warp
+        double m = fmax(cm[lane], cm[lane + 32]);
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
         double s = 0;
-        for (int c = 0; c < IBD0_CHUNKS; c++)
-            if (cs[c] > 0) s += cs[c] * exp(cm[c] - m);
-        tot_m = m; tot_s = s;
+        if (cs[lane] > 0) s += cs[lane] * exp_nonpos(cm[lane] - m);
+        if (cs[lane + 32] > 0) s += cs[lane + 32] * exp_nonpos(cm[lane + 32] - m);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) { tot_m = m; tot_s = s; }
     }
     __syncthreads();
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -456,9 +470,9 @@ ld_ibd0_kernel(int T, int nU, int outW, const double *__restrict__ Qp, const int
                     if (u != own) m = fmax(m, q[u]);
                 double s = 0;
                 for (int c = 0; c < IBD0_CHUNKS; c++)
-                    if (c != oc && cs[c] > 0) s += cs[c] * exp(cm[c] - m);
+                    if (c != oc && cs[c] > 0) s += cs[c] * exp_nonpos(cm[c] - m);
                 for (int u = u0; u < u1; u++)
-                    if (u != own) s += exp(q[u] - m);
+                    if (u != own) s += exp_nonpos(q[u] - m);
                 r = m + log(s) - lnb;
             }
         }
@@ -1109,13 +1123,11 @@ static int build_cache(ibdgem_engine *e) {
     {
         LaunchScope ls(e, K_LD_TRANSPOSE);
         const int words = (c->H + 31) / 32;
-        ld_transpose_kernel<<<dim3(c->nW, (words + 7) / 8), 1024, 0, e->stream>>>(e->d_bits, e->Wh, c->H, c->d_infsite,
-                                                                                 c->Wpad, c->WP32, c->d_tbits);
-    }
-    {
-        LaunchScope ls(e, K_LD_MARGINALS);
-        ld_marginals_kernel<<<dim3(c->nW, (c->H + 255) / 256), 256, (size_t)c->Wpad * 9, e->stream>>>(
-            c->d_tbits, c->H, c->Wpad, c->WP32, c->d_d1, c->d_nk, c->d_C0, e->kappa, c->d_Rw, c->d_Qw);
+        int nbits = 1;
+        while ((1 << nbits) <= (int)e->prm.max_cov) nbits++;
+        ld_transpose_kernel<<<dim3((words + 7) / 8, c->nW), 1024, 0, e->stream>>>(
+            e->d_bits, e->Wh, c->H, c->d_infsite, e->d_nref, e->d_nalt, c->Wpad, c->WP32, nbits, c->d_C0, e->alpha, e->beta,
+            e->kappa, c->d_tbits, c->d_Rw, c->d_Qw);
     }
     IBD_CUDA(cudaGetLastError());
     c->valid = true;
