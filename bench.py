@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--targets", type=int, default=1000)
     ap.add_argument("--window", type=int, default=1000)
     ap.add_argument("--cpu-sites", type=int, default=10_000, help="site sample for the CPU baseline")
+    ap.add_argument("--cpu-targets", type=int, default=16, help="targets of the single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-general", action="store_true", help="A/B: CUDA-core --LD path")
     return ap.parse_args()
@@ -74,17 +75,19 @@ def write_reference_sample(dirpath, bits_np, H, n_ref, n_alt, pos, n_sites):
             fh.write("20\t%d\tN\t%d\t%s\t%s\t%s\n" % (int(pos[i]), c, b or "*", "I" * c or "*", "]" * c or "*"))
 
 
-def run_reference_procs(binary, dirpath, targets, window):
-    """One process per target (the reference is single-threaded; independent processes sharded
-    with -s are how it uses more than one core).  Returns wall seconds."""
+def run_reference_procs(binary, dirpath, target_lists, window):
+    """One process per target list (the reference is single-threaded; independent processes
+    sharded with -S are how it uses more than one core).  Returns wall seconds."""
     procs = []
+    for k, tl in enumerate(target_lists):
+        with open(os.path.join(dirpath, "targets_%d.txt" % k), "w") as fh:
+            fh.write("".join("i%d\n" % t for t in tl))
+        os.makedirs(os.path.join(dirpath, "out_%d" % k), exist_ok=True)
     t0 = time.perf_counter()
-    for t in targets:
-        out = os.path.join(dirpath, "out_%d" % t)
-        os.makedirs(out, exist_ok=True)
+    for k, tl in enumerate(target_lists):
         procs.append(subprocess.Popen([binary, "-H", "p.hap", "-L", "p.legend", "-I", "p.indv", "-P", "u.pileup",
-                                       "--LD", "-w", str(window), "-s", "i%d" % t, "-O", out], cwd=dirpath,
-                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+                                       "--LD", "-w", str(window), "-S", "targets_%d.txt" % k, "-O", "out_%d" % k],
+                                      cwd=dirpath, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError("reference binary failed")
@@ -97,20 +100,25 @@ def host_sample(args, seed=1):
     return synth_panel_numpy(args.cpu_sites, args.samples, seed=seed)
 
 
-def cpu_baseline(args, sample=None, n_procs=1):
-    """Times the reference's own CPU implementation of the path on a bounded sample."""
+def cpu_baseline(args, sample=None, n_procs=1, targets_per_proc=None, tmp=None):
+    """Times the reference's own CPU implementation of the path on a bounded sample: the first
+    cpu_sites sites of the workload, targets_per_proc targets per process, full background."""
     d = sample if sample is not None else host_sample(args)
     S1 = args.cpu_sites
     H = 2 * args.samples
+    tpp = targets_per_proc or args.cpu_targets
     inf = int(((d["n_ref"][:S1].astype(int) + d["n_alt"][:S1]) >= 1).sum())
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "ibdgem")
-    tmp = tempfile.mkdtemp(prefix="ibdgem_cpu_")
+    own_tmp = tmp is None
+    if own_tmp:
+        tmp = tempfile.mkdtemp(prefix="ibdgem_cpu_")
     try:
         if os.path.exists(ref_bin):
-            write_reference_sample(tmp, d["bits"], H, d["n_ref"], d["n_alt"], d["pos"], S1)
-            targets = list(range(n_procs))
-            wall = run_reference_procs(ref_bin, tmp, targets, args.window)
-            comps = len(targets) * inf * (args.samples - 1) * 4
+            if not os.path.exists(os.path.join(tmp, "p.hap")):
+                write_reference_sample(tmp, d["bits"], H, d["n_ref"], d["n_alt"], d["pos"], S1)
+            lists = [[(k * tpp + j) % args.samples for j in range(tpp)] for k in range(n_procs)]
+            wall = run_reference_procs(ref_bin, tmp, lists, args.window)
+            comps = n_procs * tpp * inf * (args.samples - 1) * 4
             kind = "reference"
             note = "oracle/_ref/ibdgem (unmodified reference, as-shipped flags -ggdb3 = -O0)"
         else:
@@ -119,17 +127,18 @@ def cpu_baseline(args, sample=None, n_procs=1):
             hap = unpack_rows(d["bits"], H, np.arange(S1))
             prm = oracle.Params(window=args.window, ld_mode=1)
             t0 = time.perf_counter()
-            comps = oracle.ld_loop_bench(prm, d["n_ref"][:S1], d["n_alt"][:S1], hap, np.arange(1, dtype=np.int32),
+            comps = oracle.ld_loop_bench(prm, d["n_ref"][:S1], d["n_alt"][:S1], hap, np.arange(tpp, dtype=np.int32),
                                          np.arange(args.samples, dtype=np.int32))
             wall = time.perf_counter() - t0
             kind = "port"
             note = "oracle/liboracle.so orc_ld_loop_bench (C restatement of src/ibdgem.c:673-721, -O2)"
             n_procs = 1
     finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+        if own_tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
     return dict(value=comps / wall, unit=UNIT, cores=n_procs, kind=kind,
-                sample="%s; first %d sites x %d target(s) x %d background, --LD -w %d, %.2f s wall" % (
-                    note, S1, n_procs, args.samples - 1, args.window, wall)), comps, wall
+                sample="%s; first %d sites x %d target(s) per process x %d process(es) x %d background, --LD -w %d, "
+                       "%.2f s wall" % (note, S1, tpp, n_procs, args.samples - 1, args.window, wall)), comps, wall
 
 
 def reference_arm(args):
@@ -138,13 +147,18 @@ def reference_arm(args):
         return
     n_procs = max(1, min(os.cpu_count() or 1, 64))
     sample = host_sample(args)
+    tpp = max(1, args.cpu_targets // 4)
     vals = []
     last = None
-    for i in range(args.warmup + args.steps):
-        cb, comps, wall = cpu_baseline(args, sample, n_procs)
-        if i >= args.warmup:
-            vals.append((comps, wall))
-        last = cb
+    tmp = tempfile.mkdtemp(prefix="ibdgem_ref_")
+    try:
+        for i in range(args.warmup + args.steps):
+            cb, comps, wall = cpu_baseline(args, sample, n_procs, tpp, tmp)
+            if i >= args.warmup:
+                vals.append((comps, wall))
+            last = cb
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     comps = sum(c for c, _ in vals)
     wall = sum(w for _, w in vals)
     v = comps / wall
@@ -153,9 +167,9 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall / max(len(vals), 1) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "--LD scoring, bounded CPU sample of C3: first %d sites x %d targets (one process "
-                               "per target on %d host cores) x %d background, window %d" % (
-                                   args.cpu_sites, n_procs, n_procs, args.samples - 1, args.window)},
+        "config": {"workload": "--LD scoring, bounded CPU sample of C3 per step: first %d sites x %d targets (%d per "
+                               "process, one process per host core, %d cores) x %d background, window %d" % (
+                                   args.cpu_sites, n_procs * tpp, tpp, n_procs, args.samples - 1, args.window)},
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -164,49 +178,52 @@ def reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread, every
+    few ms; nvidia-smi would manage one sample per step)."""
 
-    def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, index, period_s=0.004):
+        import threading
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+
+            def run():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for n, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(n)
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception:
+                        pass
+                    time.sleep(period_s)
+
+            self._thread = threading.Thread(target=run, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._thread = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self._thread is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        self.f.close()
-        os.unlink(self.f.name)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.samples:
+            out = {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                   "reasons": sorted(self.reasons), "samples": len(self.samples),
+                   "power_w_max": max(self.power) if self.power else None}
         return out
 
 
@@ -220,6 +237,7 @@ def main():
     import torch.distributed as dist
     import ibdgem_b200 as ib
     from ibdgem_b200.engine import _CScores
+    from ibdgem_b200.shard import gather_window_scores
     from ibdgem_b200.synth import synth_panel_torch
 
     if not torch.cuda.is_available():
@@ -260,7 +278,6 @@ def main():
     o_wn = pinned((T, maxW), torch.int32)
     o_ll = pinned((T, maxW, 3), torch.float64)
     d_ll = torch.empty((T, maxW, 3), dtype=torch.float64, device=dev)
-    d_all = torch.empty((world * T, maxW, 3), dtype=torch.float64, device=dev) if world > 1 else None
     cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr(), o_we.data_ptr(), o_wn.data_ptr(), o_ll.data_ptr(),
                   None, None, None, None, None, None, d_ll.data_ptr())
 
@@ -276,7 +293,7 @@ def main():
         eng.invalidate()
         eng.score_ld_raw(targets, bg, -1, cs)
         if world > 1:
-            dist.all_gather_into_tensor(d_all.view(-1), d_ll.view(-1))
+            gather_window_scores(d_ll, world * T)  # one NCCL all_gather of [T][maxW][3] fp64 per rank
 
     def barrier():
         if world > 1:
@@ -333,21 +350,34 @@ def main():
                 peaks = json.load(fh)
         except OSError:
             pass
-        # Algorithmic work of the dominant kernel: one multiply-accumulate of the
-        # weighted binary contraction sum_s n_s h_s k_s per comparison = 2 op / comparison; the int8
-        # tensor-core rate of sm_100a is 2x its bf16 rate, so the denominator is 2 x the measured dense
-        # bf16 figure.
+        # Algorithmic work of the dominant kernel (DESIGN.md "Roofline"): one multiply-accumulate of the
+        # weighted binary contraction sum_s n_s h_s k_s per comparison = 2 op / comparison.  The kernel
+        # runs it as int8 on tcgen05 (kind::i8), whose rate is 2x the bf16 rate, so the denominator is
+        # 2 x the measured dense bf16 figure of MEASURED_PEAKS.json (sustained: the kernel is timed
+        # inside a long step).  That figure was taken at the power-capped clock of a bf16 GEMM
+        # (~1.35 GHz); 0/1 x small-integer operands toggle few bits and this kernel holds the full
+        # boost clock, so frac can exceed 1 — pipe_peak_at_clock is the hardware ceiling
+        # (148 SMs x 8192 int8 MAC/clk x 2) at the SM clock sampled during the run.
         flop_per_launch = 2.0 * comps_rank * args.steps / max(dom_n, 1)
         avg_ms = dom_ms / max(dom_n, 1)
         achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
         bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
         peak = 2.0 * bf16 if ld_path == 1 else bf16
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        pipe_peak = 148 * 8192 * 2 * sm_mhz * 1e6 / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(dom)
+        except (OSError, ValueError):
+            pass
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "kernel": dom, "avg_launch_ms": avg_ms,
+                    "frac": achieved / peak, "traffic": traffic, "kernel": dom, "avg_launch_ms": avg_ms,
                     "launches": dom_n,
                     "peak_source": ("2 x bf16_tflops_sustained of measured MEASURED_PEAKS.json (int8 tcgen05 rate "
                                     "= 2 x bf16)" if ld_path == 1 else "bf16_tflops_sustained of measured") if peaks
                     else "fallback 1.4 PFLOP/s sustained bf16",
+                    "pipe_peak_at_clock": pipe_peak, "frac_of_pipe_peak": achieved / pipe_peak,
                     "kernel_share_of_step": dom_ms / (ms_total) if ms_total > 0 else None,
                     "kernels_ms_per_step": {k: v[0] / args.steps for k, v in stats.items() if v[1]}}
         out = {

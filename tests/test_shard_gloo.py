@@ -1,0 +1,91 @@
+"""world_size-2 gloo test of the N>1 path (host logic only): targets sharded contiguously, every
+rank scores its shard (here with the CPU oracle — the GPU engine is exercised by the -m gpu tests),
+one all_gather of per-window scores; the gathered table must equal the unsharded run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ibdgem_b200.shard import gather_window_scores, shard_bounds, shard_targets
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 5, 8, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _case():
+    import oracle
+    rng = np.random.default_rng(3)
+    S, N, W = 600, 12, 50
+    af = np.clip(rng.beta(0.5, 2.0, S), 0.01, 0.99)
+    hap = (rng.random((S, 2 * N)) < af[:, None]).astype(np.uint8)
+    pos = (1000 + 60 * np.arange(S)).astype(np.uint64)
+    d = rng.poisson(2.0, S)
+    n_alt = rng.binomial(d, 0.3).astype(np.uint8)
+    n_ref = (d - n_alt).astype(np.uint8)
+    keep = np.ones(S, np.uint8)
+    prm = oracle.Params(window=W, ld_mode=1)
+    targets = np.array([0, 3, 4, 7, 9], np.int32)  # odd count: shards of 3 and 2
+    return prm, pos, keep, n_ref, n_alt, hap, targets, np.arange(N, dtype=np.int32)
+
+
+def _score(targets):
+    import oracle
+    prm, pos, keep, n_ref, n_alt, hap, _, bg = _case()
+    maxW = len(pos) // prm.window + 2
+    out = np.full((len(targets), maxW, 3), np.nan)
+    for k, t in enumerate(targets):
+        o = oracle.compare_target(prm, pos, keep, n_ref, n_alt, hap, int(t), bg)
+        out[k, : o["n_windows"]] = o["w_log"]
+    return out
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        targets = _case()[6]
+        mine = shard_targets(targets, world, rank)
+        local = torch.from_numpy(_score(mine))
+        full = gather_window_scores(local, len(targets))
+        q.put((rank, full.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gather_matches_unsharded():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    want = _score(_case()[6])
+    for r in range(world):
+        np.testing.assert_array_equal(np.isnan(got[r]), np.isnan(want))
+        np.testing.assert_array_equal(np.nan_to_num(got[r]), np.nan_to_num(want))
