@@ -201,3 +201,46 @@ def test_hiddengem_log_front_end_matches_text_path():
         s_log, sc_log, _ = e.viterbi_batch(ll, [0, n], True)
     np.testing.assert_array_equal(s_lin, s_log)
     np.testing.assert_allclose(sc_lin, sc_log, rtol=0, atol=1e-7)
+
+
+def test_c3_full_size_spot_checks_against_oracle():
+    """BASELINE.json configs[2] at full size (1,000,000 sites x 2,504 samples x 1,000 targets, window
+    1,000): windows are independent, so any window of any target can be re-scored by the CPU oracle
+    from that window's slice of the inputs.  Nine (target, window) cells, all three likelihoods, plus
+    size-independent integer properties of the whole table."""
+    import torch
+    import ibdgem_b200 as ib
+    import oracle
+    from ibdgem_b200.synth import synth_panel_torch, unpack_rows
+    S, N, T, W = 1_000_000, 2504, 1000, 1000
+    d = synth_panel_torch(S, N, seed=1, device="cuda")
+    bits = d["bits"].numpy().view(np.uint32)
+    pos = d["pos"].numpy().view(np.uint64)
+    n_ref, n_alt, keep = d["n_ref"].numpy(), d["n_alt"].numpy(), d["keep"].numpy()
+    targets = np.arange(T, dtype=np.int32)
+    bg = np.arange(N, dtype=np.int32)
+    with ib.Engine(ib.Params(window_size=W)) as e:
+        e.upload_sites(pos, n_ref, n_alt, keep)
+        e.upload_panel(bits, N)
+        sc = e.score_ld(targets, bg, -1)
+        assert e.last_ld_path() == 1  # the tensor-core path is the one that ran
+    nW = S // W
+    assert (sc.n_windows == nW).all()
+    assert (sc.w_nsites[:, :nW] == W).all() and int(sc.processed[0]) == S and int(sc.skipped[0]) == 0
+    np.testing.assert_array_equal(sc.w_start[0, :nW], pos[0::W])
+    np.testing.assert_array_equal(sc.w_end[0, :nW], pos[W - 1::W])
+    assert np.isfinite(sc.w_loglik[:, :nW]).all()
+    # LIBD0 of a window is a mean over the background minus the target.  The reads were drawn from
+    # individual 0, whose term dominates every window: all targets but 0 see (nearly) the same LIBD0,
+    # and target 0 — whose own entry is omitted — sees a far smaller one.
+    l0 = sc.w_loglik[:, :nW, 0]
+    assert np.ptp(l0[1:], axis=0).max() < 1e-3
+    assert (l0[0] < l0[1] - 100.0).all()
+    prm = oracle.Params(window=W, ld_mode=1)
+    for w in (0, 417, nW - 1):
+        sl = slice(w * W, (w + 1) * W)
+        hap = unpack_rows(bits, 2 * N, np.arange(w * W, (w + 1) * W))
+        for t in (0, 333, T - 1):
+            o = oracle.compare_target(prm, pos[sl], keep[sl], n_ref[sl], n_alt[sl], hap, int(t), bg)
+            assert o["n_windows"] == 1
+            np.testing.assert_allclose(sc.w_loglik[t, w], o["w_log"][0], rtol=0, atol=1e-6)
