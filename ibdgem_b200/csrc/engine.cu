@@ -28,7 +28,7 @@ const char *const kKernelNames[K_COUNT] = {
     "site_table",     "scan_count",    "scan_offsets",  "scan_rank",    "window_nonld", "counters",
     "expand_sites",   "ld_general",    "ld_finalize",   "ld_compact",   "ld_c0",        "ld_transpose",
     "ld_tables",     "ld_expand_bg",  "ld_expand_tgt", "ld_windows",  "ld_ibd0",
-    "ld_mma",         "viterbi",       "fill",
+    "ld_mma",         "viterbi",       "viterbi_norm",  "viterbi_back", "viterbi_out", "fill",
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -357,19 +357,93 @@ window_nonld_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ tar
     }
 }
 
+// K_WINDOW_NONLD, shared window map (no -v, no -D): one CTA per window, one thread per target.
+// The window's rows of the per-site log table (56 bytes per site, target-independent) are staged
+// in shared memory once per CTA; every thread then walks the sites with its target's genotype
+// bits, so the table is read from HBM once per window instead of once per target.
+constexpr int NONLD_TILE = 256;  // sites staged per pass
+__global__ void __launch_bounds__(128)
+window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ targets, int T,
+                           const uint64_t *__restrict__ pos, const uint8_t *__restrict__ status,
+                           const double *__restrict__ lnlik7, int outW, double *__restrict__ wll,
+                           int32_t *__restrict__ wn, uint64_t *__restrict__ ws, uint64_t *__restrict__ we,
+                           int32_t *__restrict__ nwin_out) {
+    __shared__ double sl[NONLD_TILE][7];
+    __shared__ int64_t ssite[NONLD_TILE];
+    __shared__ int segcnt[NONLD_TILE / 32];
+    constexpr int PASSES = NONLD_TILE / 128;
+    const int w = blockIdx.x;
+    const int nw = m.nwin[0];
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
+    if (w == 0 && t < T) nwin_out[t] = nw;
+    if (w >= nw || w >= m.maxW) return;
+    const int64_t s0 = m.wfirst[w], s1 = m.wlast[w];
+    const int indiv = t < T ? targets[t] : 0;
+    const int lane = threadIdx.x & 31;
+    double a0 = 0, a1 = 0, a2 = 0;
+    int n = 0;
+    for (int64_t sb = s0; sb <= s1; sb += NONLD_TILE) {
+        __syncthreads();
+        // compact the informative sites of this pass into shared memory, in site order
+        unsigned bal[PASSES];
+#pragma unroll
+        for (int q = 0; q < PASSES; q++) {
+            const int64_t s = sb + q * 128 + threadIdx.x;
+            bal[q] = __ballot_sync(0xffffffffu, s <= s1 && status[s] == 1);
+            if (lane == 0) segcnt[(q * 128 + threadIdx.x) >> 5] = __popc(bal[q]);
+        }
+        __syncthreads();
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < PASSES; q++) {
+            const int seg = (q * 128 + (int)threadIdx.x) >> 5;
+            int base = 0;
+            for (int k = 0; k < seg; k++) base += segcnt[k];
+            if ((bal[q] >> lane) & 1u) ssite[base + __popc(bal[q] & ((1u << lane) - 1u))] = sb + q * 128 + threadIdx.x;
+        }
+        for (int k = 0; k < NONLD_TILE / 32; k++) cnt += segcnt[k];
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 7; i += blockDim.x) sl[i / 7][i % 7] = lnlik7[ssite[i / 7] * 7 + i % 7];
+        __syncthreads();
+        if (t < T) {
+            for (int j = 0; j < cnt; j++) {
+                const uint32_t pr = hap_pair(v.bits + ssite[j] * v.Wh, indiv);
+                const int g = (int)(pr & 1u) + (int)(pr >> 1);
+                a0 += sl[j][0];
+                a1 += sl[j][1 + g];
+                a2 += sl[j][4 + g];
+            }
+            n += cnt;
+        }
+    }
+    if (t < T) {
+        const int64_t o = (int64_t)t * outW + w;
+        wll[o * 3 + 0] = a0;
+        wll[o * 3 + 1] = a1;
+        wll[o * 3 + 2] = a2;
+        wn[o] = n;
+        ws[o] = pos[s0];
+        we[o] = pos[s1];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K_COUNTERS: processed / skipped / final coverage histogram per target (src/ibdgem.c:537-545,
-// 585-630, 734, 761-768).  One block per row; integer atomics only, so the result is exact.
+// 585-630, 734, 761-768).  grid = (site chunks, rows); shared-memory histogram per block, then
+// 64-bit integer atomics into the row's (pre-zeroed) counters, so the result is exact.
+constexpr int COUNTERS_CHUNK = 8192;
 __global__ void __launch_bounds__(256)
 counters_kernel(SiteView v, const int32_t *__restrict__ targets, int C,
                 unsigned long long *__restrict__ out /*[rows][C+3]*/) {
-    const int t = blockIdx.x;
+    const int t = blockIdx.y;
     const int indiv = targets ? targets[t] : 0;
     extern __shared__ unsigned long long sh[];  // [C+3]
     for (int i = threadIdx.x; i < C + 3; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     unsigned long long proc = 0, skip = 0, cov = 0;
-    for (int64_t s = threadIdx.x; s < v.S; s += blockDim.x) {
+    const int64_t s_begin = (int64_t)blockIdx.x * COUNTERS_CHUNK;
+    const int64_t s_end = min(v.S, s_begin + COUNTERS_CHUNK);
+    for (int64_t s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
         int r = 0, a = 0, g = 0;
         const int st = site_eval(v, t, indiv, s, r, a, g);
         if (st == 0) {
@@ -384,7 +458,8 @@ counters_kernel(SiteView v, const int32_t *__restrict__ targets, int C,
     atomicAdd(&sh[1], skip);
     atomicAdd(&sh[2], cov);
     __syncthreads();
-    for (int i = threadIdx.x; i < C + 3; i += blockDim.x) out[(int64_t)t * (C + 3) + i] = sh[i];
+    for (int i = threadIdx.x; i < C + 3; i += blockDim.x)
+        if (sh[i]) atomicAdd(&out[(int64_t)t * (C + 3) + i], sh[i]);
 }
 
 // K_EXPAND_SITES: the LIBD0/LIBD1/LIBD2 columns of every tab.txt row (src/ibdgem.c:641-663,
@@ -1041,9 +1116,14 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     } else {
         {
             LaunchScope ls(e, K_WINDOW_NONLD);
-            const int64_t warps = (int64_t)nWT;
-            window_nonld_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
-                v, m, d_targets, T, e->d_pos, e->d_f, e->d_lnlik7, e->d_P, C, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
+            if (shared) {
+                window_nonld_shared_kernel<<<dim3((unsigned)std::max(e->nW_shared, 1), (unsigned)((T + 127) / 128)), 128, 0, e->stream>>>(
+                    v, m, d_targets, T, e->d_pos, e->d_status, e->d_lnlik7, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
+            } else {
+                const int64_t warps = (int64_t)nWT;
+                window_nonld_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
+                    v, m, d_targets, T, e->d_pos, e->d_f, e->d_lnlik7, e->d_P, C, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
+            }
         }
         IBD_CUDA(cudaGetLastError());
     }
@@ -1097,8 +1177,10 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     const int crows = shared ? 1 : T;
     if (want_counters) {
         if (scratch(e, SC_COUNTERS, (size_t)crows * crow * 8, (void **)&d_cnt)) return 1;
+        IBD_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)crows * crow * 8, e->stream));
         LaunchScope ls(e, K_COUNTERS);
-        counters_kernel<<<crows, 256, (size_t)crow * 8, e->stream>>>(v, shared ? nullptr : d_targets, C, d_cnt);
+        counters_kernel<<<dim3((unsigned)((S + COUNTERS_CHUNK - 1) / COUNTERS_CHUNK), crows), 256, (size_t)crow * 8, e->stream>>>(
+            v, shared ? nullptr : d_targets, C, d_cnt);
     }
     // expanded per-site outputs
     uint8_t *d_st = nullptr;

@@ -45,7 +45,10 @@ enum KernelId {
     K_LD_WINDOWS,       // tensor path: window bookkeeping + LIBD2
     K_LD_IBD0,          // tensor path: LIBD0 log-mean-exp with exclusion by omission
     K_LD_MMA,           // tensor path: tcgen05 window GEMM + fused log-sum-exp epilogue -> LIBD1
-    K_VITERBI,          // H1-H3 batched hiddengem
+    K_VITERBI,          // H2 hiddengem forward pass (or the whole per-table kernel for small batches)
+    K_VITERBI_NORM,     // H1 ln of the normalised likelihoods, to bin-major
+    K_VITERBI_BACK,     // H3 back-trace + state counts
+    K_VITERBI_OUT,      // scores / states back to table-major
     K_FILL,             // NaN fill of device score buffers
     K_COUNT
 };
@@ -136,7 +139,7 @@ int resolve_timers(ibdgem_engine *e);
 enum ScratchSlot {
     SC_TARGETS = 0, SC_BG, SC_TGT_COUNTS, SC_BLOCKCNT, SC_WFIRST, SC_WLAST, SC_NWIN, SC_KTOT, SC_WLL,
     SC_WN, SC_WS, SC_WE, SC_COUNTERS, SC_SITE_STATUS, SC_SITE_LIK, SC_LD_PART, SC_NREFPANEL,
-    SC_HG_LIK, SC_HG_OFF, SC_HG_STATE, SC_HG_SCORE, SC_HG_COUNTS,
+    SC_HG_LIK, SC_HG_OFF, SC_HG_STATE, SC_HG_SCORE, SC_HG_COUNTS, SC_HG_NRMT, SC_HG_SCORET, SC_HG_FROMT, SC_HG_LAST,
     SC_MMA_TGT, SC_MMA_BG, SC_MMA_ROWLSE, SC_MMA_BGIDX, SC_MMA_MISC, SC_SLOTS
 };
 int scratch(ibdgem_engine *e, int slot, size_t bytes, void **out);
