@@ -44,7 +44,7 @@ def launches(path):
         a = agg.setdefault(n, [0, 0.0])
         a[0] += 1
         a[1] += float(r["Metric Value"].replace(",", ""))
-    ours = {k: v for k, v in agg.items() if "ibdgem" in k or "mma::" in k}
+    ours = {k: v for k, v in agg.items() if "native::" not in k and "at::" not in k and "elementwise" not in k}
     tot = sum(v[1] for v in ours.values())
     print("| kernel | launches | total ms | ms / launch | share of engine kernels |")
     print("|---|---|---|---|---|")
