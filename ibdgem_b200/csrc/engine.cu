@@ -127,7 +127,7 @@ __global__ void fill_nan_kernel(double *p, int64_t n) {
 // lane: the AF-range and max-cov filters (src/ibdgem.c:616-626), IBD0, IBD1|g, IBD2|g
 // (src/ibd-math.c:84-142, src/ibdgem.c:632-651) and their logs.
 __global__ void __launch_bounds__(256)
-site_table_kernel(int64_t S, int32_t N, int64_t Wh, const uint32_t *__restrict__ bits,
+site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint32_t *__restrict__ bits,
                   const uint8_t *__restrict__ hostkeep, const uint8_t *__restrict__ nref,
                   const uint8_t *__restrict__ nalt, const double *__restrict__ afuser,
                   const double *__restrict__ Ptab, int C, double min_af, double max_af, int max_cov,
@@ -140,7 +140,7 @@ site_table_kernel(int64_t S, int32_t N, int64_t Wh, const uint32_t *__restrict__
     const int nfull = H >> 5, rem = H & 31;
     const bool vec4 = ((Wh & 3) == 0);
     const int n4 = vec4 ? (nfull >> 2) : 0;
-    for (int64_t s0 = warp0 * 32; s0 < S; s0 += nwarps * 32) {
+    for (int64_t s0 = s_begin + warp0 * 32; s0 < S; s0 += nwarps * 32) {  // S = exclusive end of the range
         const int rows = (int)min((int64_t)32, S - s0);
         int mycnt = 0;
         for (int r = 0; r < rows; r++) {
@@ -188,6 +188,20 @@ site_table_kernel(int64_t S, int32_t N, int64_t Wh, const uint32_t *__restrict__
             status[s] = k ? ((r + a >= 1) ? 1 : 2) : 0;
         }
     }
+}
+
+// Site status without the panel: when no -A table is given and the AF range is the default [0, 1]
+// the AF filter of src/ibdgem.c:616 cannot fire (f = count / 2N), so keep / status follow from the
+// site arrays alone and the window map can be built before the panel has arrived.
+__global__ void __launch_bounds__(256)
+site_status_kernel(int64_t S, const uint8_t *__restrict__ hostkeep, const uint8_t *__restrict__ nref,
+                   const uint8_t *__restrict__ nalt, int max_cov, uint8_t *__restrict__ keep, uint8_t *__restrict__ status) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int r = nref[s], a = nalt[s];
+    const bool k = hostkeep[s] && (r + a <= max_cov);
+    keep[s] = k ? 1 : 0;
+    status[s] = k ? ((r + a >= 1) ? 1 : 2) : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -666,6 +680,30 @@ __global__ void ld_finalize_kernel(const LdPartial *__restrict__ part, int nz, W
     wll[i * 3 + 1] = M1 + log(S1) - log(4.0 * (double)nr);
 }
 
+int wait_panel_upto(ibdgem_engine *e, int64_t s_end) {
+    while (e->chunks_waited < (int)e->chunk_end.size() &&
+           (e->chunks_waited == 0 || e->chunk_end[(size_t)e->chunks_waited - 1] < s_end)) {
+        IBD_CUDA(cudaStreamWaitEvent(e->stream, e->chunk_ev[(size_t)e->chunks_waited], 0));
+        e->chunks_waited++;
+    }
+    return 0;
+}
+
+int ensure_table(ibdgem_engine *e, int64_t s_end) {
+    if (wait_panel_upto(e, s_end)) return 1;
+    if (e->table_upto >= s_end) return 0;
+    {
+        LaunchScope ls(e, K_SITE_TABLE);
+        const int64_t n = s_end - e->table_upto;
+        site_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+            e->table_upto, s_end, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C,
+            e->prm.min_af, e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7, e->d_lnlik7);
+    }
+    IBD_CUDA(cudaGetLastError());
+    e->table_upto = s_end;
+    return 0;
+}
+
 }  // namespace ibdgem
 
 using namespace ibdgem;
@@ -845,6 +883,9 @@ int ibdgem_engine_destroy(ibdgem_engine *e) {
             delete b;
         }
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
+    for (auto ev : e->chunk_ev) cudaEventDestroy(ev);
+    if (e->ev_order) cudaEventDestroy(e->ev_order);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
     return 0;
 }
@@ -913,11 +954,44 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
         if (dev_alloc(e, (void **)&e->d_bits, (size_t)n_sites * words_per_site * 4)) return 1;
     }
     e->N = n_indiv;
-    IBD_CUDA(cudaMemcpyAsync(e->d_bits, bits, (size_t)n_sites * words_per_site * 4, cudaMemcpyHostToDevice,
-                             e->stream));
+    // chunked copy on the copy stream, ordered after whatever the engine stream still reads from d_bits
+    if (!e->copy_stream) {
+        IBD_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        IBD_CUDA(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
+    }
+    // Few, equal chunks: every chunk is a separate (less efficient) round of launches, and the copy
+    // engine competes with the scoring kernels for HBM, so finer pipelining measured slower
+    // (end-to-end C3 step: 4 chunks 15.5 ms, 8: 15.8, 16: 18.2, 24: 21.1; unpipelined 22.5).
+    const int nchunk = n_sites >= PANEL_CHUNKS * PANEL_CHUNK_MIN ? PANEL_CHUNKS : 1;
+    while ((int)e->chunk_ev.size() < nchunk) {
+        cudaEvent_t ev;
+        IBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->chunk_ev.push_back(ev);
+    }
+    IBD_CUDA(cudaEventRecord(e->ev_order, e->stream));
+    IBD_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_order, 0));
+    e->chunk_end.assign((size_t)nchunk, 0);
+    const int64_t per = (n_sites + nchunk - 1) / nchunk;
+    for (int k = 0; k < nchunk; k++) {
+        const int64_t s0 = (int64_t)k * per, s1 = std::min<int64_t>(n_sites, s0 + per);
+        IBD_CUDA(cudaMemcpyAsync(e->d_bits + (size_t)s0 * words_per_site, bits + (size_t)s0 * words_per_site,
+                                 (size_t)(s1 - s0) * words_per_site * 4, cudaMemcpyHostToDevice, e->copy_stream));
+        IBD_CUDA(cudaEventRecord(e->chunk_ev[(size_t)k], e->copy_stream));
+        e->chunk_end[(size_t)k] = s1;
+    }
+    e->chunks_waited = 0;
     e->have_panel = true;
     e->prepared = false;
+    e->table_upto = 0;
     ld_tensor_invalidate(e);
+    return 0;
+}
+
+int ibdgem_engine_sync_uploads(ibdgem_engine *e) {
+    if (!e) return 1;
+    IBD_CUDA(cudaSetDevice(e->device));
+    if (e->copy_stream) IBD_CUDA(cudaStreamSynchronize(e->copy_stream));
+    IBD_CUDA(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
@@ -976,18 +1050,23 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
             dev_alloc(e, (void **)&e->d_nwin_shared, 4) || dev_alloc(e, (void **)&e->d_ktot_shared, 8))
             return 1;
     }
-    {
+    e->table_upto = 0;
+    // With no -A table and the default AF range the filter verdicts do not depend on the panel:
+    // the window map is built from the site arrays at once, and the per-site table (which reads the
+    // panel) is evaluated chunk by chunk as the rows arrive (ensure_table).
+    e->lazy_table = !e->d_afuser && e->prm.min_af <= 0.0 && e->prm.max_af >= 1.0;
+    if (e->lazy_table) {
         LaunchScope ls(e, K_SITE_TABLE);
-        const int blocks = (int)((S + 255) / 256);  // one batch of 32 panel lines per warp
-        site_table_kernel<<<blocks, 256, 0, e->stream>>>(
-            S, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C,
-            e->prm.min_af, e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7,
-            e->d_lnlik7);
+        site_status_kernel<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(S, e->d_hostkeep, e->d_nref, e->d_nalt,
+                                                                              (int)e->prm.max_cov, e->d_keep, e->d_status);
+    } else if (ensure_table(e, S)) {
+        return 1;
     }
     IBD_CUDA(cudaGetLastError());
     int32_t *d_nwin = e->d_nwin_shared;
     int64_t *d_ktot = e->d_ktot_shared;
     SiteView v = make_view(e, nullptr, 0);
+    v.bits = nullptr;  // the shared map (vflag = 0, no per-target counts) never looks at genotypes
     if (build_window_map(e, v, nullptr, 1, maxW, e->d_wfirst, e->d_wlast, d_nwin, d_ktot, e->d_rank)) return 1;
     int32_t nwin = 0;
     int64_t ktot = 0;
@@ -996,6 +1075,11 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     IBD_CUDA(cudaStreamSynchronize(e->stream));
     e->nW_shared = nwin;
     e->K_shared = ktot;
+    e->h_wlast.assign((size_t)std::max(nwin, 0), 0);
+    if (nwin > 0) {
+        IBD_CUDA(cudaMemcpyAsync(e->h_wlast.data(), e->d_wlast, (size_t)nwin * 8, cudaMemcpyDeviceToHost, e->stream));
+        IBD_CUDA(cudaStreamSynchronize(e->stream));
+    }
     e->prepared = true;
     ld_tensor_invalidate(e);
     resolve_timers(e);
@@ -1005,13 +1089,14 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
 int ibdgem_engine_invalidate(ibdgem_engine *e) {
     if (!e) return 1;
     e->prepared = false;
+    e->table_upto = 0;
     ld_tensor_invalidate(e);
     return 0;
 }
 
 int ibdgem_engine_get_site_table(ibdgem_engine *e, double *f, uint8_t *status, double *lik7) {
     if (!e) return 1;
-    if (ibdgem_engine_prepare(e)) return 1;
+    if (ibdgem_engine_prepare(e) || ensure_table(e, e->S)) return 1;
     IBD_CUDA(cudaSetDevice(e->device));
     if (f) IBD_CUDA(cudaMemcpyAsync(f, e->d_f, (size_t)e->S * 8, cudaMemcpyDeviceToHost, e->stream));
     if (status) IBD_CUDA(cudaMemcpyAsync(status, e->d_status, (size_t)e->S, cudaMemcpyDeviceToHost, e->stream));
@@ -1109,6 +1194,9 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     IBD_CUDA(cudaMemsetAsync(d_ws, 0, nWT * 8, e->stream));
     IBD_CUDA(cudaMemsetAsync(d_we, 0, nWT * 8, e->stream));
     const bool tensor = ld && !e->force_general && shared && ld_tensor_eligible(e, T, n_bg, tgt_counts);
+    // everything but the tensor path reads the per-site table and the whole panel up front; the
+    // tensor path asks for them window range by window range (upload / scoring overlap)
+    if (!tensor && ensure_table(e, S)) return 1;
     if (tensor) {
         // tensor path: fills window bookkeeping, LIBD0, LIBD1 and LIBD2 of every target
         if (ld_tensor_score(e, T, targets, d_targets, n_bg, bg, pu_idx, outW, d_wll, d_wn, d_ws, d_we, d_nwout)) return 1;
@@ -1170,6 +1258,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         }
     }
 
+    if (ensure_table(e, S)) return 1;  // no-op unless the tensor path left a tail
     // counters
     const bool want_counters = out->processed || out->skipped || out->final_total_cov || out->final_dist;
     unsigned long long *d_cnt = nullptr;

@@ -93,6 +93,17 @@ struct ibdgem_engine {
     uint32_t *d_bits = nullptr;
     bool have_sites = false, have_panel = false, prepared = false;
 
+    // The panel is copied in site chunks on its own stream; the engine stream waits for a chunk only
+    // when a kernel needs its rows, so scoring of the first windows overlaps the rest of the upload.
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_order = nullptr;          // engine stream -> copy stream ordering
+    std::vector<cudaEvent_t> chunk_ev;       // one per chunk, recorded on copy_stream
+    std::vector<int64_t> chunk_end;          // exclusive site end of each chunk
+    int chunks_waited = 0;                   // chunks the engine stream already depends on
+    int64_t table_upto = 0;                  // site_table has run on [0, table_upto)
+    bool lazy_table = false;                 // status does not need the panel (no -A, AF range [0, 1])
+    std::vector<int64_t> h_wlast;            // host copy of the shared window map (last site per window)
+
     // prepared, target-independent
     double *d_f = nullptr;
     uint8_t *d_keep = nullptr;    // passes every target-independent filter
@@ -144,6 +155,11 @@ enum ScratchSlot {
 };
 int scratch(ibdgem_engine *e, int slot, size_t bytes, void **out);
 
+// Makes the engine stream wait for the panel chunks that cover sites [0, s_end); ensure_table also
+// runs site_table on the part of [0, s_end) it has not covered yet.
+int wait_panel_upto(ibdgem_engine *e, int64_t s_end);
+int ensure_table(ibdgem_engine *e, int64_t s_end);
+
 int dev_alloc(ibdgem_engine *e, void **p, size_t bytes);
 void dev_free(ibdgem_engine *e, void *p, size_t bytes);
 
@@ -154,6 +170,8 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
                     const int32_t *h_bg, int32_t pu_idx, int32_t outW, double *d_wll /*[T][outW][3]*/, int32_t *d_wn,
                     uint64_t *d_ws, uint64_t *d_we, int32_t *d_nwout);
 void ld_tensor_release(ibdgem_engine *e);
+constexpr int PANEL_CHUNKS = 4;          // upload / scoring pipeline depth
+constexpr int64_t PANEL_CHUNK_MIN = 32768;  // sites; smaller panels go up in one piece
 void ld_tensor_invalidate(ibdgem_engine *e);
 
 }  // namespace ibdgem

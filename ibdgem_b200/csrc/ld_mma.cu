@@ -34,7 +34,8 @@ namespace ibdgem {
 // ---------------------------------------------------------------------------------------------
 // cached, target-independent operands
 struct LdCache {
-    bool valid = false;
+    bool valid = false;       // per-site operands (slots, depths, C0) are current
+    int tw_upto = 0;          // windows [0, tw_upto) have their transposed bits and marginals
     int32_t nW = 0;
     int64_t K = 0;
     int W = 0, Wpad = 0, WP32 = 0, KB = 0;
@@ -277,7 +278,7 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
 // the counts), and for each individual  Q_w[b] = C0 + R[r0] + R[r1] + kappa sum n r0 r1.
 constexpr int LD_PLANES = 7;  // counts are <= 127 (IBDGEM_MAX_COV_LIMIT)
 __global__ void __launch_bounds__(1024)
-ld_transpose_kernel(const uint32_t *__restrict__ bits, int64_t Wh, int H, const int32_t *__restrict__ infsite,
+ld_transpose_kernel(int w_off, const uint32_t *__restrict__ bits, int64_t Wh, int H, const int32_t *__restrict__ infsite,
                     const uint8_t *__restrict__ nref, const uint8_t *__restrict__ nalt, int Wpad, int WP32, int nbits,
                     const double *__restrict__ C0, double alpha, double beta, double kappa, uint32_t *__restrict__ tbits,
                     double *__restrict__ Rw, double *__restrict__ Qw) {
@@ -285,7 +286,7 @@ ld_transpose_kernel(const uint32_t *__restrict__ bits, int64_t Wh, int H, const 
     __shared__ uint32_t planes[3][LD_PLANES][32];
     // the word-column group is the fastest grid dimension: the blocks that share a window's panel rows
     // run together, so every 32-byte piece of a row is fetched from HBM once
-    const int w = blockIdx.y, j0 = blockIdx.x * 8;
+    const int w = w_off + blockIdx.y, j0 = blockIdx.x * 8;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     if (g < WP32) {
         const int32_t s = infsite[(size_t)w * Wpad + g * 32 + lane];
@@ -338,11 +339,11 @@ ld_transpose_kernel(const uint32_t *__restrict__ bits, int64_t Wh, int H, const 
 
 // screening keys and R'[k] = R[k] + ln(multiplicity) for every background haplotype column
 __global__ void __launch_bounds__(256)
-ld_tables_kernel(int nW, int ncols, int ncolpad, int H, const int32_t *__restrict__ bgU, const double *__restrict__ lnc,
+ld_tables_kernel(int w_lo, int w_hi, int ncols, int ncolpad, int H, const int32_t *__restrict__ bgU, const double *__restrict__ lnc,
                  const double *__restrict__ Rw, const double *__restrict__ Qw, double inv_abs_kappa,
                  int32_t *__restrict__ akey, double *__restrict__ Rp, double *__restrict__ Qp) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)nW * ncolpad) return;
+    const int64_t i = (int64_t)w_lo * ncolpad + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)w_hi * ncolpad) return;
     const int w = (int)(i / ncolpad), c = (int)(i % ncolpad);
     if (c < ncols) {
         const int u = c >> 1, ind = bgU[u];
@@ -400,13 +401,15 @@ ld_expand_tgt_kernel(int64_t total, int w0, int nrows, int H, int Wpad, int WP32
 
 // window bookkeeping (W2) and LIBD2 = Q_w[target] for every (target, window)
 __global__ void __launch_bounds__(256)
-ld_windows_kernel(int T, int nW, int outW, int W, int64_t K, const int32_t *__restrict__ targets, int Nind,
+ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K, const int32_t *__restrict__ targets, int Nind,
                   const int64_t *__restrict__ wfirst, const int64_t *__restrict__ wlast, const uint64_t *__restrict__ pos,
                   const double *__restrict__ Qw, double *__restrict__ wll, int32_t *__restrict__ wn,
                   uint64_t *__restrict__ ws, uint64_t *__restrict__ we, int32_t *__restrict__ nwout) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)T * outW) return;
-    const int t = (int)(i / outW), w = (int)(i % outW);
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int span = w_hi - w_lo;
+    if (j >= (int64_t)T * span) return;
+    const int t = (int)(j / span), w = w_lo + (int)(j % span);
+    const int64_t i = (int64_t)t * outW + w;
     if (w == 0) nwout[t] = nW;
     if (w >= nW) return;
     wll[i * 3 + 2] = Qw[(size_t)w * Nind + targets[t]];
@@ -420,11 +423,11 @@ ld_windows_kernel(int T, int nW, int outW, int W, int64_t K, const int32_t *__re
 // subtracted).  One block per window; 64 chunk partials so an omission re-scans one chunk only.
 constexpr int IBD0_CHUNKS = 64;
 __global__ void __launch_bounds__(256)
-ld_ibd0_kernel(int T, int nU, int outW, const double *__restrict__ Qp, const int32_t *__restrict__ ownU,
+ld_ibd0_kernel(int w_off, int T, int nU, int outW, const double *__restrict__ Qp, const int32_t *__restrict__ ownU,
                const double *__restrict__ lognb, double *__restrict__ wll) {
     __shared__ double cm[IBD0_CHUNKS], cs[IBD0_CHUNKS];
     __shared__ double tot_m, tot_s;
-    const int w = blockIdx.x;
+    const int w = w_off + blockIdx.x;
     const double *q = Qp + (size_t)w * nU;
     const int clen = (nU + IBD0_CHUNKS - 1) / IBD0_CHUNKS;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1120,21 +1123,35 @@ static int build_cache(ibdgem_engine *e) {
         LaunchScope ls(e, K_LD_C0);
         ld_c0_kernel<<<c->nW, 256, 0, e->stream>>>(c->d_l0, c->Wpad, c->d_C0);
     }
+    IBD_CUDA(cudaGetLastError());
+    c->valid = true;
+    c->tw_upto = 0;
+    return 0;
+}
+
+// Transposed bits and marginals of windows [tw_upto, w_hi).  The caller has made the engine stream
+// wait for the panel rows of those windows (wait_panel_upto / ensure_table).
+static int cache_windows(ibdgem_engine *e, int w_hi) {
+    LdCache *c = e->ld;
+    if (c->tw_upto >= w_hi) return 0;
     {
         LaunchScope ls(e, K_LD_TRANSPOSE);
         const int words = (c->H + 31) / 32;
         int nbits = 1;
         while ((1 << nbits) <= (int)e->prm.max_cov) nbits++;
-        ld_transpose_kernel<<<dim3((words + 7) / 8, c->nW), 1024, 0, e->stream>>>(
-            e->d_bits, e->Wh, c->H, c->d_infsite, e->d_nref, e->d_nalt, c->Wpad, c->WP32, nbits, c->d_C0, e->alpha, e->beta,
-            e->kappa, c->d_tbits, c->d_Rw, c->d_Qw);
+        ld_transpose_kernel<<<dim3((words + 7) / 8, w_hi - c->tw_upto), 1024, 0, e->stream>>>(
+            c->tw_upto, e->d_bits, e->Wh, c->H, c->d_infsite, e->d_nref, e->d_nalt, c->Wpad, c->WP32, nbits, c->d_C0, e->alpha,
+            e->beta, e->kappa, c->d_tbits, c->d_Rw, c->d_Qw);
     }
     IBD_CUDA(cudaGetLastError());
-    c->valid = true;
+    c->tw_upto = w_hi;
     return 0;
 }
 
-int ld_tensor_prepare(ibdgem_engine *e) { return build_cache(e); }
+int ld_tensor_prepare(ibdgem_engine *e) {
+    if (build_cache(e) || ensure_table(e, e->S)) return 1;
+    return cache_windows(e, e->ld->nW);
+}
 
 // Fills every window output of the call: d_wll [T][outW][3], d_wn, d_ws, d_we [T][outW], d_nwout [T].
 int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const int32_t *d_targets, int32_t n_bg,
@@ -1174,14 +1191,27 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         }
     }
     const int nW = c->nW;
-    {
-        LaunchScope ls(e, K_LD_WINDOWS);
-        const int64_t n = (int64_t)T * outW;
-        ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-            T, nW, outW, c->W, c->K, d_targets, c->N, e->d_wfirst, e->d_wlast, e->d_pos, c->d_Qw, d_wll, d_wn, d_ws, d_we,
-            d_nwout);
+    // Window ranges: one per panel chunk still in flight (a range is the windows whose last site has
+    // arrived), so the scoring of early windows overlaps the rest of the upload; a single range when
+    // the panel is already resident.
+    std::vector<int> range_end;
+    if (e->chunks_waited < (int)e->chunk_end.size() && e->chunk_end.size() > 1 && c->tw_upto == 0) {
+        int w = 0;
+        for (size_t k = 0; k < e->chunk_end.size(); k++) {
+            while (w < nW && e->h_wlast[(size_t)w] < e->chunk_end[k]) w++;
+            range_end.push_back(k + 1 == e->chunk_end.size() ? nW : w);
+        }
+    } else {
+        range_end.push_back(nW);
     }
+    auto range_sites = [&](size_t k) { return range_end.size() == 1 ? e->S : e->chunk_end[k]; };
     if (nU == 0) {  // every background member excluded: LIBD0 = LIBD1 = 0/0 (d_wll is NaN-filled)
+        if (ensure_table(e, e->S) || cache_windows(e, nW)) return 1;
+        LaunchScope ls(e, K_LD_WINDOWS);
+        const int64_t n = (int64_t)T * nW;
+        ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+            0, nW, T, nW, outW, c->W, c->K, d_targets, c->N, e->d_wfirst, e->d_wlast, e->d_pos, c->d_Qw, d_wll, d_wn, d_ws, d_we,
+            d_nwout);
         IBD_CUDA(cudaGetLastError());
         return 0;
     }
@@ -1222,20 +1252,33 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     IBD_CUDA(cudaMemcpyAsync(d_rowown, row_own.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     // the host vectors above are pageable: the copies are staged before these calls return
 
+    int w_lo = 0;
+    for (size_t rk = 0; rk < range_end.size(); rk++) {
+    const int w_hi = range_end[rk];
+    if (ensure_table(e, range_sites(rk))) return 1;  // waits for the chunk, evaluates its per-site table
+    if (w_hi == w_lo) continue;
+    if (cache_windows(e, w_hi)) return 1;
+    {
+        LaunchScope ls(e, K_LD_WINDOWS);
+        const int64_t n = (int64_t)T * (w_hi - w_lo);
+        ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+            w_lo, w_hi, T, nW, outW, c->W, c->K, d_targets, c->N, e->d_wfirst, e->d_wlast, e->d_pos, c->d_Qw, d_wll, d_wn, d_ws,
+            d_we, d_nwout);
+    }
     {
         LaunchScope ls(e, K_LD_TABLES);
-        const int64_t n = (int64_t)nW * ncolpad;
-        ld_tables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(nW, ncols, ncolpad, c->H, d_bgU, d_lnc, c->d_Rw,
+        const int64_t n = (int64_t)(w_hi - w_lo) * ncolpad;
+        ld_tables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(w_lo, w_hi, ncols, ncolpad, c->H, d_bgU, d_lnc, c->d_Rw,
                                                                              c->d_Qw, 1.0 / -e->kappa, d_akey, d_Rp, d_Qp);
     }
     {
         LaunchScope ls(e, K_LD_IBD0);
-        ld_ibd0_kernel<<<nW, 256, 0, e->stream>>>(T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll);
+        ld_ibd0_kernel<<<w_hi - w_lo, 256, 0, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll);
     }
     IBD_CUDA(cudaGetLastError());
     // windows are processed in batches so the expanded int8 operands stay within a fixed budget
-    for (int w0 = 0; w0 < nW; w0 += nWb) {
-        const int nw = std::min(nWb, nW - w0);
+    for (int w0 = w_lo; w0 < w_hi; w0 += nWb) {
+        const int nw = std::min(nWb, w_hi - w0);
         {
             LaunchScope ls(e, K_LD_EXPAND_BG);
             const int64_t n = (int64_t)nw * ncols * c->WP32;
@@ -1297,6 +1340,8 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             cudaFree(d_trace);
         }
     }
+    w_lo = w_hi;
+    }  // window ranges
     IBD_CUDA(cudaGetLastError());
     return 0;
 }

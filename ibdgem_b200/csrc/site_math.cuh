@@ -58,7 +58,7 @@ struct SiteView {
     const uint8_t *keep;       // [S] target-independent filters (incl. max-cov on original counts)
     const uint8_t *nref;       // [S]
     const uint8_t *nalt;       // [S]
-    const uint32_t *bits;      // [S][Wh]
+    const uint32_t *bits;      // [S][Wh]; may be NULL for a target-independent pass (vflag = 0)
     int64_t Wh;
     int64_t S;
     const uint8_t *tgt_counts; // NULL or [T][S][2]
@@ -68,7 +68,7 @@ struct SiteView {
 __device__ __forceinline__ int site_eval(const SiteView &v, int tslot, int indiv, int64_t s, int &r,
                                          int &a, int &g) {
     if (!v.keep[s]) return 0;
-    const uint32_t pr = hap_pair(v.bits + s * v.Wh, indiv);
+    const uint32_t pr = v.bits ? hap_pair(v.bits + s * v.Wh, indiv) : 0u;  // bits == NULL: genotype not needed
     g = (int)(pr & 1u) + (int)(pr >> 1);
     if (v.vflag && g == 0) return 0;  // src/ibdgem.c:584-587
     if (v.tgt_counts) {

@@ -114,6 +114,9 @@ class Engine:
         self._check(self._lib.ibdgem_engine_upload_panel(self._h, C.c_int64(bits.shape[0]), C.c_int32(n_indiv),
                                                          _ptr(bits), C.c_int64(bits.shape[1])))
 
+    def sync_uploads(self):
+        self._check(self._lib.ibdgem_engine_sync_uploads(self._h))
+
     def prepare(self):
         self._check(self._lib.ibdgem_engine_prepare(self._h))
 

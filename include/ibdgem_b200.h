@@ -99,6 +99,12 @@ int ibdgem_engine_upload_sites(ibdgem_engine *e, int64_t n_sites, const uint64_t
  * bits zero.  Replaces the per-target re-read of the .hap file (src/ibdgem.c:573, 771). */
 int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indiv,
                                const uint32_t *bits, int64_t words_per_site);
+/* The panel copy is issued in site chunks on the engine's copy stream and may still be in flight
+ * when upload_panel returns: `bits` must stay valid and unchanged until the next call on this engine
+ * that returns results (prepare / get_site_table / score_* all wait for what they read), or until
+ * ibdgem_engine_sync_uploads().  With page-locked `bits` the copy overlaps the scoring of the windows
+ * whose rows have already arrived; with pageable memory it is simply complete on return. */
+int ibdgem_engine_sync_uploads(ibdgem_engine *e);
 
 /* Target-independent stage: allele frequency by popcount over the packed row (find_f_impute /
  * find_f_vcf, src/ibd-parse.c:91-110), the AF-range and max-cov filters (src/ibdgem.c:616-626),
