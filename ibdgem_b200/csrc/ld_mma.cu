@@ -497,6 +497,13 @@ constexpr int A_SLAB = BM * KBYTES;   // 16 KB
 constexpr int B_SLAB = BN * KBYTES;   // 16 KB
 constexpr int EPI_WARP0 = 4;
 constexpr int NSETS = 4;              // epilogue warp sets of 4 warps (one warp per TMEM lane quarter)
+// Units are handed out dynamically (an atomic counter): CTA pairs differ by ~15 % in speed (the two
+// dies), and pairs that pick up neighbouring units — the row blocks of one window — stream the same
+// background tiles at the same time, which is what lets L2 serve them.  The number travels to every
+// role of both CTAs through a ring in shared memory.  No "empty" barriers: the producer is at most one
+// unit ahead of the MMA issuer (operand rings), which is at most two tiles ahead of the epilogue
+// (accumulator slots), which is at most one unit ahead of the merge warps (bar 2) — 3 < URING.
+constexpr int URING = 8;
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 // CG = CTAs per MMA (tcgen05 cta_group).  CG = 2 pairs two SMs on one 256 x 256 tile: each CTA keeps
@@ -515,9 +522,10 @@ struct Cfg {
     static constexpr int OFF_MERGE = OFF_KEYS + NSETS * 4 * SETCOLS * 4;  // NSETS x 128 x double2: the sets' (max, sum) per row
     static constexpr int OFF_KMAX = OFF_MERGE + NSETS * BM * 16;          // 2 x 128 int32, shared by the sets
     static constexpr int OFF_BAR = OFF_KMAX + 2 * BM * 4;
-    static constexpr int NBAR = 2 * MAXKB + 2 * NSTAGE + 2 * NACC;
+    static constexpr int NBAR = 2 * MAXKB + 2 * NSTAGE + 2 * NACC + URING;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-    static constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;              // + alignment slack
+    static constexpr int OFF_URING = OFF_TMEM + 16;                      // URING unit numbers handed out by the scheduler
+    static constexpr int SMEM_BYTES = OFF_URING + URING * 4 + 1024;      // + alignment slack
     static constexpr uint32_t IDESC = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (0u << 10) /* B = u8 */ |
                                       ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
@@ -542,6 +550,7 @@ struct Params {
     double *wll;             // [T][outW][3]
     int debug;               // IBDGEM_MMA_DEBUG experiments (0 = product behaviour)
     int warm_tiles;          // leading tiles of a unit whose maximum is taken before they are screened
+    int *unit_counter;       // next unit to hand out (zeroed before the launch)
     unsigned long long *trace;  // IBDGEM_MMA_TRACE: [4][1024] event log of CTA 0 (nullptr = off)
 };
 // event log entry: clock64 << 16 | event << 12 | tile; one lane per traced warp writes
@@ -607,6 +616,42 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// wait with cluster-scope acquire: the ring entry may have been written by the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+    }
+}
+// unit number of iteration `it` for any role of either CTA (-1: no more units)
+__device__ __forceinline__ int unit_of(const int *uring, uint64_t *ufull, int it) {
+    mbar_wait_cluster(ufull + (it % URING), (uint32_t)((it / URING) & 1));
+    return *reinterpret_cast<const volatile int *>(uring + (it % URING));
+}
+// scheduler (producer lane of CTA 0): publish unit u for iteration `it` in both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void unit_publish(int *uring, uint64_t *ufull, int it, int u) {
+    const int i = it % URING;
+    *reinterpret_cast<volatile int *>(uring + i) = u;
+    asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(ufull + i)) : "memory");
+    if constexpr (CG == 2) {
+        uint32_t rdata, rbar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(rdata) : "r"(smem_u32(uring + i)));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, 1;" : "=r"(rbar) : "r"(smem_u32(ufull + i)));
+        asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(rdata), "r"(u) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+    }
+}
+
 template <class CF>
 __global__ void __launch_bounds__(CF::THREADS, 1)
 ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const Params p) {
@@ -621,19 +666,26 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     uint64_t *a_full = bars, *a_empty = bars + MAXKB;
     uint64_t *b_full = bars + 2 * MAXKB, *b_empty = b_full + NSTAGE;
     uint64_t *acc_full = b_empty + NSTAGE, *acc_empty = acc_full + NACC;
+    uint64_t *ufull = acc_empty + NACC;
+    int *uring = reinterpret_cast<int *>(smem + CF::OFF_URING);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t rank = 0;  // CTA rank in the pair; rank 0 issues the MMAs
     if constexpr (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int group0 = (int)(blockIdx.x / CG), ngroups = (int)(gridDim.x / CG);
 
+    if (p.trace && warp == 1 && lane == 0 && blockIdx.x < 256) {  // per-CTA start stamp (global timer, ns)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[3 * 1024 + blockIdx.x * 2] = t;
+    }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < MAXKB; i++) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+        for (int i = 0; i < URING; i++) mbar_init(ufull + i, 1);
         for (int i = 0; i < NSTAGE; i++) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * NSETS * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -661,8 +713,26 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         if (lane == 0) {
             int st = 0;
             uint32_t ph = 0;
-            int it = 0;
-            for (int u = group0; u < p.n_units; u += ngroups, it++) {
+            int u_next = -1;
+            auto fetch_unit = [&]() {
+                const int v = atomicAdd(p.unit_counter, 1);
+                return v < p.n_units ? v : -1;
+            };
+            if (rank == 0) {  // scheduler: CTA 0 of the pair draws the unit numbers for every role of both CTAs
+                u_next = fetch_unit();
+                unit_publish<CG>(uring, ufull, 0, u_next);
+            }
+            for (int it = 0;; it++) {
+                int u;
+                if (rank == 0) {
+                    u = u_next;
+                    if (u < 0) break;
+                    u_next = fetch_unit();  // one ahead, so the number is waiting when the roles get there
+                    unit_publish<CG>(uring, ufull, it + 1, u_next);
+                } else {
+                    u = unit_of(uring, ufull, it);
+                    if (u < 0) break;
+                }
                 const int w = u / p.MB, mb = u % p.MB;
                 auto load_a = [&](int kb) {
                     mbar_wait(a_empty + kb, (uint32_t)((it & 1) ^ 1));
@@ -695,7 +765,8 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             int tr_n = 0;
             const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + OFF_A));
             const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem + OFF_B));
-            for (int u = group0; u < p.n_units; u += ngroups, it++) {
+            for (;; it++) {
+                if (unit_of(uring, ufull, it) < 0) break;
                 for (int n = 0; n < p.NT; n++, g++) {
                     const bool first = n == 0, last = n == p.NT - 1;
                     const uint32_t acc = g % NACC, use = g / NACC;
@@ -756,7 +827,9 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         const double2 *mb_buf = reinterpret_cast<const double2 *>(smem + OFF_MERGE);
         const int r0 = (warp - 2) * 64 + lane * 2;  // first of the target's two rows within the CTA's 128
         asm volatile("bar.arrive 2, %0;" ::"n"(NSETS * 128 + 64) : "memory");  // buffer free for unit 0
-        for (int u = group0; u < p.n_units; u += ngroups) {
+        for (int it = 0;; it++) {
+            const int u = unit_of(uring, ufull, it);
+            if (u < 0) break;
             const int w = p.w0 + u / p.MB, mb = u % p.MB;
             const int row = (mb * CG + (int)rank) * BM + r0;
             const bool ok = row < p.nrows;  // nrows is even: both rows or neither
@@ -808,7 +881,9 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
         int it = 0;
         int tr_n = 0;
         const int tr_role = ew == 0 ? 1 : (ew == 15 ? 2 : 3);
-        for (int u = group0; u < p.n_units; u += ngroups, it++, g0 += (uint32_t)p.NT) {
+        for (;; it++, g0 += (uint32_t)p.NT) {
+            const int u = unit_of(uring, ufull, it);
+            if (u < 0) break;
             const int w = p.w0 + u / p.MB, mb = u % p.MB;
             const int row = (mb * CG + (int)rank) * BM + rloc;
             const bool row_ok = row < p.nrows;
@@ -952,6 +1027,11 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if (p.trace && warp == 1 && lane == 0 && blockIdx.x < 256) {  // per-CTA end stamp
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[3 * 1024 + blockIdx.x * 2 + 1] = t;
+    }
     if constexpr (CG == 2) cluster_sync_all();  // the peer's shared memory and barriers stay alive until both are done
     if (warp == 2) {
         tc_fence_after();
@@ -1315,6 +1395,12 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             static int wt = -1;
             if (wt < 0) { const char *sw = getenv("IBDGEM_MMA_WARM_TILES"); wt = sw ? atoi(sw) : 1; }
             p.warm_tiles = wt;
+        }
+        {
+            int *d_unit;
+            if (scratch(e, SC_MMA_UNIT, 64, (void **)&d_unit)) return 1;
+            IBD_CUDA(cudaMemsetAsync(d_unit, 0, 4, e->stream));
+            p.unit_counter = d_unit;
         }
         p.trace = nullptr;
         const char *trace_path = getenv("IBDGEM_MMA_TRACE");
