@@ -885,6 +885,7 @@ int ibdgem_engine_destroy(ibdgem_engine *e) {
     for (auto ev : e->event_pool) cudaEventDestroy(ev);
     for (auto ev : e->chunk_ev) cudaEventDestroy(ev);
     if (e->ev_order) cudaEventDestroy(e->ev_order);
+    if (e->ev_book) cudaEventDestroy(e->ev_book);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
     return 0;
@@ -1194,6 +1195,8 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     IBD_CUDA(cudaMemsetAsync(d_ws, 0, nWT * 8, e->stream));
     IBD_CUDA(cudaMemsetAsync(d_we, 0, nWT * 8, e->stream));
     const bool tensor = ld && !e->force_general && shared && ld_tensor_eligible(e, T, n_bg, tgt_counts);
+    e->book_ready = false;
+    if (tensor && e->copy_stream && !e->ev_book) IBD_CUDA(cudaEventCreateWithFlags(&e->ev_book, cudaEventDisableTiming));
     // everything but the tensor path reads the per-site table and the whole panel up front; the
     // tensor path asks for them window range by window range (upload / scoring overlap)
     if (!tensor && ensure_table(e, S)) return 1;
@@ -1287,9 +1290,16 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     if (out->w_loglik_device)
         IBD_CUDA(cudaMemcpyAsync(out->w_loglik_device, d_wll, nWT * 24, cudaMemcpyDeviceToDevice, e->stream));
     if (out->w_loglik) IBD_CUDA(cudaMemcpyAsync(out->w_loglik, d_wll, nWT * 24, cudaMemcpyDeviceToHost, e->stream));
-    if (out->w_nsites) IBD_CUDA(cudaMemcpyAsync(out->w_nsites, d_wn, nWT * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (out->w_start) IBD_CUDA(cudaMemcpyAsync(out->w_start, d_ws, nWT * 8, cudaMemcpyDeviceToHost, e->stream));
-    if (out->w_end) IBD_CUDA(cudaMemcpyAsync(out->w_end, d_we, nWT * 8, cudaMemcpyDeviceToHost, e->stream));
+    // the bookkeeping arrays of the tensor path are final before the GEMM starts: copy them on the
+    // copy stream so the transfer overlaps it
+    cudaStream_t bs = e->stream;
+    if (e->book_ready) {
+        IBD_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_book, 0));
+        bs = e->copy_stream;
+    }
+    if (out->w_nsites) IBD_CUDA(cudaMemcpyAsync(out->w_nsites, d_wn, nWT * 4, cudaMemcpyDeviceToHost, bs));
+    if (out->w_start) IBD_CUDA(cudaMemcpyAsync(out->w_start, d_ws, nWT * 8, cudaMemcpyDeviceToHost, bs));
+    if (out->w_end) IBD_CUDA(cudaMemcpyAsync(out->w_end, d_we, nWT * 8, cudaMemcpyDeviceToHost, bs));
     std::vector<int32_t> h_nw(T);
     IBD_CUDA(cudaMemcpyAsync(h_nw.data(), d_nwout, (size_t)T * 4, cudaMemcpyDeviceToHost, e->stream));
     std::vector<unsigned long long> h_cnt;
@@ -1300,6 +1310,8 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     if (out->site_status) IBD_CUDA(cudaMemcpyAsync(out->site_status, d_st, (size_t)T * S, cudaMemcpyDeviceToHost, e->stream));
     if (out->site_lik) IBD_CUDA(cudaMemcpyAsync(out->site_lik, d_sl, (size_t)T * S * 24, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->book_ready) IBD_CUDA(cudaStreamSynchronize(e->copy_stream));
+    e->book_ready = false;
     resolve_timers(e);
 
     for (int t = 0; t < T; t++) {

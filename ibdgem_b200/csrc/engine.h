@@ -97,6 +97,8 @@ struct ibdgem_engine {
     // when a kernel needs its rows, so scoring of the first windows overlaps the rest of the upload.
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_order = nullptr;          // engine stream -> copy stream ordering
+    cudaEvent_t ev_book = nullptr;           // window bookkeeping of the current call is final (tensor path)
+    bool book_ready = false;
     std::vector<cudaEvent_t> chunk_ev;       // one per chunk, recorded on copy_stream
     std::vector<int64_t> chunk_end;          // exclusive site end of each chunk
     int chunks_waited = 0;                   // chunks the engine stream already depends on

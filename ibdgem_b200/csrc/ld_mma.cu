@@ -424,11 +424,17 @@ ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K,
 constexpr int IBD0_CHUNKS = 64;
 __global__ void __launch_bounds__(256)
 ld_ibd0_kernel(int w_off, int T, int nU, int outW, const double *__restrict__ Qp, const int32_t *__restrict__ ownU,
-               const double *__restrict__ lognb, double *__restrict__ wll) {
+               const double *__restrict__ lognb, double *__restrict__ wll, int stage) {
+    extern __shared__ double qs[];
     __shared__ double cm[IBD0_CHUNKS], cs[IBD0_CHUNKS];
     __shared__ double tot_m, tot_s;
     const int w = w_off + blockIdx.x;
     const double *q = Qp + (size_t)w * nU;
+    if (stage) {
+        for (int u = threadIdx.x; u < nU; u += blockDim.x) qs[u] = __ldg(q + u);
+        __syncthreads();
+        q = qs;
+    }
     const int clen = (nU + IBD0_CHUNKS - 1) / IBD0_CHUNKS;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int c = wid; c < IBD0_CHUNKS; c += 8) {
@@ -1345,6 +1351,10 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             w_lo, w_hi, T, nW, outW, c->W, c->K, d_targets, c->N, e->d_wfirst, e->d_wlast, e->d_pos, c->d_Qw, d_wll, d_wn, d_ws,
             d_we, d_nwout);
     }
+    if (w_hi == nW && e->ev_book) {  // START / END / NUM_SITES of every window are final: their copy to the
+        IBD_CUDA(cudaEventRecord(e->ev_book, e->stream));  // host can overlap the GEMM (score_common)
+        e->book_ready = true;
+    }
     {
         LaunchScope ls(e, K_LD_TABLES);
         const int64_t n = (int64_t)(w_hi - w_lo) * ncolpad;
@@ -1353,7 +1363,15 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     }
     {
         LaunchScope ls(e, K_LD_IBD0);
-        ld_ibd0_kernel<<<w_hi - w_lo, 256, 0, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll);
+        // the window's Q' row is staged in shared memory when it fits (one bulk, coalesced load instead
+        // of latency-bound passes over global memory)
+        const size_t q_smem = (size_t)nU * 8 <= 160 * 1024 ? (size_t)nU * 8 : 0;
+        static bool attr_set = false;
+        if (!attr_set) {
+            IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set = true;
+        }
+        ld_ibd0_kernel<<<w_hi - w_lo, 256, q_smem, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
     }
     IBD_CUDA(cudaGetLastError());
     // windows are processed in batches so the expanded int8 operands stay within a fixed budget

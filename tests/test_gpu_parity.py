@@ -244,3 +244,40 @@ def test_c3_full_size_spot_checks_against_oracle():
             o = oracle.compare_target(prm, pos[sl], keep[sl], n_ref[sl], n_alt[sl], hap, int(t), bg)
             assert o["n_windows"] == 1
             np.testing.assert_allclose(sc.w_loglik[t, w], o["w_log"][0], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_hiddengem_batched_pipeline_vs_oracle(ragged):
+    """>= 64 tables take the four-kernel batched path (bin-major intermediates); states must be
+    bit-exact and scores within 1e-7 of the per-table oracle, for equal-length and ragged batches,
+    with zero and all-zero (NaN) rows."""
+    import ibdgem_b200 as ib
+    import oracle
+    rng = np.random.default_rng(12)
+    n_tables = 96
+    lens = rng.integers(700, 1000, n_tables) if ragged else np.full(n_tables, 777)
+    tables, offs = [], [0]
+    for k, n in enumerate(lens):
+        seg = np.repeat(rng.integers(0, 3, n // 40 + 1), 40)[:n]
+        l = np.exp(rng.normal(-20, 3, (n, 3)))
+        l[np.arange(n), seg] *= np.exp(5.0)
+        if k % 7 == 0:
+            l[3, 2] = 0.0
+        if k % 11 == 0:
+            l[n // 2] = 0.0
+        tables.append(l)
+        offs.append(offs[-1] + int(n))
+    lik = np.concatenate(tables)
+    for pen in ((1e-3, 1e-6, 1e-3), (0.2, 0.05, 0.3)):
+        with ib.Engine(ib.Params()) as e:
+            state, score, counts = e.viterbi_batch(lik, offs, False, *pen)
+            stats = e.kernel_stats()
+        assert stats["viterbi_norm"][1] > 0  # the batched kernels are the ones that ran
+        for i, l in enumerate(tables):
+            st, sc, _ = oracle.hiddengem(l, *pen)
+            a, b = offs[i], offs[i + 1]
+            np.testing.assert_array_equal(state[a:b], st)
+            np.testing.assert_array_equal(counts[i], np.bincount(st, minlength=3))
+            fin = np.isfinite(sc)
+            np.testing.assert_array_equal(np.isnan(score[a:b]), np.isnan(sc))
+            np.testing.assert_allclose(score[a:b][fin], sc[fin], rtol=0, atol=1e-7)
