@@ -1310,7 +1310,12 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     const int MB = (nrows + mma::BM * CG - 1) / (mma::BM * CG);
 
     const size_t per_window = (size_t)(ncols + nrows) * c->Wpad;
-    const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, LD_OPERAND_BUDGET / per_window));
+    static size_t budget = 0;
+    if (!budget) {  // IBDGEM_LD_BUDGET_MB: operand budget override (tests exercise the window batching with it)
+        const char *sb = getenv("IBDGEM_LD_BUDGET_MB");
+        budget = sb && atol(sb) > 0 ? (size_t)atol(sb) << 20 : LD_OPERAND_BUDGET;
+    }
+    const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, budget / per_window));
     int32_t *d_bgU, *d_ownU, *d_rowhap, *d_rowown, *d_akey;
     double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp;
     unsigned char *d_A, *d_B;

@@ -281,3 +281,37 @@ def test_hiddengem_batched_pipeline_vs_oracle(ragged):
             fin = np.isfinite(sc)
             np.testing.assert_array_equal(np.isnan(score[a:b]), np.isnan(sc))
             np.testing.assert_allclose(score[a:b][fin], sc[fin], rtol=0, atol=1e-7)
+
+
+def test_ld_disjoint_background_many_targets_c5_shape():
+    """BASELINE.json configs[4] in miniature: targets and background are disjoint sets (-S / -B), more
+    target rows than one row block pair holds, several column tiles."""
+    ec = _engine()
+    N = 700
+    case = _synth_case(21, 6000, N, 500, True, range(0, 300), bg=list(range(300, N)))
+    results = ec.run_engine(case, expanded=False)
+    assert results[0]["ld_path"] == 1
+    import oracle
+    for k in (0, 1, 149, 299):  # the oracle is slow: four of the 300 targets
+        o = oracle.compare_target(case.params, case.pk.pos, case.pk.host_keep, case.pk.n_ref, case.pk.n_alt, case.pk.hap,
+                                  case.targets[k], case.bg, af_user=case.af_user, reseed=True)
+        ec.assert_matches_oracle(results[k], o)
+
+
+def test_ld_window_batching_under_a_small_operand_budget():
+    """The int8 operands of all windows do not fit the budget: windows go through in batches."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "import numpy as np, enginecase as ec, refcases\n"
+        "from test_gpu_parity import _synth_case\n"
+        "case = _synth_case(33, 12000, 80, 400, True, range(12), pu_idx=3)\n"
+        "res = ec.run_engine(case, expanded=False)\n"
+        "assert res[0]['ld_path'] == 1 and res[0]['kernel_stats']['ld_mma'][1] >= 3, res[0]['kernel_stats']['ld_mma']\n"
+        "for r, o in zip(res, refcases.oracle_run(case)): ec.assert_matches_oracle(r, o)\n"
+        "print('ok')\n")
+    env = dict(os.environ, IBDGEM_LD_BUDGET_MB="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
