@@ -12,8 +12,8 @@
 //     LIBD1_w(t) = C0 + LSE_i ( R[a_i] + LSE_{k not own(t)} ( R'[k] + kappa M[a_i, k] ) ) - ln 4 nB
 // is evaluated in the epilogue straight out of TMEM in fp64.  Because M is an integer, the
 // epilogue first screens every element with an integer key (round(R'[k]/|kappa|) - M); only
-// elements within 32 nats of the running row maximum reach the fp64 exp — the dropped mass is
-// below 2N e^-32 ~ 1e-10 relative.  LIBD0 (the chain over background individuals) and LIBD2 are
+// elements within D = ln(2N) + 16 nats of the running row maximum reach the fp64 exp — the dropped
+// mass is below 1e-7 relative.  LIBD0 (the chain over background individuals) and LIBD2 are
 // target-independent per individual: Q_w[b] = C0 + R[r0] + R[r1] + kappa M[r0, r1].
 //
 // Kernels in this file: ld_compact, ld_c0, ld_transpose (+ marginals) (cached per prepared
@@ -557,12 +557,13 @@ struct Params {
     int debug;               // IBDGEM_MMA_DEBUG experiments (0 = product behaviour)
     int warm_tiles;          // leading tiles of a unit whose maximum is taken before they are screened
     int *unit_counter;       // next unit to hand out (zeroed before the launch)
+    int pf_tiles;            // L2 prefetch distance of the background stream, in tiles
     unsigned long long *trace;  // IBDGEM_MMA_TRACE: [4][1024] event log of CTA 0 (nullptr = off)
 };
 // event log entry: clock64 << 16 | event << 12 | tile; one lane per traced warp writes
 #define IBD_TRACE(role, ev, tile)                                                                          \
     do {                                                                                                   \
-        if (p.trace && blockIdx.x == 0 && lane == 0 && tr_n < 1024)                                        \
+        if (p.trace && blockIdx.x == 0 && lane == 0 && tr_n < 1024 && (p.debug != 9 || (ev) == 5))        \
             p.trace[(role) * 1024 + tr_n++] = ((unsigned long long)clock64() << 16) | ((ev) << 12) | ((tile) & 0xfff); \
     } while (0)
 
@@ -683,7 +684,10 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     if (p.trace && warp == 1 && lane == 0 && blockIdx.x < 256) {  // per-CTA start stamp (global timer, ns)
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.trace[3 * 1024 + blockIdx.x * 2] = t;
+        p.trace[3 * 1024 + blockIdx.x * 4] = t;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[3 * 1024 + blockIdx.x * 4 + 2] = smid;
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
@@ -750,8 +754,8 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         // the unit's target k-blocks are interleaved with its first background tile, in
                         // the order the MMA issuer needs them
                         if (n == 0) load_a(kb);
-                        if (n + PF_TILES < p.NT)  // pull the same k-block of a later tile into L2
-                            tma_prefetch_3d(&tmapB, kb * KBYTES, ((n + PF_TILES) * CG + (int)rank) * BN, w);
+                        if (n + p.pf_tiles < p.NT)  // pull the same k-block of a later tile into L2
+                            tma_prefetch_3d(&tmapB, kb * KBYTES, ((n + p.pf_tiles) * CG + (int)rank) * BN, w);
                         mbar_wait(b_empty + st, ph ^ 1u);
                         if (rank == 0) mbar_expect_tx(b_full + st, (uint32_t)(CG * B_SLAB));
                         tma_load_3d_cg<CG>(smem + OFF_B + st * B_SLAB, &tmapB, b_full + st, kb * KBYTES,
@@ -772,7 +776,8 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + OFF_A));
             const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem + OFF_B));
             for (;; it++) {
-                if (unit_of(uring, ufull, it) < 0) break;
+                const int u_cur = unit_of(uring, ufull, it);
+                if (u_cur < 0) break;
                 for (int n = 0; n < p.NT; n++, g++) {
                     const bool first = n == 0, last = n == p.NT - 1;
                     const uint32_t acc = g % NACC, use = g / NACC;
@@ -822,8 +827,9 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                     }
                 }
-                IBD_TRACE(0, 5, g);
+                IBD_TRACE(0, 5, (u_cur % p.MB) | (((u_cur / p.MB) & 0x1ff) << 3));
             }
+            if (p.trace && lane == 0 && blockIdx.x < 256) p.trace[3 * 1024 + blockIdx.x * 4 + 3] = (unsigned long long)it;
         }
     } else {
         // ===== merge warps (2, 3): at the end of every unit the four epilogue sets leave their partial
@@ -1036,7 +1042,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     if (p.trace && warp == 1 && lane == 0 && blockIdx.x < 256) {  // per-CTA end stamp
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.trace[3 * 1024 + blockIdx.x * 2 + 1] = t;
+        p.trace[3 * 1024 + blockIdx.x * 4 + 1] = t;
     }
     if constexpr (CG == 2) cluster_sync_all();  // the peer's shared memory and barriers stay alive until both are done
     if (warp == 2) {
@@ -1125,14 +1131,19 @@ static int launch_mma(int variant, int n_units, int sm_count, cudaStream_t st, c
     if (variant == 1) return launch_mma_cfg<mma::Cfg<1, 5>>(n_units, sm_count, st, a, b, p);
     return launch_mma_cfg<mma::Cfg<2, 5>>(n_units, sm_count, st, a, b, p);
 }
-static double screen_nats() {
-    static double v = -1;
-    if (v < 0) {
+// Screening distance in nats.  An element more than D below its row maximum contributes at most
+// e^-D of the row's sum, so dropping every such element of a row with `ncols` columns changes the
+// row's log-sum-exp by less than ncols * e^-D.  D = ln(ncols) + ln(1e7) keeps that below 1e-7 (the
+// window tolerance is 1e-6); IBDGEM_SCREEN_NATS overrides it.
+static double screen_nats(int ncols) {
+    static double forced = -1;
+    if (forced < 0) {
         const char *s = getenv("IBDGEM_SCREEN_NATS");
-        v = s ? atof(s) : SCREEN_NATS;
-        if (!(v >= 8.0 && v <= 700.0)) v = SCREEN_NATS;
+        forced = s ? atof(s) : 0.0;
+        if (!(forced >= 8.0 && forced <= 700.0)) forced = 0.0;
     }
-    return v;
+    if (forced > 0.0) return forced;
+    return std::min(SCREEN_NATS, log((double)std::max(ncols, 2)) + 16.2);
 }
 
 bool ld_tensor_eligible(ibdgem_engine *e, int32_t n_targets, int32_t n_bg, const uint8_t *tgt_counts) {
@@ -1281,7 +1292,9 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     // arrived), so the scoring of early windows overlaps the rest of the upload; a single range when
     // the panel is already resident.
     std::vector<int> range_end;
-    if (e->chunks_waited < (int)e->chunk_end.size() && e->chunk_end.size() > 1 && c->tw_upto == 0) {
+    const bool in_flight = e->chunks_waited < (int)e->chunk_end.size() && e->chunk_end.size() > 1 &&
+                           cudaEventQuery(e->chunk_ev[e->chunk_end.size() - 1]) == cudaErrorNotReady;
+    if (in_flight && c->tw_upto == 0) {
         int w = 0;
         for (size_t k = 0; k < e->chunk_end.size(); k++) {
             while (w < nW && e->h_wlast[(size_t)w] < e->chunk_end[k]) w++;
@@ -1404,7 +1417,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.n_units = nw * MB;
         p.nrows = nrows; p.ncolpad = ncolpad;
         p.H = c->H; p.outW = outW;
-        p.delta = (int)ceil(screen_nats() / -e->kappa) + 2;
+        p.delta = (int)ceil(screen_nats(ncols) / -e->kappa) + 2;
         p.kappa = e->kappa;
         p.akey = d_akey; p.Rp = d_Rp; p.Rw = c->d_Rw;
         p.row_hap = d_rowhap; p.row_own = d_rowown;
@@ -1424,6 +1437,9 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             if (scratch(e, SC_MMA_UNIT, 64, (void **)&d_unit)) return 1;
             IBD_CUDA(cudaMemsetAsync(d_unit, 0, 4, e->stream));
             p.unit_counter = d_unit;
+            static int pf = -1;
+            if (pf < 0) { const char *spf = getenv("IBDGEM_MMA_PF"); pf = spf ? atoi(spf) : mma::PF_TILES; }
+            p.pf_tiles = pf;
         }
         p.trace = nullptr;
         const char *trace_path = getenv("IBDGEM_MMA_TRACE");
