@@ -195,10 +195,40 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     return __hiloint2double(__double2hiint(p) + n * 1048576, __double2loint(p));
 }
 
+// exp(x) for x <= 0 with relative error below 3e-10: same reduction as exp_nonpos, degree-8 Taylor
+// polynomial evaluated by Estrin's scheme (dependency depth 5 instead of 12).  Used for the screened
+// candidates of the GEMM epilogue only: every such term is at most the row maximum, so the row's
+// log-sum-exp moves by less than 3e-10.
+__device__ __forceinline__ double exp_nonpos_fast(double x) {
+    if (!(x > -700.0)) return 0.0;
+    const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double nr = t - 6755399441055744.0;
+    double r = fma(nr, -6.93147180369123816490e-01, x);
+    r = fma(nr, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2;
+    const double p01 = fma(r, 1.0, 1.0);
+    const double p23 = fma(r, 1.66666666666666666667e-01, 0.5);
+    const double p45 = fma(r, 8.33333333333333333333e-03, 4.16666666666666666667e-02);
+    const double p67 = fma(r, 1.98412698412698412698e-04, 1.38888888888888888889e-03);
+    const double lo = fma(r2, p23, p01);
+    const double hi = fma(r2, p67, p45);
+    const double p = fma(r4, fma(r4, 2.48015873015873015873e-05, hi), lo);
+    return __hiloint2double(__double2hiint(p) + n * 1048576, __double2loint(p));
+}
+
 // running log-sum-exp (max m, scaled sum s) += e^x
 __device__ __forceinline__ void lse_add(double &m, double &s, double x) {
     const bool up = x > m;
     const double e = exp_nonpos(up ? m - x : x - m);  // one exp whichever way the maximum moves
+    s = up ? fma(s, e, 1.0) : s + e;
+    m = up ? x : m;
+}
+
+// the same with the short-chain exp, for the screened candidates of the GEMM epilogue
+__device__ __forceinline__ void lse_add_fast(double &m, double &s, double x) {
+    const bool up = x > m;
+    const double e = exp_nonpos_fast(up ? m - x : x - m);
     s = up ? fma(s, e, 1.0) : s + e;
     m = up ? x : m;
 }
@@ -1019,7 +1049,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         const int vj = pick32(v, j);
                         const int M = skeys[c * 32 + j] - vj;  // v = key - M
                         const double rp = __shfl_sync(0xffffffffu, rp_cur[c], j);
-                        if (act) lse_add(m, s, fma(p.kappa, (double)M, rp));
+                        if (act) lse_add_fast(m, s, fma(p.kappa, (double)M, rp));
                     }
                 }
                 tc_fence_before();
