@@ -201,7 +201,17 @@ int pack_impute(const std::string &hap_fn, const std::string &legend_fn, const s
             return 1;
         }
         uint32_t *row = out->bits.data() + s * (size_t)out->Wh;
-        for (size_t h = 0; h < H; h++) {
+        size_t h = 0;
+        // fast path: eight text bytes "a b c d " carry four alleles; check the pattern, pick bit 0 of
+        // the four digits and gather them with one multiply
+        for (; h + 4 <= H && 2 * h + 8 <= hn; h += 4) {
+            uint64_t x;
+            memcpy(&x, hl + 2 * h, 8);
+            if ((x & 0xFFFEFFFEFFFEFFFEull) != 0x2030203020302030ull) break;  // not "[01] [01] [01] [01] "
+            const uint64_t nib = (((x & 0x0001000100010001ull) * 0x0001000200040008ull) >> 48) & 0xFu;
+            row[h >> 5] |= (uint32_t)nib << (h & 31);
+        }
+        for (; h < H; h++) {
             const char c = hl[2 * h];
             if (c == '1') row[h >> 5] |= 1u << (h & 31);
             else if (c != '0') {
