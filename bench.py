@@ -311,6 +311,9 @@ def main():
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
+            every = torch.zeros(world, device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(every, ms)
+            timed.per_rank = [float(x) / steps for x in every.tolist()]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -322,6 +325,7 @@ def main():
     eng.reset_stats()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_total = timed(score, args.steps)
+    rank_ms = getattr(timed, "per_rank", None)
     clocks = sampler.stop() if sampler else None
     stats = eng.kernel_stats()
     ld_path = eng.last_ld_path()
@@ -399,6 +403,8 @@ def main():
             "gpu_launches": launches,
             "roofline": roofline,
         }
+        if rank_ms:
+            out["ms_per_step_by_rank"] = rank_ms  # value uses the maximum
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_baseline(args)
             out["cpu_baseline"] = cb
