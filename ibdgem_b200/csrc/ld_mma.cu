@@ -758,17 +758,21 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                 const int v = atomicAdd(p.unit_counter, 1);
                 return v < p.n_units ? v : -1;
             };
-            if (rank == 0) {  // scheduler: CTA 0 of the pair draws the unit numbers for every role of both CTAs
+            // scheduler: CTA 0 of the pair draws the unit numbers for every role of both CTAs.  The atomic
+            // for the unit after next is issued at the START of a unit and its result is first touched
+            // when the unit's loads are all out — a global round trip in front of a unit's first load
+            // showed up as a ~7,000-cycle bubble per unit in the device trace.
+            int pending = -1;
+            if (rank == 0) {
                 u_next = fetch_unit();
                 unit_publish<CG>(uring, ufull, 0, u_next);
+                pending = atomicAdd(p.unit_counter, 1);
             }
             for (int it = 0;; it++) {
                 int u;
                 if (rank == 0) {
                     u = u_next;
                     if (u < 0) break;
-                    u_next = fetch_unit();  // one ahead, so the number is waiting when the roles get there
-                    unit_publish<CG>(uring, ufull, it + 1, u_next);
                 } else {
                     u = unit_of(uring, ufull, it);
                     if (u < 0) break;
@@ -792,6 +796,11 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                                            (n * CG + (int)rank) * BN, w);
                         if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                     }
+                if (rank == 0) {
+                    u_next = pending < p.n_units ? pending : -1;
+                    unit_publish<CG>(uring, ufull, it + 1, u_next);
+                    if (u_next >= 0) pending = atomicAdd(p.unit_counter, 1);
+                }
             }
         }
     } else if (warp == 1) {
@@ -828,8 +837,10 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         if (!r2) mbar_wait(b_full + st2, ph2);
                         if (!r1 || !r2) IBD_TRACE(0, 4, g);
                         if (first) {  // the unit's target k-blocks arrive one by one
+                            IBD_TRACE(0, 6, kb);
                             mbar_wait(a_full + kb, (uint32_t)(it & 1));
                             if (two) mbar_wait(a_full + kb + 1, (uint32_t)(it & 1));
+                            IBD_TRACE(0, 7, kb);
                         }
                         tc_fence_after();
                         if (elect_one()) {
