@@ -1135,11 +1135,9 @@ static int make_operand_map(CUtensorMap *m, void *base, int Wpad, int rows, int 
 template <class CF>
 static int launch_mma_cfg(int n_units, int sm_count, cudaStream_t st, const CUtensorMap &a, const CUtensorMap &b,
                           const mma::Params &p) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        IBD_CUDA(cudaFuncSetAttribute(mma::ld_mma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
-        attr_set = true;
-    }
+    // function attributes are per device (the command-line front-end drives one engine per GPU from
+    // threads of one process); setting it is cheap enough to do on every launch
+    IBD_CUDA(cudaFuncSetAttribute(mma::ld_mma_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
     const int groups = std::max(1, std::min(n_units, sm_count / CF::CG));  // persistent: one CTA (pair) per SM (pair)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(groups * CF::CG));
@@ -1425,11 +1423,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         // the window's Q' row is staged in shared memory when it fits (one bulk, coalesced load instead
         // of latency-bound passes over global memory)
         const size_t q_smem = (size_t)nU * 8 <= 160 * 1024 ? (size_t)nU * 8 : 0;
-        static bool attr_set = false;
-        if (!attr_set) {
-            IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr_set = true;
-        }
+        IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         ld_ibd0_kernel<<<w_hi - w_lo, 256, q_smem, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
     }
     IBD_CUDA(cudaGetLastError());

@@ -117,3 +117,21 @@ def test_hiddengem_matches_reference_stdout(golden_dir, run, ind, tag, args):
             assert float(x) == pytest.approx(float(y), rel=2e-5)
         exact += a == b
     assert exact >= 0.9 * (len(w) - 4)  # the printed 6 digits agree except at rounding ties
+
+
+def test_targets_sharded_over_two_devices(golden_dir, tmp_path):
+    """--gpus 2: one host thread and one engine per device, contiguous shards of the target list."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    _run("ibdgem", ["-H", "panel.hap", "-L", "panel.legend", "-I", "panel.indv", "-P", "unk.pileup", "-O", str(tmp_path),
+                    "--LD", "-w", "10", "--gpus", "2"], cwd=ca)
+    want_files = sorted(f for f in os.listdir(os.path.join(ca, "ld_w10")) if f.endswith(".txt"))
+    assert sorted(os.listdir(tmp_path)) == want_files
+    for f in want_files:
+        got, want = open(tmp_path / f).read(), open(os.path.join(ca, "ld_w10", f)).read()
+        if f.endswith(".tab.txt"):
+            assert got.split("\n", 1)[1] == want.split("\n", 1)[1]
+        else:
+            _same_summary(got, want, exact=False)
