@@ -960,10 +960,20 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
         IBD_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         IBD_CUDA(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
     }
-    // Few, equal chunks: every chunk is a separate (less efficient) round of launches, and the copy
-    // engine competes with the scoring kernels for HBM, so finer pipelining measured slower
-    // (end-to-end C3 step: 4 chunks 15.5 ms, 8: 15.8, 16: 18.2, 24: 21.1; unpipelined 22.5).
-    const int nchunk = n_sites >= PANEL_CHUNKS * PANEL_CHUNK_MIN ? PANEL_CHUNKS : 1;
+    // Few, equal chunks.  Scoring a chunk's windows takes about as long as copying it (9.3 ms vs 11.7 ms
+    // for the whole C3 panel) and every chunk is a separate, less efficient round of launches
+    // (~0.25 ms), so the end-to-end step is ~ copy + (scoring + 0.5 ms D2H) / chunks + 0.25 ms x chunks:
+    // measured 2 chunks 17.1 ms, 3: 15.7, 4: 14.9, 5: 14.7, 6: 15.0; unpipelined 22.5.  Tapered chunk sizes
+    // (IBDGEM_PANEL_TAPER) measured worse: a large first chunk delays the start of scoring.
+    static int want_chunks = 0;
+    static double taper = 1.0;  // each chunk is `taper` times the size of the one before it
+    if (!want_chunks) {
+        const char *sc = getenv("IBDGEM_PANEL_CHUNKS"), *st = getenv("IBDGEM_PANEL_TAPER");
+        want_chunks = sc ? std::max(1, atoi(sc)) : PANEL_CHUNKS;
+        taper = st ? atof(st) : PANEL_TAPER;
+        if (!(taper > 0.1 && taper <= 1.0)) taper = 1.0;
+    }
+    const int nchunk = n_sites >= want_chunks * PANEL_CHUNK_MIN ? want_chunks : 1;
     while ((int)e->chunk_ev.size() < nchunk) {
         cudaEvent_t ev;
         IBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -972,13 +982,19 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
     IBD_CUDA(cudaEventRecord(e->ev_order, e->stream));
     IBD_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_order, 0));
     e->chunk_end.assign((size_t)nchunk, 0);
-    const int64_t per = (n_sites + nchunk - 1) / nchunk;
-    for (int k = 0; k < nchunk; k++) {
-        const int64_t s0 = (int64_t)k * per, s1 = std::min<int64_t>(n_sites, s0 + per);
+    double wsum = 0, wk = 1;
+    for (int k = 0; k < nchunk; k++, wk *= taper) wsum += wk;
+    int64_t s0 = 0;
+    double acc = 0;
+    wk = 1;
+    for (int k = 0; k < nchunk; k++, wk *= taper) {
+        acc += wk / wsum;
+        const int64_t s1 = k + 1 == nchunk ? n_sites : std::min<int64_t>(n_sites, std::max<int64_t>(s0 + 1, (int64_t)(acc * (double)n_sites)));
         IBD_CUDA(cudaMemcpyAsync(e->d_bits + (size_t)s0 * words_per_site, bits + (size_t)s0 * words_per_site,
                                  (size_t)(s1 - s0) * words_per_site * 4, cudaMemcpyHostToDevice, e->copy_stream));
         IBD_CUDA(cudaEventRecord(e->chunk_ev[(size_t)k], e->copy_stream));
         e->chunk_end[(size_t)k] = s1;
+        s0 = s1;
     }
     e->chunks_waited = 0;
     e->have_panel = true;

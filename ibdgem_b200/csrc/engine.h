@@ -172,7 +172,8 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
                     const int32_t *h_bg, int32_t pu_idx, int32_t outW, double *d_wll /*[T][outW][3]*/, int32_t *d_wn,
                     uint64_t *d_ws, uint64_t *d_we, int32_t *d_nwout);
 void ld_tensor_release(ibdgem_engine *e);
-constexpr int PANEL_CHUNKS = 4;          // upload / scoring pipeline depth
+constexpr int PANEL_CHUNKS = 5;          // upload / scoring pipeline depth
+constexpr double PANEL_TAPER = 1.0;       // chunk k is PANEL_TAPER^k of the first chunk
 constexpr int64_t PANEL_CHUNK_MIN = 32768;  // sites; smaller panels go up in one piece
 void ld_tensor_invalidate(ibdgem_engine *e);
 
