@@ -389,44 +389,79 @@ ld_tables_kernel(int w_lo, int w_hi, int ncols, int ncolpad, int H, const int32_
 
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
-// background operand: [window][column][Wpad] bytes, 0/1, K-major
+// background operand: [window][column][Wpad] bytes, 0/1, K-major.  grid = (word chunks, windows of
+// the batch); a thread expands EXPAND_ILP 32-site words, all loads issued before the first store.
+constexpr int EXPAND_ILP = 4;
 __global__ void __launch_bounds__(256)
-ld_expand_bg_kernel(int64_t total, int w0, int ncols, int H, int WP32, const int32_t *__restrict__ bgU,
+ld_expand_bg_kernel(int w0, int ncols, int H, int WP32, const int32_t *__restrict__ bgU,
                     const uint32_t *__restrict__ tbits, uint4 *__restrict__ out) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int g = (int)(i % WP32);
-    const int64_t wc = i / WP32;
-    const int c = (int)(wc % ncols), w = w0 + (int)(wc / ncols);
-    const int hap = 2 * bgU[c >> 1] + (c & 1);
-    const uint32_t word = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
-    uint4 lo, hi;
-    lo.x = spread4(word & 15u); lo.y = spread4((word >> 4) & 15u); lo.z = spread4((word >> 8) & 15u); lo.w = spread4((word >> 12) & 15u);
-    hi.x = spread4((word >> 16) & 15u); hi.y = spread4((word >> 20) & 15u); hi.z = spread4((word >> 24) & 15u); hi.w = spread4(word >> 28);
-    out[i * 2] = lo;
-    out[i * 2 + 1] = hi;
+    const int wl = blockIdx.y, w = w0 + wl;
+    const int per_window = ncols * WP32;
+    const int base = blockIdx.x * (256 * EXPAND_ILP) + threadIdx.x;
+    uint32_t word[EXPAND_ILP];
+#pragma unroll
+    for (int k = 0; k < EXPAND_ILP; k++) {
+        const int i = base + k * 256;
+        word[k] = 0;
+        if (i < per_window) {
+            const int c = i / WP32, g = i - c * WP32;
+            const int hap = 2 * __ldg(bgU + (c >> 1)) + (c & 1);
+            word[k] = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
+        }
+    }
+    uint4 *o = out + (size_t)wl * per_window * 2;
+#pragma unroll
+    for (int k = 0; k < EXPAND_ILP; k++) {
+        const int i = base + k * 256;
+        if (i < per_window) {
+            const uint32_t x = word[k];
+            uint4 lo, hi;
+            lo.x = spread4(x & 15u); lo.y = spread4((x >> 4) & 15u); lo.z = spread4((x >> 8) & 15u); lo.w = spread4((x >> 12) & 15u);
+            hi.x = spread4((x >> 16) & 15u); hi.y = spread4((x >> 20) & 15u); hi.z = spread4((x >> 24) & 15u); hi.w = spread4(x >> 28);
+            o[(size_t)i * 2] = lo;
+            o[(size_t)i * 2 + 1] = hi;
+        }
+    }
 }
 
 // target operand: [window][row][Wpad] bytes, n_s * h_s, K-major
 __global__ void __launch_bounds__(256)
-ld_expand_tgt_kernel(int64_t total, int w0, int nrows, int H, int Wpad, int WP32, const int32_t *__restrict__ targets,
+ld_expand_tgt_kernel(int w0, int nrows, int H, int Wpad, int WP32, const int32_t *__restrict__ targets,
                      const uint32_t *__restrict__ tbits, const uint8_t *__restrict__ nk, uint4 *__restrict__ out) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int g = (int)(i % WP32);
-    const int64_t wr = i / WP32;
-    const int r = (int)(wr % nrows), w = w0 + (int)(wr / nrows);
-    const int hap = 2 * targets[r >> 1] + (r & 1);
-    const uint32_t word = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
-    const uint4 *nv = reinterpret_cast<const uint4 *>(nk + (size_t)w * Wpad + g * 32);
-    const uint4 n0 = __ldg(nv), n1 = __ldg(nv + 1);
-    uint4 lo, hi;
-    lo.x = (spread4(word & 15u) * 0xFFu) & n0.x; lo.y = (spread4((word >> 4) & 15u) * 0xFFu) & n0.y;
-    lo.z = (spread4((word >> 8) & 15u) * 0xFFu) & n0.z; lo.w = (spread4((word >> 12) & 15u) * 0xFFu) & n0.w;
-    hi.x = (spread4((word >> 16) & 15u) * 0xFFu) & n1.x; hi.y = (spread4((word >> 20) & 15u) * 0xFFu) & n1.y;
-    hi.z = (spread4((word >> 24) & 15u) * 0xFFu) & n1.z; hi.w = (spread4(word >> 28) * 0xFFu) & n1.w;
-    out[i * 2] = lo;
-    out[i * 2 + 1] = hi;
+    const int wl = blockIdx.y, w = w0 + wl;
+    const int per_window = nrows * WP32;
+    const int base = blockIdx.x * (256 * EXPAND_ILP) + threadIdx.x;
+    uint32_t word[EXPAND_ILP];
+    uint4 n0[EXPAND_ILP], n1[EXPAND_ILP];
+#pragma unroll
+    for (int k = 0; k < EXPAND_ILP; k++) {
+        const int i = base + k * 256;
+        word[k] = 0;
+        n0[k] = n1[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < per_window) {
+            const int r = i / WP32, g = i - r * WP32;
+            const int hap = 2 * __ldg(targets + (r >> 1)) + (r & 1);
+            word[k] = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
+            const uint4 *nv = reinterpret_cast<const uint4 *>(nk + (size_t)w * Wpad + g * 32);
+            n0[k] = __ldg(nv);
+            n1[k] = __ldg(nv + 1);
+        }
+    }
+    uint4 *o = out + (size_t)wl * per_window * 2;
+#pragma unroll
+    for (int k = 0; k < EXPAND_ILP; k++) {
+        const int i = base + k * 256;
+        if (i < per_window) {
+            const uint32_t x = word[k];
+            uint4 lo, hi;
+            lo.x = (spread4(x & 15u) * 0xFFu) & n0[k].x; lo.y = (spread4((x >> 4) & 15u) * 0xFFu) & n0[k].y;
+            lo.z = (spread4((x >> 8) & 15u) * 0xFFu) & n0[k].z; lo.w = (spread4((x >> 12) & 15u) * 0xFFu) & n0[k].w;
+            hi.x = (spread4((x >> 16) & 15u) * 0xFFu) & n1[k].x; hi.y = (spread4((x >> 20) & 15u) * 0xFFu) & n1[k].y;
+            hi.z = (spread4((x >> 24) & 15u) * 0xFFu) & n1[k].z; hi.w = (spread4(x >> 28) * 0xFFu) & n1[k].w;
+            o[(size_t)i * 2] = lo;
+            o[(size_t)i * 2 + 1] = hi;
+        }
+    }
 }
 
 // window bookkeeping (W2) and LIBD2 = Q_w[target] for every (target, window)
@@ -1432,15 +1467,15 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         const int nw = std::min(nWb, w_hi - w0);
         {
             LaunchScope ls(e, K_LD_EXPAND_BG);
-            const int64_t n = (int64_t)nw * ncols * c->WP32;
-            ld_expand_bg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(n, w0, ncols, c->H, c->WP32, d_bgU, c->d_tbits,
-                                                                                    reinterpret_cast<uint4 *>(d_B));
+            const int per_block = 256 * EXPAND_ILP;
+            ld_expand_bg_kernel<<<dim3((unsigned)((ncols * c->WP32 + per_block - 1) / per_block), (unsigned)nw), 256, 0, e->stream>>>(
+                w0, ncols, c->H, c->WP32, d_bgU, c->d_tbits, reinterpret_cast<uint4 *>(d_B));
         }
         {
             LaunchScope ls(e, K_LD_EXPAND_TGT);
-            const int64_t n = (int64_t)nw * nrows * c->WP32;
-            ld_expand_tgt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-                n, w0, nrows, c->H, c->Wpad, c->WP32, d_targets, c->d_tbits, c->d_nk, reinterpret_cast<uint4 *>(d_A));
+            const int per_block = 256 * EXPAND_ILP;
+            ld_expand_tgt_kernel<<<dim3((unsigned)((nrows * c->WP32 + per_block - 1) / per_block), (unsigned)nw), 256, 0, e->stream>>>(
+                w0, nrows, c->H, c->Wpad, c->WP32, d_targets, c->d_tbits, c->d_nk, reinterpret_cast<uint4 *>(d_A));
         }
         IBD_CUDA(cudaGetLastError());
         CUtensorMap mapA, mapB;
