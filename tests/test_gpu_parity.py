@@ -315,3 +315,24 @@ def test_ld_window_batching_under_a_small_operand_budget():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_ld_deep_pileup_large_max_cov():
+    """Depths well above the default: the int8 target operand carries n_s up to max_cov (unsigned),
+    the count bit planes need 6 bits, and kappa * M spans thousands of nats."""
+    ec = _engine()
+    case = _synth_case(71, 5000, 48, 300, True, range(10), pu_idx=4, depth=14.0, max_cov=60)
+    results = ec.run_engine(case, expanded=False)
+    assert results[0]["ld_path"] == 1
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
+
+
+def test_ld_window_larger_than_tensor_tile_uses_general_path():
+    """Windows above 1,024 sites do not fit the resident target tile: the general path takes over."""
+    ec = _engine()
+    case = _synth_case(72, 5000, 24, 1500, True, range(4))
+    results = ec.run_engine(case, expanded=False)
+    assert results[0]["ld_path"] == 0
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
