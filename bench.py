@@ -383,6 +383,9 @@ def main():
                                     "= 2 x bf16)" if ld_path == 1 else "bf16_tflops_sustained of measured") if peaks
                     else "fallback 1.4 PFLOP/s sustained bf16",
                     "pipe_peak_at_clock": pipe_peak, "frac_of_pipe_peak": achieved / pipe_peak,
+                    "note": "frac can exceed 1: the bf16 denominator was measured power-capped (~1.35 GHz, ~1 kW); this "
+                            "int8 kernel on 0/1 operands holds the full SM clock (see clocks) at ~300 W. "
+                            "frac_of_pipe_peak is against 148 SM x 8192 int8 MAC/clk x 2 at the sampled clock.",
                     "kernel_share_of_step": dom_ms / (ms_total) if ms_total > 0 else None,
                     "kernels_ms_per_step": {k: v[0] / args.steps for k, v in stats.items() if v[1]}}
         out = {
