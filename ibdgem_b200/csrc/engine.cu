@@ -27,7 +27,7 @@ void set_error(const char *fmt, ...) {
 const char *const kKernelNames[K_COUNT] = {
     "site_table",     "scan_count",    "scan_offsets",  "scan_rank",    "window_nonld", "counters",
     "expand_sites",   "ld_general",    "ld_finalize",   "ld_compact",   "ld_c0",        "ld_transpose",
-    "ld_tables",     "ld_expand_bg",  "ld_expand_tgt", "ld_windows",  "ld_ibd0",
+    "ld_expand_bg",  "ld_expand_tgt", "ld_windows",  "ld_ibd0",
     "ld_mma",         "viterbi",       "viterbi_norm",  "viterbi_back", "viterbi_out", "fill",
 };
 

@@ -39,7 +39,6 @@ enum KernelId {
     K_LD_C0,            // tensor path: per-window sum of l0
     K_LD_TRANSPOSE,     // tensor path: site-major bits -> window-padded haplotype-major bits, fused with the
                         // per-window per-haplotype linear terms and the per-individual chain
-    K_LD_TABLES,        // tensor path: screening keys / R' / Q' of the call's background columns
     K_LD_EXPAND_BG,     // tensor path: background operand (0/1 int8, K-major)
     K_LD_EXPAND_TGT,    // tensor path: target operand (depth-weighted int8, K-major)
     K_LD_WINDOWS,       // tensor path: window bookkeeping + LIBD2

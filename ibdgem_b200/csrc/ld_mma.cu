@@ -17,7 +17,7 @@
 // target-independent per individual: Q_w[b] = C0 + R[r0] + R[r1] + kappa M[r0, r1].
 //
 // Kernels in this file: ld_compact, ld_c0, ld_transpose (+ marginals) (cached per prepared
-// panel); ld_tables, ld_expand_bg, ld_expand_tgt, ld_windows, ld_mma, ld_ibd0 (per call).
+// panel); ld_expand_bg, ld_expand_tgt, ld_windows, ld_mma, ld_ibd0 (per call).
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
@@ -42,13 +42,11 @@ struct LdCache {
     int H = 0, N = 0;
     int32_t *d_infsite = nullptr;  // [nW][Wpad] site index of each window slot, -1 = padding
     uint8_t *d_nk = nullptr;       // [nW][Wpad] pileup depth n_s of the slot
-    double *d_d1 = nullptr;        // [nW][Wpad] l1 - l0
+    uint8_t *d_nr = nullptr;       // [nW][Wpad] REF-matching bases n_ref of the slot (n_alt = n_s - n_ref)
     double *d_l0 = nullptr;        // [nW][Wpad] l0
     double *d_C0 = nullptr;        // [nW]
     uint32_t *d_tbits = nullptr;   // [nW][H][WP32] haplotype-major window-padded bits
-    double *d_Rw = nullptr;        // [nW][H]
-    double *d_Qw = nullptr;        // [nW][N]
-    size_t b_infsite = 0, b_nk = 0, b_d1 = 0, b_l0 = 0, b_C0 = 0, b_tbits = 0, b_Rw = 0, b_Qw = 0;
+    size_t b_infsite = 0, b_nk = 0, b_nr = 0, b_l0 = 0, b_C0 = 0, b_tbits = 0;
 };
 
 constexpr int KEY_PAD = -(1 << 30);   // key of padding / excluded columns
@@ -253,17 +251,16 @@ __global__ void __launch_bounds__(256)
 ld_compact_kernel(int64_t S, const uint8_t *__restrict__ status, const uint32_t *__restrict__ rank,
                   const uint8_t *__restrict__ nref, const uint8_t *__restrict__ nalt,
                   const double *__restrict__ lnP, int C, int W, int Wpad, int32_t *__restrict__ infsite,
-                  uint8_t *__restrict__ nk, double *__restrict__ d1, double *__restrict__ l0) {
+                  uint8_t *__restrict__ nk, uint8_t *__restrict__ nr, double *__restrict__ l0) {
     const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= S || status[s] != 1) return;
     const uint32_t r = rank[s];
     const int64_t slot = (int64_t)(r / (uint32_t)W) * Wpad + (r % (uint32_t)W);
     const int a = nref[s], b = nalt[s];
-    const double *L = lnP + (size_t)(a * C + b) * 3;
     infsite[slot] = (int32_t)s;
     nk[slot] = (uint8_t)(a + b);
-    d1[slot] = L[1] - L[0];
-    l0[slot] = L[0];
+    nr[slot] = (uint8_t)a;
+    l0[slot] = lnP[(size_t)(a * C + b) * 3];
 }
 
 // C0_w = sum of l0 over the window, fixed-order tree so the value is reproducible
@@ -299,34 +296,19 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, int lane) {
     return x;
 }
 
-// K_LD_TRANSPOSE: site-major panel bits -> [window][haplotype][32-site words], fused with the
-// per-window marginals.  Block = (one window, 8 word columns = 256 haplotypes).  Warp g transposes
-// the 32 x 32 bit blocks of window slots 32g .. 32g+31 in registers and builds the bit planes of
-// n_ref, n_alt and n of those slots; the tile goes through shared memory so the stores are whole
-// rows.  Then 4 threads per haplotype turn its rows into integers by AND + popcount against the
-// planes:  A = sum x n_ref, B = sum x n_alt  ->  R_w[x] = alpha A + beta B  (l1 - l0 is linear in
-// the counts), and for each individual  Q_w[b] = C0 + R[r0] + R[r1] + kappa sum n r0 r1.
-constexpr int LD_PLANES = 7;  // counts are <= 127 (IBDGEM_MAX_COV_LIMIT)
+// K_LD_TRANSPOSE: site-major panel bits -> [window][haplotype][32-site words].  Block = (8 word
+// columns = 256 haplotypes, one window); warp g transposes the 32 x 32 bit blocks of window slots
+// 32g .. 32g+31 in registers; the tile goes through shared memory so the stores are whole rows.
 __global__ void __launch_bounds__(1024)
 ld_transpose_kernel(int w_off, const uint32_t *__restrict__ bits, int64_t Wh, int H, const int32_t *__restrict__ infsite,
-                    const uint8_t *__restrict__ nref, const uint8_t *__restrict__ nalt, int Wpad, int WP32, int nbits,
-                    const double *__restrict__ C0, double alpha, double beta, double kappa, uint32_t *__restrict__ tbits,
-                    double *__restrict__ Rw, double *__restrict__ Qw) {
+                    int Wpad, int WP32, uint32_t *__restrict__ tbits) {
     __shared__ uint32_t tile[256 * 33];
-    __shared__ uint32_t planes[3][LD_PLANES][32];
     // the word-column group is the fastest grid dimension: the blocks that share a window's panel rows
     // run together, so every 32-byte piece of a row is fetched from HBM once
     const int w = w_off + blockIdx.y, j0 = blockIdx.x * 8;
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
     if (g < WP32) {
         const int32_t s = infsite[(size_t)w * Wpad + g * 32 + lane];
-        const int r = s >= 0 ? nref[s] : 0, a = s >= 0 ? nalt[s] : 0;
-        for (int b = 0; b < nbits; b++) {
-            const uint32_t pr = __ballot_sync(0xffffffffu, (r >> b) & 1);
-            const uint32_t pa = __ballot_sync(0xffffffffu, (a >> b) & 1);
-            const uint32_t pn = __ballot_sync(0xffffffffu, ((r + a) >> b) & 1);
-            if (lane == 0) { planes[0][b][g] = pr; planes[1][b][g] = pa; planes[2][b][g] = pn; }
-        }
         const uint32_t *row = bits + (size_t)(s < 0 ? 0 : s) * Wh;
         uint32_t word[8];
 #pragma unroll
@@ -340,135 +322,150 @@ ld_transpose_kernel(int w_off, const uint32_t *__restrict__ bits, int64_t Wh, in
             const int hap = j0 * 32 + hl;
             if (hap < H) tbits[((size_t)w * H + hap) * WP32 + lane] = tile[hl * 33 + lane];
         }
-    // marginals: threads 4h .. 4h+3 share haplotype h of the tile (its partner 2i <-> 2i+1 is the next row)
-    const int hl = threadIdx.x >> 2, sub = threadIdx.x & 3;
-    const int hap = j0 * 32 + hl;
-    int A = 0, B = 0, Mq = 0;
-    for (int gg = sub; gg < WP32; gg += 4) {
-        const uint32_t x = tile[hl * 33 + gg];
-        const uint32_t both = x & tile[(hl ^ 1) * 33 + gg];
-        for (int b = 0; b < nbits; b++) {
-            A += __popc(x & planes[0][b][gg]) << b;
-            B += __popc(x & planes[1][b][gg]) << b;
-            Mq += __popc(both & planes[2][b][gg]) << b;
-        }
-    }
-    A += __shfl_xor_sync(0xffffffffu, A, 1); A += __shfl_xor_sync(0xffffffffu, A, 2);
-    B += __shfl_xor_sync(0xffffffffu, B, 1); B += __shfl_xor_sync(0xffffffffu, B, 2);
-    Mq += __shfl_xor_sync(0xffffffffu, Mq, 1); Mq += __shfl_xor_sync(0xffffffffu, Mq, 2);
-    const double R = fma(alpha, (double)A, beta * (double)B);
-    const double Rp = __shfl_xor_sync(0xffffffffu, R, 4);
-    if (sub == 0 && hap < H) {
-        Rw[(size_t)w * H + hap] = R;
-        if ((hap & 1) == 0) Qw[(size_t)w * (H / 2) + (hap >> 1)] = ((C0[w] + R) + Rp) + kappa * (double)Mq;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // per-call kernels
 
-// screening keys and R'[k] = R[k] + ln(multiplicity) for every background haplotype column
-__global__ void __launch_bounds__(256)
-ld_tables_kernel(int w_lo, int w_hi, int ncols, int ncolpad, int H, const int32_t *__restrict__ bgU, const double *__restrict__ lnc,
-                 const double *__restrict__ Rw, const double *__restrict__ Qw, double inv_abs_kappa,
-                 int32_t *__restrict__ akey, double *__restrict__ Rp, double *__restrict__ Qp) {
-    const int64_t i = (int64_t)w_lo * ncolpad + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)w_hi * ncolpad) return;
-    const int w = (int)(i / ncolpad), c = (int)(i % ncolpad);
-    if (c < ncols) {
-        const int u = c >> 1, ind = bgU[u];
-        const double rp = Rw[(size_t)w * H + 2 * ind + (c & 1)] + lnc[u];
-        Rp[i] = rp;
-        akey[i] = (int32_t)rint(rp * inv_abs_kappa);
-        if ((c & 1) == 0) Qp[(size_t)w * (ncols / 2) + u] = Qw[(size_t)w * (H / 2) + ind] + lnc[u];
-    } else {
-        Rp[i] = -INFINITY;
-        akey[i] = KEY_PAD;
-    }
-}
-
 __device__ __forceinline__ uint32_t spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+// One 32-site word of a haplotype as 0/1 bytes (eight 32-bit lanes of four sites).
+__device__ __forceinline__ void spread32(uint32_t x, uint32_t (&e)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) e[k] = spread4((x >> (4 * k)) & 15u);
+}
+__device__ __forceinline__ unsigned warp_sum(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
-// background operand: [window][column][Wpad] bytes, 0/1, K-major.  grid = (word chunks, windows of
-// the batch); a thread expands EXPAND_ILP 32-site words, all loads issued before the first store.
-constexpr int EXPAND_ILP = 4;
+// K_LD_EXPAND_BG: one warp per (window, background individual), lane = 32-site word.  Writes the
+// individual's two haplotype columns of the GEMM's background operand (0/1 bytes, K-major) and, from
+// the same bytes, the integers of the window's marginals by dp4a against the slot counts:
+//   A = sum x n_ref, N = sum x n  ->  R[x] = alpha A + beta (N - A)   (l1 - l0 is linear in the counts)
+//   M = sum n r0 r1               ->  Q[b] = C0 + R[r0] + R[r1] + kappa M   (the chain of src/ibdgem.c:715)
+// and from them the column tables of the call: R'[k] = R[k] + ln(multiplicity), the screening key
+// round(R'/|kappa|), Q'[b] = Q[b] + ln(multiplicity).  Individuals nU .. npadU-1 are the padding columns.
 __global__ void __launch_bounds__(256)
-ld_expand_bg_kernel(int w0, int ncols, int H, int WP32, const int32_t *__restrict__ bgU,
-                    const uint32_t *__restrict__ tbits, uint4 *__restrict__ out) {
+ld_expand_bg_kernel(int w0, int nU, int npadU, int ncols, int ncolpad, int H, int Wpad, int WP32,
+                    const int32_t *__restrict__ bgU, const double *__restrict__ lnc, const uint32_t *__restrict__ tbits,
+                    const uint8_t *__restrict__ nr, const uint8_t *__restrict__ nk, const double *__restrict__ C0,
+                    double alpha, double beta, double kappa, double inv_abs_kappa, unsigned char *__restrict__ out,
+                    int32_t *__restrict__ akey, double *__restrict__ Rp, double *__restrict__ Qp) {
+    const int lane = threadIdx.x & 31;
+    const int u = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int wl = blockIdx.y, w = w0 + wl;
-    const int per_window = ncols * WP32;
-    const int base = blockIdx.x * (256 * EXPAND_ILP) + threadIdx.x;
-    uint32_t word[EXPAND_ILP];
-#pragma unroll
-    for (int k = 0; k < EXPAND_ILP; k++) {
-        const int i = base + k * 256;
-        word[k] = 0;
-        if (i < per_window) {
-            const int c = i / WP32, g = i - c * WP32;
-            const int hap = 2 * __ldg(bgU + (c >> 1)) + (c & 1);
-            word[k] = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
+    if (u >= npadU) return;
+    if (u >= nU) {  // padding columns never pass the screen
+        if (lane < 2 && 2 * u + lane < ncolpad) {
+            akey[(size_t)w * ncolpad + 2 * u + lane] = KEY_PAD;
+            Rp[(size_t)w * ncolpad + 2 * u + lane] = -INFINITY;
         }
+        return;
     }
-    uint4 *o = out + (size_t)wl * per_window * 2;
+    const int ind = __ldg(bgU + u);
+    unsigned A0 = 0, N0 = 0, A1 = 0, N1 = 0, M = 0;
+    if (lane < WP32) {
+        const uint32_t x0 = __ldg(tbits + ((size_t)w * H + 2 * ind) * WP32 + lane);
+        const uint32_t x1 = __ldg(tbits + ((size_t)w * H + 2 * ind + 1) * WP32 + lane);
+        const uint4 *cr = reinterpret_cast<const uint4 *>(nr + (size_t)w * Wpad + lane * 32);
+        const uint4 *cn = reinterpret_cast<const uint4 *>(nk + (size_t)w * Wpad + lane * 32);
+        const uint4 r0 = __ldg(cr), r1 = __ldg(cr + 1), n0 = __ldg(cn), n1 = __ldg(cn + 1);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const uint32_t nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+        uint32_t e0[8], e1[8];
+        spread32(x0, e0);
+        spread32(x1, e1);
 #pragma unroll
-    for (int k = 0; k < EXPAND_ILP; k++) {
-        const int i = base + k * 256;
-        if (i < per_window) {
-            const uint32_t x = word[k];
-            uint4 lo, hi;
-            lo.x = spread4(x & 15u); lo.y = spread4((x >> 4) & 15u); lo.z = spread4((x >> 8) & 15u); lo.w = spread4((x >> 12) & 15u);
-            hi.x = spread4((x >> 16) & 15u); hi.y = spread4((x >> 20) & 15u); hi.z = spread4((x >> 24) & 15u); hi.w = spread4(x >> 28);
-            o[(size_t)i * 2] = lo;
-            o[(size_t)i * 2 + 1] = hi;
+        for (int k = 0; k < 8; k++) {
+            A0 = __dp4a(e0[k], rr[k], A0);
+            N0 = __dp4a(e0[k], nn[k], N0);
+            A1 = __dp4a(e1[k], rr[k], A1);
+            N1 = __dp4a(e1[k], nn[k], N1);
+            M = __dp4a(e0[k] & e1[k], nn[k], M);
         }
+        uint4 *o0 = reinterpret_cast<uint4 *>(out + ((size_t)wl * ncols + 2 * u) * Wpad) + lane * 2;
+        uint4 *o1 = reinterpret_cast<uint4 *>(out + ((size_t)wl * ncols + 2 * u + 1) * Wpad) + lane * 2;
+        o0[0] = make_uint4(e0[0], e0[1], e0[2], e0[3]);
+        o0[1] = make_uint4(e0[4], e0[5], e0[6], e0[7]);
+        o1[0] = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+        o1[1] = make_uint4(e1[4], e1[5], e1[6], e1[7]);
+    }
+    A0 = warp_sum(A0); N0 = warp_sum(N0); A1 = warp_sum(A1); N1 = warp_sum(N1); M = warp_sum(M);
+    if (lane == 0) {
+        const double R0 = fma(alpha, (double)A0, beta * (double)(N0 - A0));  // N - A = sum x n_alt >= 0
+        const double R1 = fma(alpha, (double)A1, beta * (double)(N1 - A1));
+        const double lc = lnc[u];
+        const double p0 = R0 + lc, p1 = R1 + lc;
+        Rp[(size_t)w * ncolpad + 2 * u] = p0;
+        Rp[(size_t)w * ncolpad + 2 * u + 1] = p1;
+        akey[(size_t)w * ncolpad + 2 * u] = (int32_t)rint(p0 * inv_abs_kappa);
+        akey[(size_t)w * ncolpad + 2 * u + 1] = (int32_t)rint(p1 * inv_abs_kappa);
+        Qp[(size_t)w * nU + u] = (((C0[w] + R0) + R1) + kappa * (double)M) + lc;
     }
 }
 
-// target operand: [window][row][Wpad] bytes, n_s * h_s, K-major
+// K_LD_EXPAND_TGT: one warp per (window, target).  Writes the target's two haplotype rows of the
+// GEMM's target operand (n_s x_s bytes, K-major; skipped when out == nullptr), R of both rows for the
+// merge step, and LIBD2_w(t) = Q_w[t] (the non-LD product of src/ibdgem.c:667, 752 in log space).
 __global__ void __launch_bounds__(256)
-ld_expand_tgt_kernel(int w0, int nrows, int H, int Wpad, int WP32, const int32_t *__restrict__ targets,
-                     const uint32_t *__restrict__ tbits, const uint8_t *__restrict__ nk, uint4 *__restrict__ out) {
+ld_expand_tgt_kernel(int w0, int T, int H, int Wpad, int WP32, int outW, const int32_t *__restrict__ targets,
+                     const uint32_t *__restrict__ tbits, const uint8_t *__restrict__ nr, const uint8_t *__restrict__ nk,
+                     const double *__restrict__ C0, double alpha, double beta, double kappa,
+                     unsigned char *__restrict__ out, double *__restrict__ Rt, double *__restrict__ wll) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int wl = blockIdx.y, w = w0 + wl;
-    const int per_window = nrows * WP32;
-    const int base = blockIdx.x * (256 * EXPAND_ILP) + threadIdx.x;
-    uint32_t word[EXPAND_ILP];
-    uint4 n0[EXPAND_ILP], n1[EXPAND_ILP];
+    if (t >= T) return;
+    const int ind = __ldg(targets + t);
+    unsigned A0 = 0, N0 = 0, A1 = 0, N1 = 0, M = 0;
+    if (lane < WP32) {
+        const uint32_t x0 = __ldg(tbits + ((size_t)w * H + 2 * ind) * WP32 + lane);
+        const uint32_t x1 = __ldg(tbits + ((size_t)w * H + 2 * ind + 1) * WP32 + lane);
+        const uint4 *cr = reinterpret_cast<const uint4 *>(nr + (size_t)w * Wpad + lane * 32);
+        const uint4 *cn = reinterpret_cast<const uint4 *>(nk + (size_t)w * Wpad + lane * 32);
+        const uint4 r0 = __ldg(cr), r1 = __ldg(cr + 1), n0 = __ldg(cn), n1 = __ldg(cn + 1);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const uint32_t nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+        uint32_t e0[8], e1[8];
+        spread32(x0, e0);
+        spread32(x1, e1);
 #pragma unroll
-    for (int k = 0; k < EXPAND_ILP; k++) {
-        const int i = base + k * 256;
-        word[k] = 0;
-        n0[k] = n1[k] = make_uint4(0u, 0u, 0u, 0u);
-        if (i < per_window) {
-            const int r = i / WP32, g = i - r * WP32;
-            const int hap = 2 * __ldg(targets + (r >> 1)) + (r & 1);
-            word[k] = __ldg(tbits + ((size_t)w * H + hap) * WP32 + g);
-            const uint4 *nv = reinterpret_cast<const uint4 *>(nk + (size_t)w * Wpad + g * 32);
-            n0[k] = __ldg(nv);
-            n1[k] = __ldg(nv + 1);
+        for (int k = 0; k < 8; k++) {
+            A0 = __dp4a(e0[k], rr[k], A0);
+            N0 = __dp4a(e0[k], nn[k], N0);
+            A1 = __dp4a(e1[k], rr[k], A1);
+            N1 = __dp4a(e1[k], nn[k], N1);
+            M = __dp4a(e0[k] & e1[k], nn[k], M);
+        }
+        if (out) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {  // n_s where the allele is 1
+                e0[k] = (e0[k] * 0xFFu) & nn[k];
+                e1[k] = (e1[k] * 0xFFu) & nn[k];
+            }
+            uint4 *o0 = reinterpret_cast<uint4 *>(out + ((size_t)wl * 2 * T + 2 * t) * Wpad) + lane * 2;
+            uint4 *o1 = reinterpret_cast<uint4 *>(out + ((size_t)wl * 2 * T + 2 * t + 1) * Wpad) + lane * 2;
+            o0[0] = make_uint4(e0[0], e0[1], e0[2], e0[3]);
+            o0[1] = make_uint4(e0[4], e0[5], e0[6], e0[7]);
+            o1[0] = make_uint4(e1[0], e1[1], e1[2], e1[3]);
+            o1[1] = make_uint4(e1[4], e1[5], e1[6], e1[7]);
         }
     }
-    uint4 *o = out + (size_t)wl * per_window * 2;
-#pragma unroll
-    for (int k = 0; k < EXPAND_ILP; k++) {
-        const int i = base + k * 256;
-        if (i < per_window) {
-            const uint32_t x = word[k];
-            uint4 lo, hi;
-            lo.x = (spread4(x & 15u) * 0xFFu) & n0[k].x; lo.y = (spread4((x >> 4) & 15u) * 0xFFu) & n0[k].y;
-            lo.z = (spread4((x >> 8) & 15u) * 0xFFu) & n0[k].z; lo.w = (spread4((x >> 12) & 15u) * 0xFFu) & n0[k].w;
-            hi.x = (spread4((x >> 16) & 15u) * 0xFFu) & n1[k].x; hi.y = (spread4((x >> 20) & 15u) * 0xFFu) & n1[k].y;
-            hi.z = (spread4((x >> 24) & 15u) * 0xFFu) & n1[k].z; hi.w = (spread4(x >> 28) * 0xFFu) & n1[k].w;
-            o[(size_t)i * 2] = lo;
-            o[(size_t)i * 2 + 1] = hi;
-        }
+    A0 = warp_sum(A0); N0 = warp_sum(N0); A1 = warp_sum(A1); N1 = warp_sum(N1); M = warp_sum(M);
+    if (lane == 0) {
+        const double R0 = fma(alpha, (double)A0, beta * (double)(N0 - A0));  // N - A = sum x n_alt >= 0
+        const double R1 = fma(alpha, (double)A1, beta * (double)(N1 - A1));
+        Rt[((size_t)w * T + t) * 2] = R0;
+        Rt[((size_t)w * T + t) * 2 + 1] = R1;
+        wll[((size_t)t * outW + w) * 3 + 2] = ((C0[w] + R0) + R1) + kappa * (double)M;
     }
 }
 
-// window bookkeeping (W2) and LIBD2 = Q_w[target] for every (target, window)
+// window bookkeeping (W2) for every (target, window)
 __global__ void __launch_bounds__(256)
-ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K, const int32_t *__restrict__ targets, int Nind,
-                  const int64_t *__restrict__ wfirst, const int64_t *__restrict__ wlast, const uint64_t *__restrict__ pos,
-                  const double *__restrict__ Qw, double *__restrict__ wll, int32_t *__restrict__ wn,
+ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K, const int64_t *__restrict__ wfirst,
+                  const int64_t *__restrict__ wlast, const uint64_t *__restrict__ pos, int32_t *__restrict__ wn,
                   uint64_t *__restrict__ ws, uint64_t *__restrict__ we, int32_t *__restrict__ nwout) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int span = w_hi - w_lo;
@@ -477,7 +474,6 @@ ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K,
     const int64_t i = (int64_t)t * outW + w;
     if (w == 0) nwout[t] = nW;
     if (w >= nW) return;
-    wll[i * 3 + 2] = Qw[(size_t)w * Nind + targets[t]];
     const int64_t left = K - (int64_t)w * W;
     wn[i] = (int32_t)(left < W ? left : W);
     ws[i] = pos[wfirst[w]];
@@ -613,8 +609,7 @@ struct Params {
     double kappa;
     const int32_t *akey;     // [nW][ncolpad]
     const double *Rp;        // [nW][ncolpad]
-    const double *Rw;        // [nW][H]
-    const int32_t *row_hap;  // [nrows] panel haplotype of each row
+    const double *Rt;        // [nW][nrows] R_w of each target row
     const int32_t *row_own;  // [nrows] first excluded column of the row, or -1
     const double *C0;        // [nW]
     const double *lognb4;    // [T] ln(4 n_refpanel) or NaN
@@ -923,8 +918,8 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             const bool ok = row < p.nrows;  // nrows is even: both rows or neither
             double rw0 = 0.0, rw1 = 0.0, lnb = 0.0;
             if (ok) {
-                rw0 = __ldg(p.Rw + (size_t)w * p.H + __ldg(p.row_hap + row));
-                rw1 = __ldg(p.Rw + (size_t)w * p.H + __ldg(p.row_hap + row + 1));
+                rw0 = __ldg(p.Rt + (size_t)w * p.nrows + row);
+                rw1 = __ldg(p.Rt + (size_t)w * p.nrows + row + 1);
                 lnb = __ldg(p.lognb4 + (row >> 1));
             }
             const double c0w = __ldg(p.C0 + w);
@@ -1237,12 +1232,10 @@ void ld_tensor_release(ibdgem_engine *e) {
     if (!c) return;
     dev_free(e, c->d_infsite, c->b_infsite);
     dev_free(e, c->d_nk, c->b_nk);
-    dev_free(e, c->d_d1, c->b_d1);
+    dev_free(e, c->d_nr, c->b_nr);
     dev_free(e, c->d_l0, c->b_l0);
     dev_free(e, c->d_C0, c->b_C0);
     dev_free(e, c->d_tbits, c->b_tbits);
-    dev_free(e, c->d_Rw, c->b_Rw);
-    dev_free(e, c->d_Qw, c->b_Qw);
     delete c;
     e->ld = nullptr;
 }
@@ -1269,26 +1262,23 @@ static int build_cache(ibdgem_engine *e) {
         c->N = e->N;
         c->H = 2 * e->N;
         const size_t slots = (size_t)c->nW * c->Wpad;
-        c->b_infsite = slots * 4; c->b_nk = slots; c->b_d1 = slots * 8; c->b_l0 = slots * 8; c->b_C0 = (size_t)c->nW * 8;
+        c->b_infsite = slots * 4; c->b_nk = slots; c->b_nr = slots; c->b_l0 = slots * 8; c->b_C0 = (size_t)c->nW * 8;
         c->b_tbits = (size_t)c->nW * c->H * c->WP32 * 4;
-        c->b_Rw = (size_t)c->nW * c->H * 8;
-        c->b_Qw = (size_t)c->nW * c->N * 8;
         if (dev_alloc(e, (void **)&c->d_infsite, c->b_infsite) || dev_alloc(e, (void **)&c->d_nk, c->b_nk) ||
-            dev_alloc(e, (void **)&c->d_d1, c->b_d1) || dev_alloc(e, (void **)&c->d_l0, c->b_l0) ||
-            dev_alloc(e, (void **)&c->d_C0, c->b_C0) || dev_alloc(e, (void **)&c->d_tbits, c->b_tbits) ||
-            dev_alloc(e, (void **)&c->d_Rw, c->b_Rw) || dev_alloc(e, (void **)&c->d_Qw, c->b_Qw))
+            dev_alloc(e, (void **)&c->d_nr, c->b_nr) || dev_alloc(e, (void **)&c->d_l0, c->b_l0) ||
+            dev_alloc(e, (void **)&c->d_C0, c->b_C0) || dev_alloc(e, (void **)&c->d_tbits, c->b_tbits))
             return 1;
     }
     c->K = e->K_shared;
     IBD_CUDA(cudaMemsetAsync(c->d_infsite, 0xFF, c->b_infsite, e->stream));
     IBD_CUDA(cudaMemsetAsync(c->d_nk, 0, c->b_nk, e->stream));
-    IBD_CUDA(cudaMemsetAsync(c->d_d1, 0, c->b_d1, e->stream));
+    IBD_CUDA(cudaMemsetAsync(c->d_nr, 0, c->b_nr, e->stream));
     IBD_CUDA(cudaMemsetAsync(c->d_l0, 0, c->b_l0, e->stream));
     {
         LaunchScope ls(e, K_LD_COMPACT);
         ld_compact_kernel<<<(unsigned)((e->S + 255) / 256), 256, 0, e->stream>>>(
             e->S, e->d_status, e->d_rank, e->d_nref, e->d_nalt, e->d_lnP, e->C, c->W, c->Wpad, c->d_infsite, c->d_nk,
-            c->d_d1, c->d_l0);
+            c->d_nr, c->d_l0);
     }
     {
         LaunchScope ls(e, K_LD_C0);
@@ -1300,7 +1290,7 @@ static int build_cache(ibdgem_engine *e) {
     return 0;
 }
 
-// Transposed bits and marginals of windows [tw_upto, w_hi).  The caller has made the engine stream
+// Transposed bits of windows [tw_upto, w_hi).  The caller has made the engine stream
 // wait for the panel rows of those windows (wait_panel_upto / ensure_table).
 static int cache_windows(ibdgem_engine *e, int w_hi) {
     LdCache *c = e->ld;
@@ -1308,11 +1298,8 @@ static int cache_windows(ibdgem_engine *e, int w_hi) {
     {
         LaunchScope ls(e, K_LD_TRANSPOSE);
         const int words = (c->H + 31) / 32;
-        int nbits = 1;
-        while ((1 << nbits) <= (int)e->prm.max_cov) nbits++;
         ld_transpose_kernel<<<dim3((words + 7) / 8, w_hi - c->tw_upto), 1024, 0, e->stream>>>(
-            c->tw_upto, e->d_bits, e->Wh, c->H, c->d_infsite, e->d_nref, e->d_nalt, c->Wpad, c->WP32, nbits, c->d_C0, e->alpha,
-            e->beta, e->kappa, c->d_tbits, c->d_Rw, c->d_Qw);
+            c->tw_upto, e->d_bits, e->Wh, c->H, c->d_infsite, c->Wpad, c->WP32, c->d_tbits);
     }
     IBD_CUDA(cudaGetLastError());
     c->tw_upto = w_hi;
@@ -1347,7 +1334,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     }
     const int nU = (int)bgU.size();
     const double nan = (double)NAN;
-    std::vector<int32_t> ownU(T), row_hap(2 * (size_t)T), row_own(2 * (size_t)T);
+    std::vector<int32_t> ownU(T), row_own(2 * (size_t)T);
     std::vector<double> lognb(T), lognb4(T);
     for (int t = 0; t < T; t++) {
         auto itw = where.find(h_targets[t]);
@@ -1356,10 +1343,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         ownU[t] = own;
         lognb[t] = nb > 0 ? log((double)nb) : nan;
         lognb4[t] = nb > 0 ? log(4.0 * (double)nb) : nan;
-        for (int i = 0; i < 2; i++) {
-            row_hap[2 * t + i] = 2 * h_targets[t] + i;
-            row_own[2 * t + i] = own >= 0 ? 2 * own : -1;
-        }
+        row_own[2 * t] = row_own[2 * t + 1] = own >= 0 ? 2 * own : -1;
     }
     const int nW = c->nW;
     // Window ranges: one per panel chunk still in flight (a range is the windows whose last site has
@@ -1378,13 +1362,23 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         range_end.push_back(nW);
     }
     auto range_sites = [&](size_t k) { return range_end.size() == 1 ? e->S : e->chunk_end[k]; };
+    const int nrows = 2 * T;
     if (nU == 0) {  // every background member excluded: LIBD0 = LIBD1 = 0/0 (d_wll is NaN-filled)
-        if (ensure_table(e, e->S) || cache_windows(e, nW)) return 1;
-        LaunchScope ls(e, K_LD_WINDOWS);
-        const int64_t n = (int64_t)T * nW;
-        ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-            0, nW, T, nW, outW, c->W, c->K, d_targets, c->N, e->d_wfirst, e->d_wlast, e->d_pos, c->d_Qw, d_wll, d_wn, d_ws, d_we,
-            d_nwout);
+        double *d_Rt;
+        if (ensure_table(e, e->S) || cache_windows(e, nW) || scratch(e, SC_MMA_ROWLSE, (size_t)nW * nrows * 8, (void **)&d_Rt))
+            return 1;
+        {
+            LaunchScope ls(e, K_LD_WINDOWS);
+            const int64_t n = (int64_t)T * nW;
+            ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+                0, nW, T, nW, outW, c->W, c->K, e->d_wfirst, e->d_wlast, e->d_pos, d_wn, d_ws, d_we, d_nwout);
+        }
+        {
+            LaunchScope ls(e, K_LD_EXPAND_TGT);
+            ld_expand_tgt_kernel<<<dim3((unsigned)((T + 7) / 8), (unsigned)nW), 256, 0, e->stream>>>(
+                0, T, c->H, c->Wpad, c->WP32, outW, d_targets, c->d_tbits, c->d_nr, c->d_nk, c->d_C0, e->alpha, e->beta, e->kappa,
+                nullptr, d_Rt, d_wll);
+        }
         IBD_CUDA(cudaGetLastError());
         return 0;
     }
@@ -1393,7 +1387,6 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     const int CG = mma_cg(variant);
     const int NT = (ncols + mma::BN * CG - 1) / (mma::BN * CG);
     const int ncolpad = NT * mma::BN * CG;
-    const int nrows = 2 * T;
     const int MB = (nrows + mma::BM * CG - 1) / (mma::BM * CG);
 
     const size_t per_window = (size_t)(ncols + nrows) * c->Wpad;
@@ -1403,14 +1396,14 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         budget = sb && atol(sb) > 0 ? (size_t)atol(sb) << 20 : LD_OPERAND_BUDGET;
     }
     const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, budget / per_window));
-    int32_t *d_bgU, *d_ownU, *d_rowhap, *d_rowown, *d_akey;
-    double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp;
+    int32_t *d_bgU, *d_ownU, *d_rowown, *d_akey;
+    double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp, *d_Rt;
     unsigned char *d_A, *d_B;
-    const size_t misc_i = (size_t)nU + T + 4 * (size_t)T;
+    const size_t misc_i = (size_t)nU + T + 2 * (size_t)T;
     const size_t misc_d = (size_t)nU + 2 * (size_t)T;
     if (scratch(e, SC_MMA_MISC, misc_i * 4 + misc_d * 8 + 64, (void **)&d_lnc) ||
         scratch(e, SC_MMA_BGIDX, (size_t)nW * ncolpad * 4, (void **)&d_akey) ||
-        scratch(e, SC_MMA_ROWLSE, (size_t)nW * ncolpad * 8 + (size_t)nW * nU * 8, (void **)&d_Rp) ||
+        scratch(e, SC_MMA_ROWLSE, ((size_t)nW * ncolpad + (size_t)nW * nU + (size_t)nW * nrows) * 8, (void **)&d_Rp) ||
         scratch(e, SC_MMA_TGT, (size_t)nWb * nrows * c->Wpad, (void **)&d_A) ||
         scratch(e, SC_MMA_BG, (size_t)nWb * ncols * c->Wpad, (void **)&d_B))
         return 1;
@@ -1418,15 +1411,14 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     d_lognb4 = d_lognb + T;
     d_bgU = reinterpret_cast<int32_t *>(d_lognb4 + T);
     d_ownU = d_bgU + nU;
-    d_rowhap = d_ownU + T;
-    d_rowown = d_rowhap + 2 * (size_t)T;
+    d_rowown = d_ownU + T;
     d_Qp = d_Rp + (size_t)nW * ncolpad;
+    d_Rt = d_Qp + (size_t)nW * nU;
     IBD_CUDA(cudaMemcpyAsync(d_lnc, lnc.data(), (size_t)nU * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lognb, lognb.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_lognb4, lognb4.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_bgU, bgU.data(), (size_t)nU * 4, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_ownU, ownU.data(), (size_t)T * 4, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_rowhap, row_hap.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     IBD_CUDA(cudaMemcpyAsync(d_rowown, row_own.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     // the host vectors above are pageable: the copies are staged before these calls return
 
@@ -1440,26 +1432,11 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         LaunchScope ls(e, K_LD_WINDOWS);
         const int64_t n = (int64_t)T * (w_hi - w_lo);
         ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-            w_lo, w_hi, T, nW, outW, c->W, c->K, d_targets, c->N, e->d_wfirst, e->d_wlast, e->d_pos, c->d_Qw, d_wll, d_wn, d_ws,
-            d_we, d_nwout);
+            w_lo, w_hi, T, nW, outW, c->W, c->K, e->d_wfirst, e->d_wlast, e->d_pos, d_wn, d_ws, d_we, d_nwout);
     }
     if (w_hi == nW && e->ev_book) {  // START / END / NUM_SITES of every window are final: their copy to the
         IBD_CUDA(cudaEventRecord(e->ev_book, e->stream));  // host can overlap the GEMM (score_common)
         e->book_ready = true;
-    }
-    {
-        LaunchScope ls(e, K_LD_TABLES);
-        const int64_t n = (int64_t)(w_hi - w_lo) * ncolpad;
-        ld_tables_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(w_lo, w_hi, ncols, ncolpad, c->H, d_bgU, d_lnc, c->d_Rw,
-                                                                             c->d_Qw, 1.0 / -e->kappa, d_akey, d_Rp, d_Qp);
-    }
-    {
-        LaunchScope ls(e, K_LD_IBD0);
-        // the window's Q' row is staged in shared memory when it fits (one bulk, coalesced load instead
-        // of latency-bound passes over global memory)
-        const size_t q_smem = (size_t)nU * 8 <= 160 * 1024 ? (size_t)nU * 8 : 0;
-        IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        ld_ibd0_kernel<<<w_hi - w_lo, 256, q_smem, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
     }
     IBD_CUDA(cudaGetLastError());
     // windows are processed in batches so the expanded int8 operands stay within a fixed budget
@@ -1467,15 +1444,16 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         const int nw = std::min(nWb, w_hi - w0);
         {
             LaunchScope ls(e, K_LD_EXPAND_BG);
-            const int per_block = 256 * EXPAND_ILP;
-            ld_expand_bg_kernel<<<dim3((unsigned)((ncols * c->WP32 + per_block - 1) / per_block), (unsigned)nw), 256, 0, e->stream>>>(
-                w0, ncols, c->H, c->WP32, d_bgU, c->d_tbits, reinterpret_cast<uint4 *>(d_B));
+            const int npadU = ncolpad / 2;
+            ld_expand_bg_kernel<<<dim3((unsigned)((npadU + 7) / 8), (unsigned)nw), 256, 0, e->stream>>>(
+                w0, nU, npadU, ncols, ncolpad, c->H, c->Wpad, c->WP32, d_bgU, d_lnc, c->d_tbits, c->d_nr, c->d_nk, c->d_C0,
+                e->alpha, e->beta, e->kappa, 1.0 / -e->kappa, d_B, d_akey, d_Rp, d_Qp);
         }
         {
             LaunchScope ls(e, K_LD_EXPAND_TGT);
-            const int per_block = 256 * EXPAND_ILP;
-            ld_expand_tgt_kernel<<<dim3((unsigned)((nrows * c->WP32 + per_block - 1) / per_block), (unsigned)nw), 256, 0, e->stream>>>(
-                w0, nrows, c->H, c->Wpad, c->WP32, d_targets, c->d_tbits, c->d_nk, reinterpret_cast<uint4 *>(d_A));
+            ld_expand_tgt_kernel<<<dim3((unsigned)((T + 7) / 8), (unsigned)nw), 256, 0, e->stream>>>(
+                w0, T, c->H, c->Wpad, c->WP32, outW, d_targets, c->d_tbits, c->d_nr, c->d_nk, c->d_C0, e->alpha, e->beta,
+                e->kappa, d_A, d_Rt, d_wll);
         }
         IBD_CUDA(cudaGetLastError());
         CUtensorMap mapA, mapB;
@@ -1489,8 +1467,8 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.H = c->H; p.outW = outW;
         p.delta = (int)ceil(screen_nats(ncols) / -e->kappa) + 2;
         p.kappa = e->kappa;
-        p.akey = d_akey; p.Rp = d_Rp; p.Rw = c->d_Rw;
-        p.row_hap = d_rowhap; p.row_own = d_rowown;
+        p.akey = d_akey; p.Rp = d_Rp; p.Rt = d_Rt;
+        p.row_own = d_rowown;
         p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
         {
             static int dbg = -1;
@@ -1534,6 +1512,14 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             }
             cudaFree(d_trace);
         }
+    }
+    {
+        LaunchScope ls(e, K_LD_IBD0);
+        // the window's Q' row is staged in shared memory when it fits (one bulk, coalesced load instead
+        // of latency-bound passes over global memory)
+        const size_t q_smem = (size_t)nU * 8 <= 160 * 1024 ? (size_t)nU * 8 : 0;
+        IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        ld_ibd0_kernel<<<w_hi - w_lo, 256, q_smem, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
     }
     w_lo = w_hi;
     }  // window ranges
