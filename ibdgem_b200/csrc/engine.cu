@@ -56,14 +56,22 @@ LaunchScope::~LaunchScope() {
     e->pending.push_back({id, a, b});
 }
 int resolve_timers(ibdgem_engine *e) {
+    FILE *tl = e->timeline_path && e->t0_set && !e->pending.empty() ? fopen(e->timeline_path, "a") : nullptr;
     for (auto &p : e->pending) {
         float ms = 0;
         cudaEventSynchronize(p.b);
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) e->k_ms[p.id] += ms;
+        if (tl) {
+            float t_a = 0, t_b = 0;
+            cudaEventElapsedTime(&t_a, e->ev_t0, p.a);
+            cudaEventElapsedTime(&t_b, e->ev_t0, p.b);
+            fprintf(tl, "%s %.4f %.4f\n", kKernelNames[p.id], t_a, t_b);
+        }
         e->event_pool.push_back(p.a);
         e->event_pool.push_back(p.b);
     }
     e->pending.clear();
+    if (tl) fclose(tl);
     return 0;
 }
 
@@ -887,6 +895,8 @@ int ibdgem_engine_destroy(ibdgem_engine *e) {
     if (e->ev_order) cudaEventDestroy(e->ev_order);
     if (e->ev_book) cudaEventDestroy(e->ev_book);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (auto ev : e->range_ev) cudaEventDestroy(ev);
+    if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
     delete e;
     return 0;
 }
@@ -905,6 +915,16 @@ int ibdgem_engine_upload_sites(ibdgem_engine *e, int64_t n_sites, const uint64_t
         return 1;
     }
     IBD_CUDA(cudaSetDevice(e->device));
+    if (!e->timeline_path) e->timeline_path = getenv("IBDGEM_TIMELINE");
+    if (e->timeline_path && e->timing) {
+        if (!e->ev_t0) {
+            IBD_CUDA(cudaEventCreate(&e->ev_t0));
+            IBD_CUDA(cudaEventCreate(&e->ev_wll));
+            IBD_CUDA(cudaEventCreate(&e->ev_bookdone));
+        }
+        IBD_CUDA(cudaEventRecord(e->ev_t0, e->stream));
+        e->t0_set = true;
+    }
     if (e->have_panel && e->S != n_sites) {
         set_error("[::] ERROR: site count %lld does not match the uploaded panel (%lld rows).",
                   (long long)n_sites, (long long)e->S);
@@ -960,11 +980,13 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
         IBD_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         IBD_CUDA(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
     }
-    // Few, equal chunks.  Scoring a chunk's windows takes about as long as copying it (9.3 ms vs 11.7 ms
-    // for the whole C3 panel) and every chunk is a separate, less efficient round of launches
-    // (~0.25 ms), so the end-to-end step is ~ copy + (scoring + 0.5 ms D2H) / chunks + 0.25 ms x chunks:
-    // measured 2 chunks 17.1 ms, 3: 15.7, 4: 14.9, 5: 14.7, 6: 15.0; unpipelined 22.5.  Tapered chunk sizes
-    // (IBDGEM_PANEL_TAPER) measured worse: a large first chunk delays the start of scoring.
+    // Equal chunks.  Scoring a chunk's windows takes less time than copying it (C3: 9.0 ms of scoring
+    // against 11.6 ms of PCIe for the whole panel), so the GPU keeps up with the copy and the end-to-end
+    // step is ~ copy + one chunk's scoring + its result copy.  Measured at C3 (bench.py e2e, ms):
+    // 1 chunk 22.5, 5: 13.6, 8: 13.1, 12: 12.8, 16: 12.65, 20: 12.6, 24: 13.3, 32: 14.9, 64: 20.2 — past ~20 the
+    // per-range launches (a dozen per range) cost more than the shorter tail saves.  Tapered sizes
+    // (IBDGEM_PANEL_TAPER < 1) measured no better: the scoring rate is too close to the copy rate for
+    // shrinking chunks to stay ahead.
     static int want_chunks = 0;
     static double taper = 1.0;  // each chunk is `taper` times the size of the one before it
     if (!want_chunks) {
@@ -973,10 +995,11 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
         taper = st ? atof(st) : PANEL_TAPER;
         if (!(taper > 0.1 && taper <= 1.0)) taper = 1.0;
     }
-    const int nchunk = n_sites >= want_chunks * PANEL_CHUNK_MIN ? want_chunks : 1;
+    const size_t panel_bytes = (size_t)n_sites * (size_t)words_per_site * 4;
+    const int nchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)want_chunks, panel_bytes / PANEL_CHUNK_MIN_BYTES));
     while ((int)e->chunk_ev.size() < nchunk) {
         cudaEvent_t ev;
-        IBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        IBD_CUDA(cudaEventCreateWithFlags(&ev, e->t0_set ? cudaEventDefault : cudaEventDisableTiming));
         e->chunk_ev.push_back(ev);
     }
     IBD_CUDA(cudaEventRecord(e->ev_order, e->stream));
@@ -1216,6 +1239,8 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     // everything but the tensor path reads the per-site table and the whole panel up front; the
     // tensor path asks for them window range by window range (upload / scoring overlap)
     if (!tensor && ensure_table(e, S)) return 1;
+    e->wll_streamed = false;
+    e->h_wll_out = out->w_loglik;
     if (tensor) {
         // tensor path: fills window bookkeeping, LIBD0, LIBD1 and LIBD2 of every target
         if (ld_tensor_score(e, T, targets, d_targets, n_bg, bg, pu_idx, outW, d_wll, d_wn, d_ws, d_we, d_nwout)) return 1;
@@ -1305,7 +1330,9 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     // results -> host
     if (out->w_loglik_device)
         IBD_CUDA(cudaMemcpyAsync(out->w_loglik_device, d_wll, nWT * 24, cudaMemcpyDeviceToDevice, e->stream));
-    if (out->w_loglik) IBD_CUDA(cudaMemcpyAsync(out->w_loglik, d_wll, nWT * 24, cudaMemcpyDeviceToHost, e->stream));
+    if (out->w_loglik && !e->wll_streamed)
+        IBD_CUDA(cudaMemcpyAsync(out->w_loglik, d_wll, nWT * 24, cudaMemcpyDeviceToHost, e->stream));
+    if (e->t0_set) IBD_CUDA(cudaEventRecord(e->ev_wll, e->wll_streamed ? e->d2h_stream : e->stream));
     // the bookkeeping arrays of the tensor path are final before the GEMM starts: copy them on the
     // copy stream so the transfer overlaps it
     cudaStream_t bs = e->stream;
@@ -1316,6 +1343,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     if (out->w_nsites) IBD_CUDA(cudaMemcpyAsync(out->w_nsites, d_wn, nWT * 4, cudaMemcpyDeviceToHost, bs));
     if (out->w_start) IBD_CUDA(cudaMemcpyAsync(out->w_start, d_ws, nWT * 8, cudaMemcpyDeviceToHost, bs));
     if (out->w_end) IBD_CUDA(cudaMemcpyAsync(out->w_end, d_we, nWT * 8, cudaMemcpyDeviceToHost, bs));
+    if (e->t0_set) IBD_CUDA(cudaEventRecord(e->ev_bookdone, bs));
     std::vector<int32_t> h_nw(T);
     IBD_CUDA(cudaMemcpyAsync(h_nw.data(), d_nwout, (size_t)T * 4, cudaMemcpyDeviceToHost, e->stream));
     std::vector<unsigned long long> h_cnt;
@@ -1327,8 +1355,20 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     if (out->site_lik) IBD_CUDA(cudaMemcpyAsync(out->site_lik, d_sl, (size_t)T * S * 24, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
     if (e->book_ready) IBD_CUDA(cudaStreamSynchronize(e->copy_stream));
+    if (e->wll_streamed) IBD_CUDA(cudaStreamSynchronize(e->d2h_stream));
     e->book_ready = false;
     resolve_timers(e);
+    if (e->t0_set) {
+        if (FILE *tl = fopen(e->timeline_path, "a")) {
+            float ms = 0;
+            for (size_t k = 0; k < e->chunk_end.size(); k++)
+                if (cudaEventElapsedTime(&ms, e->ev_t0, e->chunk_ev[k]) == cudaSuccess) fprintf(tl, "chunk%d_arrived %.4f %.4f\n", (int)k, ms, ms);
+            if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_wll) == cudaSuccess) fprintf(tl, "wll_on_host %.4f %.4f\n", ms, ms);
+            if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_bookdone) == cudaSuccess) fprintf(tl, "bookkeeping_on_host %.4f %.4f\n", ms, ms);
+            fprintf(tl, "---\n");
+            fclose(tl);
+        }
+    }
 
     for (int t = 0; t < T; t++) {
         if (want_windows && h_nw[t] > outW) {

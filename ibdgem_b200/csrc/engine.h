@@ -98,6 +98,12 @@ struct ibdgem_engine {
     cudaEvent_t ev_order = nullptr;          // engine stream -> copy stream ordering
     cudaEvent_t ev_book = nullptr;           // window bookkeeping of the current call is final (tensor path)
     bool book_ready = false;
+    // window scores of the tensor path leave for the host range by range while later ranges are still
+    // being scored: d2h_stream carries them (copy_stream is busy with the panel chunks)
+    cudaStream_t d2h_stream = nullptr;
+    std::vector<cudaEvent_t> range_ev;
+    double *h_wll_out = nullptr;   // the call's host destination, or nullptr
+    bool wll_streamed = false;     // ld_tensor_score has already issued the copies of d_wll
     std::vector<cudaEvent_t> chunk_ev;       // one per chunk, recorded on copy_stream
     std::vector<int64_t> chunk_end;          // exclusive site end of each chunk
     int chunks_waited = 0;                   // chunks the engine stream already depends on
@@ -130,6 +136,11 @@ struct ibdgem_engine {
     int64_t k_launches[ibdgem::K_COUNT] = {0};
     std::vector<ibdgem::PendingTimer> pending;
     std::vector<cudaEvent_t> event_pool;
+    // IBDGEM_TIMELINE=<file> (with timing on): every launch, panel chunk and result copy of a step
+    // as milliseconds since the step's upload_sites, appended to the file (tools/timeline.py)
+    const char *timeline_path = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_wll = nullptr, ev_bookdone = nullptr;
+    bool t0_set = false;
 
     int last_ld_path = -1;
     int force_general = 0;
@@ -171,9 +182,9 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
                     const int32_t *h_bg, int32_t pu_idx, int32_t outW, double *d_wll /*[T][outW][3]*/, int32_t *d_wn,
                     uint64_t *d_ws, uint64_t *d_we, int32_t *d_nwout);
 void ld_tensor_release(ibdgem_engine *e);
-constexpr int PANEL_CHUNKS = 5;          // upload / scoring pipeline depth
+constexpr int PANEL_CHUNKS = 16;         // upload / scoring pipeline depth
 constexpr double PANEL_TAPER = 1.0;       // chunk k is PANEL_TAPER^k of the first chunk
-constexpr int64_t PANEL_CHUNK_MIN = 32768;  // sites; smaller panels go up in one piece
+constexpr size_t PANEL_CHUNK_MIN_BYTES = (size_t)16 << 20;  // ~0.3 ms of PCIe; smaller panels use fewer chunks
 void ld_tensor_invalidate(ibdgem_engine *e);
 
 }  // namespace ibdgem

@@ -311,8 +311,18 @@ ld_transpose_kernel(int w_off, const uint32_t *__restrict__ bits, int64_t Wh, in
         const int32_t s = infsite[(size_t)w * Wpad + g * 32 + lane];
         const uint32_t *row = bits + (size_t)(s < 0 ? 0 : s) * Wh;
         uint32_t word[8];
+        if ((Wh & 3) == 0) {
+            // rows are 16-byte aligned: two 16-byte loads per lane (a lane reads its own row, so every
+            // load instruction costs 32 L1 wavefronts whatever its width)
+            uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+            if (s >= 0 && j0 < Wh) lo = __ldg(reinterpret_cast<const uint4 *>(row + j0));
+            if (s >= 0 && j0 + 4 < Wh) hi = __ldg(reinterpret_cast<const uint4 *>(row + j0 + 4));
+            word[0] = lo.x; word[1] = lo.y; word[2] = lo.z; word[3] = lo.w;
+            word[4] = hi.x; word[5] = hi.y; word[6] = hi.z; word[7] = hi.w;
+        } else {
 #pragma unroll
-        for (int jj = 0; jj < 8; jj++) word[jj] = (s >= 0 && j0 + jj < Wh) ? __ldg(row + j0 + jj) : 0u;
+            for (int jj = 0; jj < 8; jj++) word[jj] = (s >= 0 && j0 + jj < Wh) ? __ldg(row + j0 + jj) : 0u;
+        }
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) tile[(jj * 32 + lane) * 33 + g] = transpose32(word[jj], lane);
     }
@@ -480,10 +490,10 @@ ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K,
     we[i] = pos[wlast[w]];
 }
 
-// LIBD0: log-mean-exp of Q'_w over the background, the target's own entry omitted (never
-// subtracted).  One block per window; 64 chunk partials so an omission re-scans one chunk only.
+// LIBD0: log-mean-exp of Q'_w over the background without the target's own entry.  One block per
+// window; 64 chunk partials so that re-summing without a dominating own entry scans one chunk only.
 constexpr int IBD0_CHUNKS = 64;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)  // latency-bound: several windows per SM, not one
 ld_ibd0_kernel(int w_off, int T, int nU, int outW, const double *__restrict__ Qp, const int32_t *__restrict__ ownU,
                const double *__restrict__ lognb, double *__restrict__ wll, int stage) {
     extern __shared__ double qs[];
@@ -528,8 +538,12 @@ ld_ibd0_kernel(int w_off, int T, int nU, int outW, const double *__restrict__ Qp
             r = nan;  // n_refpanel = 0: 0/0 in the reference
         } else {
             const int own = ownU[t];
-            if (own < 0 || q[own] < tot_m - 60.0) {
-                r = tot_m + log(tot_s) - lnb;
+            double x = 0;
+            if (own >= 0 && q[own] >= tot_m - 60.0) x = exp_nonpos(q[own] - tot_m);
+            if (x + x <= tot_s) {
+                // own term at most half of the mass: tot_s - x loses at most one bit.  A dominating own
+                // term (the target is the pileup's source) would cancel, so it is left out by re-summing.
+                r = tot_m + log(tot_s - x) - lnb;
             } else {
                 const int oc = own / clen;
                 double m = -INFINITY;
@@ -1422,6 +1436,11 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     IBD_CUDA(cudaMemcpyAsync(d_rowown, row_own.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
     // the host vectors above are pageable: the copies are staged before these calls return
 
+    const bool stream_out = range_end.size() > 1 && e->h_wll_out != nullptr;
+    if (stream_out) {
+        if (!e->d2h_stream) IBD_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+        e->wll_streamed = true;
+    }
     int w_lo = 0;
     for (size_t rk = 0; rk < range_end.size(); rk++) {
     const int w_hi = range_end[rk];
@@ -1521,8 +1540,32 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         ld_ibd0_kernel<<<w_hi - w_lo, 256, q_smem, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
     }
+    if (stream_out) {
+        // the range's columns of d_wll [T][outW][3] are final: a strided copy to the host on its own stream
+        while (e->range_ev.size() <= rk) {
+            cudaEvent_t ev;
+            IBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->range_ev.push_back(ev);
+        }
+        IBD_CUDA(cudaEventRecord(e->range_ev[rk], e->stream));
+        IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->range_ev[rk], 0));
+        IBD_CUDA(cudaMemcpy2DAsync(e->h_wll_out + (size_t)w_lo * 3, (size_t)outW * 24, d_wll + (size_t)w_lo * 3, (size_t)outW * 24,
+                                   (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDeviceToHost, e->d2h_stream));
+    }
     w_lo = w_hi;
     }  // window ranges
+    if (stream_out && outW > nW) {  // the unused columns nW .. outW-1 (NaN since the fill at the start of the call)
+        const size_t rk = range_end.size();
+        while (e->range_ev.size() <= rk) {
+            cudaEvent_t ev;
+            IBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->range_ev.push_back(ev);
+        }
+        IBD_CUDA(cudaEventRecord(e->range_ev[rk], e->stream));
+        IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->range_ev[rk], 0));
+        IBD_CUDA(cudaMemcpy2DAsync(e->h_wll_out + (size_t)nW * 3, (size_t)outW * 24, d_wll + (size_t)nW * 3, (size_t)outW * 24,
+                                   (size_t)(outW - nW) * 24, (size_t)T, cudaMemcpyDeviceToHost, e->d2h_stream));
+    }
     IBD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -35,13 +35,13 @@ def draw_downsampled_counts(case, f_site, keep_site):
     return out
 
 
-def run_engine(case, device=0, force_general=False, expanded=True):
+def run_engine(case, device=0, force_general=False, expanded=True, align_words=4):
     pk, prm = case.pk, case.params
     ep = ib.Params(epsilon=prm.epsilon, max_cov=prm.max_cov, window_size=prm.window, min_af=prm.min_af,
                    max_af=prm.max_af, variable_sites_only=prm.opt_v, device=device)
     with ib.Engine(ep) as e:
         e.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, case.af_user)
-        e.upload_panel(ib.pack_bits(pk.hap), len(pk.names))
+        e.upload_panel(ib.pack_bits(pk.hap, align_words), len(pk.names))
         e.prepare()
         f, st_shared, lik7 = e.get_site_table()
         tc = None

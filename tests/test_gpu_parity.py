@@ -222,8 +222,15 @@ def test_c3_full_size_spot_checks_against_oracle():
     with ib.Engine(ib.Params(window_size=W)) as e:
         e.upload_sites(pos, n_ref, n_alt, keep)
         e.upload_panel(bits, N)
-        sc = e.score_ld(targets, bg, -1)
+        sc = e.score_ld(targets, bg, -1)  # panel chunks still in flight: ranges of windows, streamed results
         assert e.last_ld_path() == 1  # the tensor-core path is the one that ran
+        sc2 = e.score_ld(targets, bg, -1)  # panel resident: one range, one result copy
+    for a, b in ((sc.w_start, sc2.w_start), (sc.w_end, sc2.w_end), (sc.w_nsites, sc2.w_nsites),
+                 (sc.n_windows, sc2.n_windows)):
+        np.testing.assert_array_equal(a, b)
+    # the order in which a row's tiles reach the fp64 log-sum-exp follows the dynamic unit schedule:
+    # the two runs may differ in the last bits (NaN == NaN here: the unused trailing columns)
+    np.testing.assert_allclose(sc.w_loglik, sc2.w_loglik, rtol=0, atol=1e-9, equal_nan=True)
     nW = S // W
     assert (sc.n_windows == nW).all()
     assert (sc.w_nsites[:, :nW] == W).all() and int(sc.processed[0]) == S and int(sc.skipped[0]) == 0
@@ -319,7 +326,7 @@ def test_ld_window_batching_under_a_small_operand_budget():
 
 def test_ld_deep_pileup_large_max_cov():
     """Depths well above the default: the int8 target operand carries n_s up to max_cov (unsigned),
-    the count bit planes need 6 bits, and kappa * M spans thousands of nats."""
+    the dp4a marginals sum count bytes above 31, and kappa * M spans thousands of nats."""
     ec = _engine()
     case = _synth_case(71, 5000, 48, 300, True, range(10), pu_idx=4, depth=14.0, max_cov=60)
     results = ec.run_engine(case, expanded=False)
@@ -336,3 +343,15 @@ def test_ld_window_larger_than_tensor_tile_uses_general_path():
     assert results[0]["ld_path"] == 0
     for res, ora in zip(results, refcases.oracle_run(case)):
         ec.assert_matches_oracle(res, ora)
+
+
+@pytest.mark.parametrize("ld", [True, False])
+def test_panel_rows_not_16_byte_aligned(ld):
+    """words_per_site is the caller's choice (include/ibdgem_b200.h): 3 words per row here, so no
+    kernel may assume 16-byte-aligned panel rows."""
+    ec = _engine()
+    case = _synth_case(73, 3000, 40, 100, ld, range(6), pu_idx=1)
+    for fg in ((True, False) if ld else (False,)):
+        results = ec.run_engine(case, force_general=fg, expanded=False, align_words=1)
+        for res, ora in zip(results, refcases.oracle_run(case)):
+            ec.assert_matches_oracle(res, ora)
