@@ -27,7 +27,7 @@ void set_error(const char *fmt, ...) {
 const char *const kKernelNames[K_COUNT] = {
     "site_table",     "scan_count",    "scan_offsets",  "scan_rank",    "window_nonld", "counters",
     "expand_sites",   "ld_general",    "ld_finalize",   "ld_compact",   "ld_c0",        "ld_transpose",
-    "ld_expand_bg",  "ld_expand_tgt", "ld_windows",  "ld_ibd0",
+    "ld_stage",       "ld_expand_bg",  "ld_expand_tgt", "ld_windows",   "ld_ibd0",
     "ld_mma",         "viterbi",       "viterbi_norm",  "viterbi_back", "viterbi_out", "fill",
 };
 
@@ -86,6 +86,19 @@ void dev_free(ibdgem_engine *e, void *p, size_t bytes) {
     if (!p) return;
     cudaFree(p);
     e->device_bytes -= (int64_t)(bytes ? bytes : 16);
+}
+
+int pinned_stage(ibdgem_engine *e, size_t bytes, void **out) {
+    if (e->h_pin_cap < bytes) {
+        if (e->h_pin) cudaFreeHost(e->h_pin);
+        e->h_pin = nullptr;
+        e->h_pin_cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        IBD_CUDA(cudaMallocHost(&e->h_pin, want));
+        e->h_pin_cap = want;
+    }
+    *out = e->h_pin;
+    return 0;
 }
 
 int scratch(ibdgem_engine *e, int slot, size_t bytes, void **out) {
@@ -897,6 +910,7 @@ int ibdgem_engine_destroy(ibdgem_engine *e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (auto ev : e->range_ev) cudaEventDestroy(ev);
     if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
+    if (e->h_pin) cudaFreeHost(e->h_pin);
     delete e;
     return 0;
 }
@@ -1108,18 +1122,19 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     SiteView v = make_view(e, nullptr, 0);
     v.bits = nullptr;  // the shared map (vflag = 0, no per-target counts) never looks at genotypes
     if (build_window_map(e, v, nullptr, 1, maxW, e->d_wfirst, e->d_wlast, d_nwin, d_ktot, e->d_rank)) return 1;
-    int32_t nwin = 0;
-    int64_t ktot = 0;
-    IBD_CUDA(cudaMemcpyAsync(&nwin, d_nwin, 4, cudaMemcpyDeviceToHost, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(&ktot, d_ktot, 8, cudaMemcpyDeviceToHost, e->stream));
+    // window count, kept-site total and the last site of every window in one round trip through pinned
+    // memory (the map has at most maxW windows)
+    int64_t *h_map;
+    if (pinned_stage(e, (size_t)(maxW + 2) * 8, (void **)&h_map)) return 1;
+    IBD_CUDA(cudaMemcpyAsync(h_map, d_nwin, 4, cudaMemcpyDeviceToHost, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(h_map + 1, d_ktot, 8, cudaMemcpyDeviceToHost, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(h_map + 2, e->d_wlast, (size_t)maxW * 8, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
+    const int32_t nwin = *reinterpret_cast<const int32_t *>(h_map);
+    const int64_t ktot = h_map[1];
     e->nW_shared = nwin;
     e->K_shared = ktot;
-    e->h_wlast.assign((size_t)std::max(nwin, 0), 0);
-    if (nwin > 0) {
-        IBD_CUDA(cudaMemcpyAsync(e->h_wlast.data(), e->d_wlast, (size_t)nwin * 8, cudaMemcpyDeviceToHost, e->stream));
-        IBD_CUDA(cudaStreamSynchronize(e->stream));
-    }
+    e->h_wlast.assign(h_map + 2, h_map + 2 + std::max(nwin, 0));
     e->prepared = true;
     ld_tensor_invalidate(e);
     resolve_timers(e);

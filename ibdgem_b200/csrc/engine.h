@@ -35,14 +35,14 @@ enum KernelId {
     K_EXPAND_SITES,     // expanded per-target tab values
     K_LD_GENERAL,       // L1 general CUDA-core --LD window kernel
     K_LD_FINALIZE,      // L2 merge of background-block partial log-sum-exps
-    K_LD_COMPACT,       // tensor path: informative sites -> window slots (depth, l1-l0, l0)
+    K_LD_COMPACT,       // tensor path: informative sites -> window slots (n, n_ref, l0)
     K_LD_C0,            // tensor path: per-window sum of l0
-    K_LD_TRANSPOSE,     // tensor path: site-major bits -> window-padded haplotype-major bits, fused with the
-                        // per-window per-haplotype linear terms and the per-individual chain
-    K_LD_EXPAND_BG,     // tensor path: background operand (0/1 int8, K-major)
-    K_LD_EXPAND_TGT,    // tensor path: target operand (depth-weighted int8, K-major)
-    K_LD_WINDOWS,       // tensor path: window bookkeeping + LIBD2
-    K_LD_IBD0,          // tensor path: LIBD0 log-mean-exp with exclusion by omission
+    K_LD_TRANSPOSE,     // tensor path: site-major bits -> window-padded haplotype-major bits
+    K_LD_STAGE,         // tensor path: the call's small tables, read straight from pinned host memory
+    K_LD_EXPAND_BG,     // tensor path: background operand (0/1 int8, K-major) + column marginals, keys, Q'
+    K_LD_EXPAND_TGT,    // tensor path: target operand (depth-weighted int8, K-major) + row marginals, LIBD2
+    K_LD_WINDOWS,       // tensor path: window bookkeeping
+    K_LD_IBD0,          // tensor path: LIBD0 log-mean-exp over the background without the target
     K_LD_MMA,           // tensor path: tcgen05 window GEMM + fused log-sum-exp epilogue -> LIBD1
     K_VITERBI,          // H2 hiddengem forward pass (or the whole per-table kernel for small batches)
     K_VITERBI_NORM,     // H1 ln of the normalised likelihoods, to bin-major
@@ -127,6 +127,8 @@ struct ibdgem_engine {
     ibdgem::LdCache *ld = nullptr;
 
     // scratch
+    void *h_pin = nullptr;  // pinned staging for the small per-call host <-> device tables (grow-only)
+    size_t h_pin_cap = 0;
     std::vector<ibdgem::DeviceBuf *> scratch;
     int64_t device_bytes = 0;
 
@@ -157,6 +159,9 @@ struct LaunchScope {
     ~LaunchScope();
 };
 int resolve_timers(ibdgem_engine *e);
+// Pinned host staging of at least `bytes`.  One buffer: a caller must have synchronised the stream
+// that reads or writes it before the next caller asks (every ABI call ends with such a sync).
+int pinned_stage(ibdgem_engine *e, size_t bytes, void **out);
 
 // grow-only scratch slots, kept across calls so steady-state scoring does not allocate
 enum ScratchSlot {

@@ -22,6 +22,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <map>
@@ -347,6 +348,12 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// K_LD_STAGE: words from pinned (mapped) host memory to the device
+__global__ void __launch_bounds__(256) ld_stage_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
 }
 
 // K_LD_EXPAND_BG: one warp per (window, background individual), lane = 32-site word.  Writes the
@@ -1333,26 +1340,28 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     LdCache *c = e->ld;
     // unique background individuals with multiplicities; the pileup's own individual never
     // contributes (src/ibdgem.c:714), duplicates become a ln(multiplicity) weight
-    std::map<int32_t, int32_t> mult;
+    // (ordinals were range-checked by the caller; plain arrays — this runs on the host between two
+    // stretches of device work)
+    std::vector<int32_t> mult((size_t)c->N, 0), where((size_t)c->N, -1);
+    int64_t total_bg = 0;
     for (int n = 0; n < n_bg; n++)
-        if (h_bg[n] != pu_idx) mult[h_bg[n]]++;
+        if (h_bg[n] != pu_idx) { mult[h_bg[n]]++; total_bg++; }
     std::vector<int32_t> bgU;
     std::vector<double> lnc;
-    std::map<int32_t, int32_t> where;
-    int64_t total_bg = 0;
-    for (auto &kv : mult) {
-        where[kv.first] = (int32_t)bgU.size();
-        bgU.push_back(kv.first);
-        lnc.push_back(log((double)kv.second));
-        total_bg += kv.second;
-    }
+    bgU.reserve((size_t)c->N);
+    lnc.reserve((size_t)c->N);
+    for (int32_t b = 0; b < c->N; b++)
+        if (mult[b]) {
+            where[b] = (int32_t)bgU.size();
+            bgU.push_back(b);
+            lnc.push_back(mult[b] == 1 ? 0.0 : log((double)mult[b]));
+        }
     const int nU = (int)bgU.size();
     const double nan = (double)NAN;
     std::vector<int32_t> ownU(T), row_own(2 * (size_t)T);
     std::vector<double> lognb(T), lognb4(T);
     for (int t = 0; t < T; t++) {
-        auto itw = where.find(h_targets[t]);
-        const int own = itw == where.end() ? -1 : itw->second;
+        const int own = where[h_targets[t]];
         const int64_t nb = total_bg - (own >= 0 ? mult[h_targets[t]] : 0);
         ownU[t] = own;
         lognb[t] = nb > 0 ? log((double)nb) : nan;
@@ -1428,13 +1437,25 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     d_rowown = d_ownU + T;
     d_Qp = d_Rp + (size_t)nW * ncolpad;
     d_Rt = d_Qp + (size_t)nW * nU;
-    IBD_CUDA(cudaMemcpyAsync(d_lnc, lnc.data(), (size_t)nU * 8, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_lognb, lognb.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_lognb4, lognb4.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_bgU, bgU.data(), (size_t)nU * 4, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_ownU, ownU.data(), (size_t)T * 4, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_rowown, row_own.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
-    // the host vectors above are pageable: the copies are staged before these calls return
+    {
+        // the call's small tables go up in one piece from pinned memory, laid out like SC_MMA_MISC
+        void *h_misc;
+        if (pinned_stage(e, misc_d * 8 + misc_i * 4, &h_misc)) return 1;
+        double *hd = static_cast<double *>(h_misc);
+        memcpy(hd, lnc.data(), (size_t)nU * 8);
+        memcpy(hd + nU, lognb.data(), (size_t)T * 8);
+        memcpy(hd + nU + T, lognb4.data(), (size_t)T * 8);
+        int32_t *hi = reinterpret_cast<int32_t *>(hd + misc_d);
+        memcpy(hi, bgU.data(), (size_t)nU * 4);
+        memcpy(hi + nU, ownU.data(), (size_t)T * 4);
+        memcpy(hi + nU + T, row_own.data(), (size_t)T * 8);
+        // Not a cudaMemcpyAsync: a DMA copy would queue on the host-to-device copy engine behind the panel
+        // chunks still in flight and hold the scoring of the first windows back until the whole panel is up.
+        LaunchScope ls(e, K_LD_STAGE);
+        const int n = (int)((misc_d * 8 + misc_i * 4) / 4);
+        ld_stage_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(reinterpret_cast<uint32_t *>(d_lnc),
+                                                               static_cast<const uint32_t *>(h_misc), n);
+    }
 
     const bool stream_out = range_end.size() > 1 && e->h_wll_out != nullptr;
     if (stream_out) {
