@@ -319,6 +319,7 @@ def main():
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------
     upload()
+    eng.sync_uploads()  # the panel is resident before the first step, not still arriving in chunks
     eng.prepare()
     for _ in range(max(args.warmup, 3)):
         score()

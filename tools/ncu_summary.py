@@ -27,8 +27,9 @@ def raw(path):
         name = name.replace("void ", "").replace("ibdgem::", "")[:48]
         cells = []
         for k in KEYS:
-            if k in hdr:
-                i = hdr.index(k)
+            hit = [j for j, h in enumerate(hdr) if h == k or h.endswith("." + k)]  # some carry a section prefix
+            if hit:
+                i = hit[0]
                 cells.append("%s %s" % (r[i], units[i]))
             else:
                 cells.append("n/a")
