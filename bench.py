@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-targets", type=int, default=16, help="targets of the single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-general", action="store_true", help="A/B: CUDA-core --LD path")
+    ap.add_argument("--panel-pieces", type=int, default=int(os.environ.get("IBDGEM_BENCH_PANEL_PIECES", "4")),
+                    help="N>1: the panel is replicated over NVLink in this many pieces (0 = every rank uploads all of it)")
     return ap.parse_args()
 
 
@@ -282,9 +284,22 @@ def main():
     cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr(), o_we.data_ptr(), o_wn.data_ptr(), o_ll.data_ptr(),
                   None, None, None, None, None, None, d_ll.data_ptr())
 
+    # N > 1: the packed panel is the same on every rank, so each rank copies 1/N of it over PCIe and the
+    # ranks all_gather the pieces over NVLink (shard.replicate_panel) instead of N full uploads
+    replicate = world > 1 and args.panel_pieces > 0
+    if replicate:
+        from ibdgem_b200.shard import panel_pieces, replicate_panel
+        _, padded_rows = panel_pieces(S, world, args.panel_pieces)
+        d_panel = torch.empty((padded_rows, bits.shape[1]), dtype=torch.int32, device=dev)
+        up_stream = torch.cuda.Stream(device=dev)
+
     def upload():
         eng.upload_sites(pos, n_ref, n_alt, keep)
-        eng.upload_panel(bits, N)
+        if replicate:
+            up_stream.wait_stream(stream)
+            replicate_panel(eng, d["bits"], d_panel, N, pieces=args.panel_pieces, stream=up_stream)
+        else:
+            eng.upload_panel(bits, N)
 
     def score():
         # one step = the whole path from the packed inputs resident in HBM: allele-frequency popcount
@@ -320,6 +335,7 @@ def main():
     # ---- value: inputs resident in HBM ---------------------------------------------------------
     upload()
     eng.sync_uploads()  # the panel is resident before the first step, not still arriving in chunks
+    torch.cuda.synchronize()
     eng.prepare()
     for _ in range(max(args.warmup, 3)):
         score()
@@ -344,7 +360,7 @@ def main():
         e2e_step()
     e2e_steps = max(2, min(args.steps, 3))
     ms_e2e = timed(e2e_step, e2e_steps) / e2e_steps
-    h2d = bits.nbytes + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes
+    h2d = (bits.nbytes // world if replicate else bits.nbytes) + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes
     d2h = o_nw.numel() * 4 + o_ws.numel() * 8 * 2 + o_wn.numel() * 4 + o_ll.numel() * 8
     e2e_value = comps_rank * world / (ms_e2e * 1e-3)
 
@@ -398,13 +414,16 @@ def main():
             "config": {"workload": "C3 --LD scoring: %d sites x %d-sample phased panel, %d targets per GPU, "
                                    "window %d, depth Poisson(2)+1 (BASELINE.json configs[2])" % (S, N, T, W),
                        "sites": S, "samples": N, "targets_per_gpu": T, "window": W,
-                       "parallelism": "targets sharded across %d GPU(s), panel replicated, one all_gather of "
-                                      "window scores" % world,
+                       "parallelism": "targets sharded across %d GPU(s), panel replicated%s, one all_gather of "
+                                      "window scores" % (world, (" (e2e: each rank uploads 1/%d of it over PCIe, "
+                                                                 "%d all_gather pieces over NVLink)" % (world, args.panel_pieces))
+                                                         if replicate else ""),
                        "ld_path": "tensor (tcgen05 int8 window GEMM + fused LSE)" if ld_path == 1 else "general CUDA-core",
                        "l2": "inputs larger than L2 (packed panel %.0f MB, operands %.1f GB)" % (
                            bits.nbytes / 1e6, eng.device_bytes() / 1e9)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "bytes_are": "per rank",
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches,
             "roofline": roofline,

@@ -13,6 +13,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 ABI_SYMBOLS = [
     "ibdgem_engine_create", "ibdgem_engine_destroy", "ibdgem_last_error", "ibdgem_abi_version",
     "ibdgem_engine_set_stream", "ibdgem_engine_upload_sites", "ibdgem_engine_upload_panel", "ibdgem_engine_sync_uploads",
+    "ibdgem_engine_set_panel_device", "ibdgem_engine_panel_rows_ready",
     "ibdgem_engine_prepare", "ibdgem_engine_invalidate", "ibdgem_engine_get_site_table", "ibdgem_engine_score_nonld",
     "ibdgem_engine_score_ld", "ibdgem_engine_last_ld_path", "ibdgem_engine_force_general_ld",
     "hiddengem_viterbi_batch", "ibdgem_engine_enable_timing", "ibdgem_engine_reset_stats",

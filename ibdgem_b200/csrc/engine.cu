@@ -707,6 +707,11 @@ int wait_panel_upto(ibdgem_engine *e, int64_t s_end) {
         IBD_CUDA(cudaStreamWaitEvent(e->stream, e->chunk_ev[(size_t)e->chunks_waited], 0));
         e->chunks_waited++;
     }
+    if (e->chunk_end.empty() || e->chunk_end.back() < s_end) {
+        set_error("[::] ERROR: panel rows up to %lld are needed but only %lld were declared ready "
+                  "(ibdgem_engine_panel_rows_ready).", (long long)s_end, (long long)(e->chunk_end.empty() ? 0 : e->chunk_end.back()));
+        return 1;
+    }
     return 0;
 }
 
@@ -857,8 +862,9 @@ static void free_sites(ibdgem_engine *e) {
     e->have_sites = false;
 }
 static void free_panel(ibdgem_engine *e, int64_t S) {
-    if (e->d_bits) dev_free(e, e->d_bits, (size_t)S * e->Wh * 4);
+    if (e->d_bits && e->owns_bits) dev_free(e, e->d_bits, (size_t)S * e->Wh * 4);
     e->d_bits = nullptr;
+    e->owns_bits = true;
     e->have_panel = false;
 }
 static void free_prepared(ibdgem_engine *e, int64_t S) {
@@ -983,6 +989,7 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
         free_prepared(e, e->S);
         free_panel(e, e->S);
     }
+    if (e->have_panel && !e->owns_bits) free_panel(e, e->S);  // never copy into the caller's device buffer
     if (!e->have_panel) {
         e->S = n_sites;
         e->Wh = words_per_site;
@@ -1038,6 +1045,62 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
     e->prepared = false;
     e->table_upto = 0;
     ld_tensor_invalidate(e);
+    return 0;
+}
+
+int ibdgem_engine_set_panel_device(ibdgem_engine *e, int64_t n_sites, int32_t n_indiv, const uint32_t *d_bits,
+                                   int64_t words_per_site) {
+    if (!e || n_sites <= 0 || n_indiv <= 0 || !d_bits || words_per_site * 32 < 2 * (int64_t)n_indiv) {
+        set_error("[::] ERROR in ibdgem_engine_set_panel_device(): bad arguments.");
+        return 1;
+    }
+    IBD_CUDA(cudaSetDevice(e->device));
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, d_bits) != cudaSuccess || attr.type != cudaMemoryTypeDevice || attr.device != e->device) {
+        cudaGetLastError();
+        set_error("[::] ERROR in ibdgem_engine_set_panel_device(): d_bits is not device memory of GPU %d.", e->device);
+        return 1;
+    }
+    if (e->have_sites && e->S != n_sites) {
+        set_error("[::] ERROR: panel has %lld rows but %lld sites were uploaded.", (long long)n_sites, (long long)e->S);
+        return 1;
+    }
+    // kernels of an earlier call may still read the old buffer
+    IBD_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->have_panel && (e->S != n_sites || e->Wh != words_per_site)) free_prepared(e, e->S);
+    if (e->have_panel) free_panel(e, e->S);
+    e->S = n_sites;
+    e->Wh = words_per_site;
+    e->N = n_indiv;
+    e->d_bits = const_cast<uint32_t *>(d_bits);
+    e->owns_bits = false;
+    e->chunk_end.clear();
+    e->chunks_waited = 0;
+    e->have_panel = true;
+    e->prepared = false;
+    e->table_upto = 0;
+    ld_tensor_invalidate(e);
+    return 0;
+}
+
+int ibdgem_engine_panel_rows_ready(ibdgem_engine *e, int64_t row_end, void *stream) {
+    if (!e || !e->have_panel || e->owns_bits) {
+        set_error("[::] ERROR in ibdgem_engine_panel_rows_ready(): no caller-owned device panel is set.");
+        return 1;
+    }
+    if (row_end <= 0 || row_end > e->S || (!e->chunk_end.empty() && row_end < e->chunk_end.back())) {
+        set_error("[::] ERROR in ibdgem_engine_panel_rows_ready(): row_end %lld out of order or range.", (long long)row_end);
+        return 1;
+    }
+    IBD_CUDA(cudaSetDevice(e->device));
+    const size_t k = e->chunk_end.size();
+    while (e->chunk_ev.size() <= k) {
+        cudaEvent_t ev;
+        IBD_CUDA(cudaEventCreateWithFlags(&ev, e->t0_set ? cudaEventDefault : cudaEventDisableTiming));
+        e->chunk_ev.push_back(ev);
+    }
+    IBD_CUDA(cudaEventRecord(e->chunk_ev[k], stream ? static_cast<cudaStream_t>(stream) : e->stream));
+    e->chunk_end.push_back(row_end);
     return 0;
 }
 

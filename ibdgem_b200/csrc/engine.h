@@ -90,6 +90,7 @@ struct ibdgem_engine {
     uint8_t *d_nref = nullptr, *d_nalt = nullptr, *d_hostkeep = nullptr;
     double *d_afuser = nullptr;
     uint32_t *d_bits = nullptr;
+    bool owns_bits = true;  // false: d_bits is the caller's device buffer (ibdgem_engine_set_panel_device)
     bool have_sites = false, have_panel = false, prepared = false;
 
     // The panel is copied in site chunks on its own stream; the engine stream waits for a chunk only

@@ -403,10 +403,10 @@ ld_expand_bg_kernel(int w0, int nU, int npadU, int ncols, int ncolpad, int H, in
         }
         uint4 *o0 = reinterpret_cast<uint4 *>(out + ((size_t)wl * ncols + 2 * u) * Wpad) + lane * 2;
         uint4 *o1 = reinterpret_cast<uint4 *>(out + ((size_t)wl * ncols + 2 * u + 1) * Wpad) + lane * 2;
-        o0[0] = make_uint4(e0[0], e0[1], e0[2], e0[3]);
-        o0[1] = make_uint4(e0[4], e0[5], e0[6], e0[7]);
-        o1[0] = make_uint4(e1[0], e1[1], e1[2], e1[3]);
-        o1[1] = make_uint4(e1[4], e1[5], e1[6], e1[7]);
+        __stcs(o0, make_uint4(e0[0], e0[1], e0[2], e0[3]));
+        __stcs(o0 + 1, make_uint4(e0[4], e0[5], e0[6], e0[7]));
+        __stcs(o1, make_uint4(e1[0], e1[1], e1[2], e1[3]));
+        __stcs(o1 + 1, make_uint4(e1[4], e1[5], e1[6], e1[7]));
     }
     A0 = warp_sum(A0); N0 = warp_sum(N0); A1 = warp_sum(A1); N1 = warp_sum(N1); M = warp_sum(M);
     if (lane == 0) {
@@ -463,10 +463,10 @@ ld_expand_tgt_kernel(int w0, int T, int H, int Wpad, int WP32, int outW, const i
             }
             uint4 *o0 = reinterpret_cast<uint4 *>(out + ((size_t)wl * 2 * T + 2 * t) * Wpad) + lane * 2;
             uint4 *o1 = reinterpret_cast<uint4 *>(out + ((size_t)wl * 2 * T + 2 * t + 1) * Wpad) + lane * 2;
-            o0[0] = make_uint4(e0[0], e0[1], e0[2], e0[3]);
-            o0[1] = make_uint4(e0[4], e0[5], e0[6], e0[7]);
-            o1[0] = make_uint4(e1[0], e1[1], e1[2], e1[3]);
-            o1[1] = make_uint4(e1[4], e1[5], e1[6], e1[7]);
+            __stcs(o0, make_uint4(e0[0], e0[1], e0[2], e0[3]));
+            __stcs(o0 + 1, make_uint4(e0[4], e0[5], e0[6], e0[7]));
+            __stcs(o1, make_uint4(e1[0], e1[1], e1[2], e1[3]));
+            __stcs(o1 + 1, make_uint4(e1[4], e1[5], e1[6], e1[7]));
         }
     }
     A0 = warp_sum(A0); N0 = warp_sum(N0); A1 = warp_sum(A1); N1 = warp_sum(N1); M = warp_sum(M);

@@ -114,6 +114,17 @@ class Engine:
         self._check(self._lib.ibdgem_engine_upload_panel(self._h, C.c_int64(bits.shape[0]), C.c_int32(n_indiv),
                                                          _ptr(bits), C.c_int64(bits.shape[1])))
 
+    def set_panel_device(self, d_bits_ptr: int, n_sites: int, n_indiv: int, words_per_site: int):
+        """Panel rows live in caller-owned device memory (see shard.replicate_panel); declare them
+        readable piece by piece with panel_rows_ready()."""
+        self._bits = None
+        self.N = int(n_indiv)
+        self._check(self._lib.ibdgem_engine_set_panel_device(self._h, C.c_int64(n_sites), C.c_int32(n_indiv),
+                                                             C.c_void_p(d_bits_ptr), C.c_int64(words_per_site)))
+
+    def panel_rows_ready(self, row_end: int, stream: int = 0):
+        self._check(self._lib.ibdgem_engine_panel_rows_ready(self._h, C.c_int64(row_end), C.c_void_p(stream or None)))
+
     def sync_uploads(self):
         self._check(self._lib.ibdgem_engine_sync_uploads(self._h))
 

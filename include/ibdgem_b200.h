@@ -106,6 +106,20 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
  * whose rows have already arrived; with pageable memory it is simply complete on return. */
 int ibdgem_engine_sync_uploads(ibdgem_engine *e);
 
+/* Panel already in device memory.  Multi-GPU use: the packed panel is identical on every rank, so each
+ * rank copies 1/N of it over PCIe and the ranks exchange the pieces over NVLink (one all_gather per
+ * piece; ibdgem_b200/shard.py replicate_panel) instead of N full uploads through the host bridges.
+ * `d_bits` is caller-owned device memory in the layout of ibdgem_engine_upload_panel; it must stay
+ * valid and, once declared ready, unchanged until another panel is set or the engine is destroyed.
+ * Rows become readable in pieces: after set_panel_device none is; every
+ * ibdgem_engine_panel_rows_ready(e, row_end, stream) declares rows [0, row_end) complete once the work
+ * enqueued so far on `stream` (a cudaStream_t passed as void*; NULL = the engine's own stream) has run.
+ * row_end must not decrease; scoring proceeds window range by window range as the pieces are declared,
+ * exactly as with upload_panel's own chunks, and fails if it needs rows that were never declared. */
+int ibdgem_engine_set_panel_device(ibdgem_engine *e, int64_t n_sites, int32_t n_indiv,
+                                   const uint32_t *d_bits, int64_t words_per_site);
+int ibdgem_engine_panel_rows_ready(ibdgem_engine *e, int64_t row_end, void *stream);
+
 /* Target-independent stage: allele frequency by popcount over the packed row (find_f_impute /
  * find_f_vcf, src/ibd-parse.c:91-110), the AF-range and max-cov filters (src/ibdgem.c:616-626),
  * per-site IBD0 / IBD1[g] / IBD2[g] (find_pDgf, find_pDgIBD1, src/ibd-math.c:84-142) and the

@@ -355,3 +355,37 @@ def test_panel_rows_not_16_byte_aligned(ld):
         results = ec.run_engine(case, force_general=fg, expanded=False, align_words=1)
         for res, ora in zip(results, refcases.oracle_run(case)):
             ec.assert_matches_oracle(res, ora)
+
+
+def test_panel_in_caller_device_memory_declared_in_pieces():
+    """ibdgem_engine_set_panel_device / _panel_rows_ready (the NVLink replication path of
+    shard.replicate_panel, here on one GPU): same scores as ibdgem_engine_upload_panel; rows that were
+    never declared ready are an error, not a read of unwritten memory."""
+    import torch
+    import ibdgem_b200 as ib
+    from ibdgem_b200.shard import panel_pieces, replicate_panel
+    ec = _engine()
+    case = _synth_case(74, 6000, 40, 100, True, range(7), pu_idx=3)
+    pk = case.pk
+    want = ec.run_engine(case, expanded=False)
+    bits = ib.pack_bits(pk.hap)
+    h_bits = torch.from_numpy(bits.view(np.int32)).pin_memory()
+    S, Wh = bits.shape
+    with ib.Engine(ib.Params(window_size=100)) as e:
+        e.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, None)
+        for pieces in (1, 3):
+            per, padded = panel_pieces(S, 1, pieces)
+            d_panel = torch.empty((padded, Wh), dtype=torch.int32, device="cuda")
+            side = torch.cuda.Stream()
+            replicate_panel(e, h_bits, d_panel, len(pk.names), pieces=pieces, stream=side)
+            sc = e.score_ld(case.targets, case.bg, 3)
+            for k, w in enumerate(want):
+                nw = w["n_windows"]
+                assert int(sc.n_windows[k]) == nw
+                np.testing.assert_allclose(sc.w_loglik[k, :nw], w["w_log"], rtol=0, atol=1e-9)
+                np.testing.assert_array_equal(sc.w_nsites[k, :nw], w["w_nsites"])
+        d_panel = torch.from_numpy(bits.view(np.int32)).cuda()
+        e.set_panel_device(d_panel.data_ptr(), S, len(pk.names), Wh)
+        e.panel_rows_ready(S // 2)
+        with pytest.raises(RuntimeError, match="declared ready"):
+            e.score_ld(case.targets, case.bg, 3)

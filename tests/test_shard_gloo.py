@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ibdgem_b200.shard import gather_window_scores, shard_bounds, shard_targets
+from ibdgem_b200.shard import gather_window_scores, panel_pieces, replicate_panel, shard_bounds, shard_targets
 
 
 def test_shard_bounds_partition():
@@ -89,3 +89,56 @@ def test_two_rank_gather_matches_unsharded():
     for r in range(world):
         np.testing.assert_array_equal(np.isnan(got[r]), np.isnan(want))
         np.testing.assert_array_equal(np.nan_to_num(got[r]), np.nan_to_num(want))
+
+
+class _RecordingEngine:
+    """Stands in for ibdgem_b200.Engine: replicate_panel only calls these two methods."""
+
+    def __init__(self):
+        self.calls = []
+
+    def set_panel_device(self, ptr, n_sites, n_indiv, wh):
+        self.calls.append(("set", n_sites, n_indiv, wh))
+
+    def panel_rows_ready(self, row_end, stream=0):
+        self.calls.append(("ready", row_end))
+
+
+def _panel_worker(rank, world, port, q, S, pieces):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Wh = 5
+        h_bits = torch.arange(S * Wh, dtype=torch.int32).reshape(S, Wh)  # identical on every rank
+        per, padded = panel_pieces(S, world, pieces)
+        d_panel = torch.full((padded, Wh), -1, dtype=torch.int32)
+        eng = _RecordingEngine()
+        replicate_panel(eng, h_bits, d_panel, n_indiv=40, pieces=pieces)
+        q.put((rank, d_panel[:S].numpy().copy(), eng.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("S,pieces", [(1000, 1), (1003, 4), (7, 3)])
+def test_two_rank_panel_replication(S, pieces):
+    """Every rank copies only its share of each piece; after the all_gathers both hold the whole
+    panel, and the pieces were declared to the engine in increasing row order up to S."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_panel_worker, args=(r, world, port, q, S, pieces)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    want = np.arange(S * 5, dtype=np.int32).reshape(S, 5)
+    for rank, panel, calls in got:
+        np.testing.assert_array_equal(panel, want)
+        assert calls[0] == ("set", S, 40, 5)
+        ready = [c[1] for c in calls[1:]]
+        assert ready == sorted(ready) and ready[-1] == S and len(ready) <= pieces
