@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <sys/stat.h>
+
 #include "textio.h"
 
 namespace ibdhost {
@@ -178,15 +180,17 @@ int read_positions(const std::string &fn, const char *chr, std::unordered_set<ui
     return 0;
 }
 
-int pack_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
-                const PileupStore &pu, const PackOptions &opt, PackedPanel *out) {
+int parse_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
+                 PanelText *out) {
     LineReader hap, leg;
     if (!hap.open(hap_fn) || !leg.open(legend_fn)) {
         fprintf(stderr, "[::] ERROR parsing hap/legend/indv data; make sure inputs are valid.\n");
         return 1;
     }
     out->names = names;
-    init_panel(out, (int32_t)names.size());
+    out->N = (int32_t)names.size();
+    const int64_t words = (2 * (int64_t)out->N + 31) / 32;
+    out->Wh = (words + 3) / 4 * 4;  // 16-byte rows for 128-bit loads on the device
     const size_t H = 2 * names.size();
     const char *hl, *ll;
     size_t hn, ln;
@@ -195,7 +199,14 @@ int pack_impute(const std::string &hap_fn, const std::string &legend_fn, const s
     char id[129], ref[129], alt[129];
     while (hap.next(&hl, &hn) && leg.next(&ll, &ln)) {
         const size_t s = (size_t)out->S;
-        push_site(out);
+        out->pos.push_back(0);
+        out->state.push_back(0);
+        out->id_off.push_back(0);
+        out->id_len.push_back(0);
+        out->ref.push_back('.');
+        out->alt.push_back('.');
+        out->bits.resize(out->bits.size() + (size_t)out->Wh, 0u);
+        out->S++;
         if (hn < 2 * H - 1) {
             fprintf(stderr, "[::] ERROR: .hap line %zu has %zu characters, %zu haplotypes need %zu.\n", s + 1, hn, H, 2 * H - 1);
             return 1;
@@ -223,19 +234,162 @@ int pack_impute(const std::string &hap_fn, const std::string &legend_fn, const s
         unsigned long pos;
         if (sscanf(lz.c_str(), "%128s %lu %128s %128s", id, &pos, ref, alt) != 4) continue;  // src/ibdgem.c:589
         out->pos[s] = pos;
-        if (!is_snp(ref, alt)) continue;
+        out->state[s] = is_snp(ref, alt) ? 2 : 1;
+        out->id_off[s] = out->text.size();
+        out->id_len[s] = (uint32_t)strlen(id);
+        out->text.append(id, strlen(id) + 1);  // with its NUL
+        out->ref[s] = ref[0];
+        out->alt[s] = alt[0];
+    }
+    return 0;
+}
+
+int join_pileup(PanelText *pt, const PileupStore &pu, const PackOptions &opt, PackedPanel *out) {
+    const size_t S = (size_t)pt->S;
+    out->S = pt->S;
+    out->N = pt->N;
+    out->Wh = pt->Wh;
+    out->names = pt->names;
+    out->pos = pt->pos;
+    out->bits = std::move(pt->bits);
+    out->n_ref.assign(S, 0);
+    out->n_alt.assign(S, 0);
+    out->host_keep.assign(S, 0);
+    out->dp.assign(S, 0);
+    out->chr_id.assign(S, 0);
+    out->id_off.assign(S, 0);
+    out->id_len.assign(S, 0);
+    out->ref.assign(S, '.');
+    out->alt.assign(S, '.');
+    for (size_t s = 0; s < S; s++) {
+        if (pt->state[s] != 2) continue;  // is_snp, src/ibdgem.c:592
+        const uint64_t pos = pt->pos[s];
         const int64_t pul = pu.fetch(pos);
         if (pul < 0) continue;
         if (opt.positions && !opt.positions->count(pos)) continue;
-        fill_kept(out, s, pu, pul, id, ref[0], alt[0]);
+        fill_kept(out, s, pu, pul, pt->text.c_str() + pt->id_off[s], pt->ref[s], pt->alt[s]);
     }
     if (opt.af) {
-        out->af_user.assign((size_t)out->S, NAN);
-        for (int64_t s = 0; s < out->S; s++)
-            if (out->host_keep[(size_t)s])
-                if (const double *f = opt.af->fetch(out->pos[(size_t)s])) out->af_user[(size_t)s] = *f;
+        out->af_user.assign(S, NAN);
+        for (size_t s = 0; s < S; s++)
+            if (out->host_keep[s])
+                if (const double *f = opt.af->fetch(out->pos[s])) out->af_user[s] = *f;
     }
     return 0;
+}
+
+int pack_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
+                const PileupStore &pu, const PackOptions &opt, PackedPanel *out) {
+    PanelText pt;
+    if (parse_impute(hap_fn, legend_fn, names, &pt)) return 1;
+    return join_pileup(&pt, pu, opt, out);
+}
+
+// --- binary cache ------------------------------------------------------------------------------
+namespace {
+
+struct CacheHeader {
+    char magic[8];
+    uint64_t key[6];  // size and mtime (ns) of .hap, .legend, .indv
+    int64_t S;
+    int64_t Wh;
+    int32_t N;
+    uint32_t reserved;
+    uint64_t names_bytes, text_bytes;
+};
+const char kCacheMagic[8] = {'I', 'B', 'D', 'G', 'P', 'N', 'L', '1'};
+
+bool file_key(const std::string &fn, uint64_t *size, uint64_t *mtime_ns) {
+    struct stat st;
+    if (stat(fn.c_str(), &st) != 0) return false;
+    *size = (uint64_t)st.st_size;
+    *mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    return true;
+}
+bool make_key(const std::string &hap_fn, const std::string &legend_fn, const std::string &indv_fn, uint64_t key[6]) {
+    return file_key(hap_fn, &key[0], &key[1]) && file_key(legend_fn, &key[2], &key[3]) && file_key(indv_fn, &key[4], &key[5]);
+}
+template <class T>
+bool put(FILE *f, const std::vector<T> &v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
+template <class T>
+bool get(FILE *f, std::vector<T> *v, size_t n) {
+    v->resize(n);
+    return n == 0 || fread(v->data(), sizeof(T), n, f) == n;
+}
+
+}  // namespace
+
+int save_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
+                     const std::string &indv_fn, const PanelText &pt) {
+    CacheHeader h{};
+    memcpy(h.magic, kCacheMagic, 8);
+    if (!make_key(hap_fn, legend_fn, indv_fn, h.key)) return 1;
+    std::string names;
+    for (const auto &n : pt.names) names.append(n.c_str(), n.size() + 1);
+    h.S = pt.S; h.Wh = pt.Wh; h.N = pt.N;
+    h.names_bytes = names.size();
+    h.text_bytes = pt.text.size();
+    const std::string tmp = cache_fn + ".tmp";  // a reader never sees a half-written cache
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return 1;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && (names.empty() || fwrite(names.data(), 1, names.size(), f) == names.size()) &&
+              put(f, pt.pos) && put(f, pt.state) && put(f, pt.id_off) && put(f, pt.id_len) && put(f, pt.ref) && put(f, pt.alt) &&
+              (pt.text.empty() || fwrite(pt.text.data(), 1, pt.text.size(), f) == pt.text.size()) && put(f, pt.bits);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), cache_fn.c_str()) != 0) {
+        remove(tmp.c_str());
+        return 1;
+    }
+    return 0;
+}
+
+bool load_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
+                      const std::string &indv_fn, PanelText *pt) {
+    FILE *f = fopen(cache_fn.c_str(), "rb");
+    if (!f) return false;
+    CacheHeader h;
+    uint64_t key[6];
+    bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, kCacheMagic, 8) == 0 &&
+              make_key(hap_fn, legend_fn, indv_fn, key) && memcmp(key, h.key, sizeof key) == 0 && h.S >= 0 && h.N > 0 &&
+              h.Wh * 32 >= 2 * (int64_t)h.N;
+    if (ok) {
+        const size_t S = (size_t)h.S;
+        std::vector<char> names, text;
+        ok = get(f, &names, (size_t)h.names_bytes) && get(f, &pt->pos, S) && get(f, &pt->state, S) && get(f, &pt->id_off, S) &&
+             get(f, &pt->id_len, S) && get(f, &pt->ref, S) && get(f, &pt->alt, S) && get(f, &text, (size_t)h.text_bytes) &&
+             get(f, &pt->bits, S * (size_t)h.Wh) && fgetc(f) == EOF;
+        if (ok) {
+            pt->S = h.S; pt->N = h.N; pt->Wh = h.Wh;
+            pt->text.assign(text.data(), text.size());
+            pt->names.clear();
+            for (size_t i = 0; i < names.size();) {
+                const size_t n = strnlen(names.data() + i, names.size() - i);
+                pt->names.emplace_back(names.data() + i, n);
+                i += n + 1;
+            }
+            ok = (int64_t)pt->names.size() == (int64_t)h.N;
+            for (size_t s = 0; ok && s < S; s++)  // offsets must stay inside the text blob
+                ok = pt->state[s] == 0 || (pt->id_off[s] + pt->id_len[s] < pt->text.size() && pt->text[pt->id_off[s] + pt->id_len[s]] == 0);
+        }
+    }
+    fclose(f);
+    if (!ok) *pt = PanelText();
+    return ok;
+}
+
+int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, const std::string &indv_fn,
+                       const std::string &cache_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out,
+                       bool *hit) {
+    PanelText pt;
+    const bool cached = load_panel_cache(cache_fn, hap_fn, legend_fn, indv_fn, &pt);
+    if (hit) *hit = cached;
+    if (!cached) {
+        std::vector<std::string> names;
+        if (read_indv(indv_fn, &names) || parse_impute(hap_fn, legend_fn, names, &pt)) return 1;
+        if (save_panel_cache(cache_fn, hap_fn, legend_fn, indv_fn, pt))
+            fprintf(stderr, "[::] WARNING: could not write the panel cache %s.\n", cache_fn.c_str());
+    }
+    return join_pileup(&pt, pu, opt, out);
 }
 
 int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out) {

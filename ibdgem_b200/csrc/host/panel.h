@@ -59,6 +59,37 @@ struct PackOptions {
 };
 int pack_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
                 const PileupStore &pu, const PackOptions &opt, PackedPanel *out);
+
+// The pileup-independent half of an IMPUTE panel — what the .hap / .legend / .indv text says — and
+// its binary cache (one panel is scored against many pileups; re-parsing 10 GB of
+// text per run is the reference's real wall-clock cost, src/ibdgem.c:573-574).
+struct PanelText {
+    int64_t S = 0;
+    int32_t N = 0;
+    int64_t Wh = 0;
+    std::vector<std::string> names;
+    std::vector<uint64_t> pos;    // 0 where the legend line did not parse (src/ibdgem.c:589)
+    std::vector<uint8_t> state;   // 0 = legend line unparsable, 1 = parsed but not a SNP, 2 = SNP
+    std::vector<uint64_t> id_off; // rsID of every parsed line, NUL-terminated, in `text`
+    std::vector<uint32_t> id_len;
+    std::vector<char> ref, alt;   // first character of REF / ALT
+    std::string text;
+    std::vector<uint32_t> bits;   // [S][Wh]
+};
+int parse_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
+                 PanelText *out);
+// Joins the panel text with a pileup and the option tables; takes the bits out of `pt`.
+int join_pileup(PanelText *pt, const PileupStore &pu, const PackOptions &opt, PackedPanel *out);
+// Cache file = the PanelText arrays behind a header that names size and mtime of the three input
+// files; a cache whose header does not match them is ignored and rewritten.
+int save_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
+                     const std::string &indv_fn, const PanelText &pt);
+bool load_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
+                      const std::string &indv_fn, PanelText *pt);
+// pack_impute through the cache: *hit tells whether the text files were parsed (false) or not (true).
+int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, const std::string &indv_fn,
+                       const std::string &cache_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out,
+                       bool *hit);
 int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out);
 
 }  // namespace ibdhost

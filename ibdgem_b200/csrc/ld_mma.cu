@@ -16,8 +16,12 @@
 // mass is below 1e-7 relative.  LIBD0 (the chain over background individuals) and LIBD2 are
 // target-independent per individual: Q_w[b] = C0 + R[r0] + R[r1] + kappa M[r0, r1].
 //
-// Kernels in this file: ld_compact, ld_c0, ld_transpose (+ marginals) (cached per prepared
-// panel); ld_expand_bg, ld_expand_tgt, ld_windows, ld_mma, ld_ibd0 (per call).
+// d1 is linear in the counts (d1 = n_ref * alpha + n_alt * beta), so R and the M of an individual's own
+// two haplotypes are integer dot products of 0/1 bytes with count bytes: the expansion kernels take them
+// with dp4a from the bytes they write.
+//
+// Kernels in this file: ld_compact, ld_c0, ld_transpose (cached per prepared panel); ld_stage,
+// ld_expand_bg, ld_expand_tgt, ld_windows, ld_mma, ld_ibd0 (per call).
 #include <cuda.h>
 #include <math.h>
 #include <stdio.h>
@@ -25,7 +29,6 @@
 #include <string.h>
 
 #include <algorithm>
-#include <map>
 #include <vector>
 
 #include "engine.h"
@@ -36,7 +39,7 @@ namespace ibdgem {
 // cached, target-independent operands
 struct LdCache {
     bool valid = false;       // per-site operands (slots, depths, C0) are current
-    int tw_upto = 0;          // windows [0, tw_upto) have their transposed bits and marginals
+    int tw_upto = 0;          // windows [0, tw_upto) have their transposed bits
     int32_t nW = 0;
     int64_t K = 0;
     int W = 0, Wpad = 0, WP32 = 0, KB = 0;
