@@ -45,6 +45,21 @@ void *ibdhost_pack(int mode, const char *a, const char *b, const char *c, const 
     }
     return h;
 }
+// IMPUTE panel through the binary cache; *hit = 1 when the text files were not parsed.
+void *ibdhost_pack_cached(const char *hap, const char *legend, const char *indv, const char *cache, const char *pileup,
+                          const char *chr, int *hit) {
+    Handle *h = new Handle();
+    PackOptions po;
+    bool was_hit = false;
+    const bool ok = load_pileup(pileup, chr, &h->pu) == 0 &&
+                    pack_impute_cached(hap, legend, indv, cache, h->pu, po, &h->panel, &was_hit) == 0;
+    if (hit) *hit = was_hit ? 1 : 0;
+    if (!ok) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
 void ibdhost_free(void *p) { delete static_cast<Handle *>(p); }
 int64_t ibdhost_n_sites(void *p) { return static_cast<Handle *>(p)->panel.S; }
 int32_t ibdhost_n_indiv(void *p) { return static_cast<Handle *>(p)->panel.N; }

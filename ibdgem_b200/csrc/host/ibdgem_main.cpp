@@ -2,7 +2,8 @@
 // exit codes and output tables as the reference's main()/compare_impute()/compare_vcf()
 // (src/ibdgem.c:41-66, 779-1183); the arithmetic is done by libibdgem_b200.so through the C ABI
 // (include/ibdgem_b200.h) and there is no CPU fallback.  Additive options: --gpus N (shard the
-// targets over N devices), --batch N (targets per engine call), --no-tab (skip *.tab.txt).
+// targets over N devices), --batch N (targets per engine call), --no-tab (skip *.tab.txt),
+// --panel-cache FILE (binary cache of the parsed IMPUTE panel).
 #include <getopt.h>
 #include <limits.h>
 #include <unistd.h>
@@ -14,6 +15,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -32,6 +34,7 @@ struct Options {
     const char *sq_id = "UNKWN";
     int ld = 0, in_impute = 0, in_vcf = 0, opt_s1 = 0, opt_s2 = 0, opt_b = 0, opt_a = 0, opt_p = 0, opt_v = 0, opt_d = 0;
     std::string vcf_fn, hap_fn, legend_fn, indv_fn, pu_fn, sample_fn, ref_fn, af_fn, pos_fn, sample_str, out_dir;
+    std::string cache_fn;  // --panel-cache
     const char *uchr = nullptr;
     int gpus = 1, batch = 0, no_tab = 0;
 };
@@ -129,6 +132,68 @@ struct Shared {
     int rc = 0;
 };
 
+constexpr int WRITER_THREADS = 8;  // per device shard
+
+// Per-site text of the tab.txt rows for runs without -D: the row prefix
+// "CHR\trsID\tPOS\tREF\tALT\tAF\tDP\tSQ_NREF\tSQ_NALT\t" and the seven likelihood strings a row can
+// show (LIBD0; LIBD1 and LIBD2 for g = 0, 1, 2), formatted with the C library exactly as a row-by-row
+// writer would (src/ibdgem.c:731-733).  A row is then two allele digits between copies of these.
+struct SiteText {
+    static constexpr size_t NONE = ~(size_t)0;
+    std::vector<size_t> off;   // offset of the site's record in `blob`, NONE if the site prints no row
+    std::vector<char> blob;    // record: u16 prefix length, prefix bytes, 7 x (u8 length, 15 bytes)
+    bool has(size_t s) const { return !off.empty() && off[s] != NONE; }
+    void build(const PackedPanel &P, const PileupStore &pu, const std::vector<uint8_t> &status, const std::vector<double> &f,
+               const std::vector<double> &lik7) {
+        const size_t S = (size_t)P.S;
+        off.assign(S, NONE);
+        std::vector<char> tmp(1 << 12);
+        for (size_t s = 0; s < S; s++) {
+            if (!status[s]) continue;
+            const std::string &chr = pu.chr_names[P.chr_id[s]];
+            if (tmp.size() < chr.size() + P.id_len[s] + 256) tmp.resize(chr.size() + P.id_len[s] + 256);
+            char *q = tmp.data();
+            memcpy(q, chr.data(), chr.size()); q += chr.size();
+            *q++ = '\t';
+            memcpy(q, P.text.data() + P.id_off[s], P.id_len[s]); q += P.id_len[s];
+            q += sprintf(q, "\t%lu\t%c\t%c\t%lf\t%u\t%u\t%u\t", (unsigned long)P.pos[s], P.ref[s], P.alt[s], f[s], P.dp[s],
+                         (unsigned)P.n_ref[s], (unsigned)P.n_alt[s]);
+            const size_t plen = (size_t)(q - tmp.data());
+            if (plen > 0xFFFF) continue;  // (a 64 KB rsID: leave the row to the generic writer)
+            off[s] = blob.size();
+            const uint16_t plen16 = (uint16_t)plen;
+            blob.insert(blob.end(), reinterpret_cast<const char *>(&plen16), reinterpret_cast<const char *>(&plen16) + 2);
+            blob.insert(blob.end(), tmp.data(), tmp.data() + plen);
+            for (int j = 0; j < 7; j++) {
+                char e[40];
+                const int n = put_e(e, lik7[s * 7 + (size_t)j]);
+                char slot[16] = {0};
+                slot[0] = (char)n;  // "%e" of a double is at most 14 characters
+                memcpy(slot + 1, e, (size_t)n);
+                blob.insert(blob.end(), slot, slot + 16);
+            }
+        }
+    }
+    // writes the whole row of site s for a target with alleles a0, a1 (g = a0 + a1); returns the end
+    char *put_row(char *q, size_t s, unsigned a0, unsigned a1, unsigned g) const {
+        const char *r = blob.data() + off[s];
+        uint16_t plen;
+        memcpy(&plen, r, 2);
+        memcpy(q, r + 2, plen); q += plen;
+        *q++ = (char)('0' + a0); *q++ = '\t';
+        *q++ = (char)('0' + a1); *q++ = '\t';
+        const char *slots = r + 2 + plen;
+        const int pick[3] = {0, 1 + (int)g, 4 + (int)g};
+        for (int j = 0; j < 3; j++) {
+            const char *sl = slots + 16 * pick[j];
+            memcpy(q, sl + 1, 15);  // fixed-size copy, advance by the real length
+            q += (unsigned char)sl[0];
+            *q++ = j == 2 ? '\n' : '\t';
+        }
+        return q;
+    }
+};
+
 int fail_engine() {
     fprintf(stderr, "%s\n", ibdgem_last_error());
     return 1;
@@ -166,7 +231,13 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
     std::vector<int32_t> bg(sh->background.size());
     for (size_t i = 0; i < bg.size(); i++) bg[i] = sh->background[i].ordinal;
 
-    std::vector<char> line(1 << 16);
+    // Everything a tab.txt row says besides the target's two alleles depends on the site alone (and, for
+    // the likelihoods, on the genotype class g): format it once per site, not once per target and site
+    // (1,000 targets x 1 M rows is 100 GB of text).  -D makes counts and likelihoods
+    // target-dependent; those runs format row by row.
+    SiteText site_text;
+    if (!o.no_tab && !culled) site_text.build(P, *sh->pu, st_shared, f, lik7);
+
     for (size_t b0 = t0; b0 < t1; b0 += batch) {
         const size_t T = std::min(batch, t1 - b0);
         std::vector<int32_t> tg(T);
@@ -194,9 +265,12 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
                             : ibdgem_engine_score_nonld(e, (int32_t)T, tg.data(), tc, &sc);
         if (rc) return fail_engine();
 
-        for (size_t k = 0; k < T; k++) {
+        for (size_t k = 0; k < T; k++)
+            fprintf(stderr, "Running %s-vs-%s comparison...\n", o.sq_id, sh->targets[b0 + k].name.c_str());
+
+        // one target = two files: independent, so the batch is written by a few threads
+        auto write_target = [&](size_t k, std::vector<char> &line) -> int {
             const Sample &smp = sh->targets[b0 + k];
-            fprintf(stderr, "Running %s-vs-%s comparison...\n", o.sq_id, smp.name.c_str());
             const std::string tab_fn = o.out_dir + "/" + o.sq_id + "." + smp.name + ".tab.txt";
             const std::string sum_fn = o.out_dir + "/" + o.sq_id + "." + smp.name + ".summary.txt";
             FILE *tab = o.no_tab ? nullptr : fopen(tab_fn.c_str(), "w");
@@ -204,6 +278,8 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
             if ((!o.no_tab && !tab) || !sum) {
                 fprintf(stderr, "[::] ERROR in compare_%s(): Cannot open '%s' and/or '%s' for writing.\n", o.in_vcf ? "vcf" : "impute",
                         tab_fn.c_str(), sum_fn.c_str());
+                if (tab) fclose(tab);
+                if (sum) fclose(sum);
                 return 1;
             }
             if (tab) {
@@ -214,34 +290,45 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
                 fprintf(tab, "# MEAN DEPTH = %lf\n# CULL DEPTH RATIO = %lf\n", sh->dist->mean, sh->dist->cull_p);
                 fprintf(tab, "# CHR\trsID\tPOS\tREF\tALT\tAF\tDP\tSQ_NREF\tSQ_NALT\tGT_A0\tGT_A1\tLIBD0\tLIBD1\tLIBD2\n");
                 const size_t h0 = 2 * (size_t)smp.ordinal;
+                size_t fill = 0;  // rows are gathered in `line` and written in large pieces
                 for (size_t s = 0; s < S; s++) {
                     const uint8_t st = per_target ? sst[k * S + s] : st_shared[s];
                     if (!st) continue;
                     const uint32_t *row = P.bits.data() + s * (size_t)P.Wh;
                     const unsigned a0 = (row[h0 >> 5] >> (h0 & 31)) & 1u, a1 = (row[(h0 + 1) >> 5] >> ((h0 + 1) & 31)) & 1u;
                     const unsigned g = a0 + a1;
-                    double l0, l1, l2;
-                    unsigned nr = P.n_ref[s], na = P.n_alt[s];
-                    if (culled) {
-                        l0 = slik[(k * S + s) * 3]; l1 = slik[(k * S + s) * 3 + 1]; l2 = slik[(k * S + s) * 3 + 2];
-                        nr = tc[(k * S + s) * 2];
-                        na = tc[(k * S + s) * 2 + 1];
-                    } else {
-                        l0 = lik7[s * 7]; l1 = lik7[s * 7 + 1 + g]; l2 = lik7[s * 7 + 4 + g];
-                    }
                     const std::string &chr = sh->pu->chr_names[P.chr_id[s]];
-                    if (line.size() < chr.size() + P.id_len[s] + 512) line.resize(chr.size() + P.id_len[s] + 512);
-                    char *q = line.data();
-                    memcpy(q, chr.data(), chr.size()); q += chr.size();
-                    *q++ = '\t';
-                    memcpy(q, P.text.data() + P.id_off[s], P.id_len[s]); q += P.id_len[s];
-                    q += sprintf(q, "\t%lu\t%c\t%c\t%lf\t%u\t%u\t%u\t%u\t%u\t", (unsigned long)P.pos[s], P.ref[s], P.alt[s], f[s],
-                                 P.dp[s], nr, na, a0, a1);
-                    q += put_e(q, l0); *q++ = '\t';
-                    q += put_e(q, l1); *q++ = '\t';
-                    q += put_e(q, l2); *q++ = '\n';
-                    fwrite(line.data(), 1, (size_t)(q - line.data()), tab);
+                    const size_t need = chr.size() + P.id_len[s] + 512;
+                    if (line.size() < fill + need) {
+                        if (fill) fwrite(line.data(), 1, fill, tab);
+                        fill = 0;
+                        if (line.size() < need) line.resize(need);
+                    }
+                    char *q = line.data() + fill;
+                    if (site_text.has(s)) {
+                        q = site_text.put_row(q, s, a0, a1, g);
+                    } else {
+                        double l0, l1, l2;
+                        unsigned nr = P.n_ref[s], na = P.n_alt[s];
+                        if (culled) {
+                            l0 = slik[(k * S + s) * 3]; l1 = slik[(k * S + s) * 3 + 1]; l2 = slik[(k * S + s) * 3 + 2];
+                            nr = tc[(k * S + s) * 2];
+                            na = tc[(k * S + s) * 2 + 1];
+                        } else {
+                            l0 = lik7[s * 7]; l1 = lik7[s * 7 + 1 + g]; l2 = lik7[s * 7 + 4 + g];
+                        }
+                        memcpy(q, chr.data(), chr.size()); q += chr.size();
+                        *q++ = '\t';
+                        memcpy(q, P.text.data() + P.id_off[s], P.id_len[s]); q += P.id_len[s];
+                        q += sprintf(q, "\t%lu\t%c\t%c\t%lf\t%u\t%u\t%u\t%u\t%u\t", (unsigned long)P.pos[s], P.ref[s], P.alt[s], f[s],
+                                     P.dp[s], nr, na, a0, a1);
+                        q += put_e(q, l0); *q++ = '\t';
+                        q += put_e(q, l1); *q++ = '\t';
+                        q += put_e(q, l2); *q++ = '\n';
+                    }
+                    fill = (size_t)(q - line.data());
                 }
+                if (fill) fwrite(line.data(), 1, fill, tab);
                 fprintf(tab, "# FINAL COVERAGE DISTRIBUTION:\n# COVERAGE N_SITES\n");
                 for (int c = 0; c < C; c++) fprintf(tab, "# %d %lu\n", c, (unsigned long)fdist[k * (size_t)C + (size_t)c]);
                 fprintf(tab, "# FINAL MEAN DEPTH = %lf\n", (double)totcov[k] / processed[k]);
@@ -259,7 +346,24 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
                 fprintf(sum, "%d\t%lu\t%lu\t%s\t%s\t%s\t%d\n", w + 1, (unsigned long)ws[i], (unsigned long)we[i], e0, e1, e2, wn[i]);
             }
             fclose(sum);
+            return 0;
+        };
+        const size_t n_writers = std::max<size_t>(1, std::min<size_t>({T, (size_t)WRITER_THREADS, (size_t)std::thread::hardware_concurrency()}));
+        std::atomic<size_t> next_k{0};
+        std::atomic<int> write_rc{0};
+        auto writer = [&] {
+            std::vector<char> line(1 << 20);
+            for (size_t k; (k = next_k.fetch_add(1)) < T;)
+                if (write_target(k, line)) write_rc = 1;
+        };
+        if (n_writers == 1) {
+            writer();
+        } else {
+            std::vector<std::thread> pool;
+            for (size_t i = 0; i < n_writers; i++) pool.emplace_back(writer);
+            for (auto &t : pool) t.join();
         }
+        if (write_rc) return 1;
     }
     ibdgem_engine_destroy(e);
     return 0;
@@ -296,6 +400,7 @@ int main(int argc, char *argv[]) {
                                        {"help", no_argument, 0, 'h'},
                                        {"gpus", required_argument, 0, 1001},     // additive
                                        {"batch", required_argument, 0, 1002},    // additive
+                                       {"panel-cache", required_argument, 0, 1003},  // additive
                                        {"no-tab", no_argument, &no_tab_flag, 1},  // additive
                                        {0, 0, 0, 0}};
     if (argc == 1) print_help(0);
@@ -329,6 +434,7 @@ int main(int argc, char *argv[]) {
             case 'h': print_help(0); break;
             case 1001: o.gpus = atoi(optarg); break;
             case 1002: o.batch = atoi(optarg); break;
+            case 1003: o.cache_fn = optarg; break;
             case ':':
                 fprintf(stderr, "Option -%c missing required argument.\n", optopt);
                 exit(0);
@@ -420,8 +526,16 @@ int main(int argc, char *argv[]) {
                 exit(1);
             }
         }
-        if (read_indv(o.indv_fn, &names)) exit(1);
-        if (pack_impute(o.hap_fn, o.legend_fn, names, pu, po, &panel)) exit(1);
+        if (!o.cache_fn.empty()) {
+            // binary cache of the parsed panel: later runs against the same panel (other pileups, other
+            // options) skip the text files
+            bool hit = false;
+            if (pack_impute_cached(o.hap_fn, o.legend_fn, o.indv_fn, o.cache_fn, pu, po, &panel, &hit)) exit(1);
+            fprintf(stderr, "[::] panel cache %s: %s\n", o.cache_fn.c_str(), hit ? "loaded" : "written");
+        } else {
+            if (read_indv(o.indv_fn, &names)) exit(1);
+            if (pack_impute(o.hap_fn, o.legend_fn, names, pu, po, &panel)) exit(1);
+        }
     }
     if (o.opt_s1) {
         if (read_sample_file(o.sample_fn, panel.names, false, &sh.targets)) exit(1);

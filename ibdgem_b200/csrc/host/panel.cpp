@@ -6,6 +6,9 @@
 #include <cstring>
 
 #include <sys/stat.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "textio.h"
 
@@ -180,6 +183,29 @@ int read_positions(const std::string &fn, const char *chr, std::unordered_set<ui
     return 0;
 }
 
+// 16 alleles per step: 32 text bytes "a b c ... " -> compare masks -> the even bits, packed.  Same
+// strictness as the scalar paths (every even byte '0' or '1', every odd byte a space); stops at the
+// first group that does not fit and returns the number of haplotypes done (a multiple of 16).
+#if defined(__x86_64__)
+__attribute__((target("avx2,bmi2"))) static size_t pack_alleles_avx2(const char *hl, size_t hn, size_t H, uint32_t *row) {
+    const __m256i c1 = _mm256_set1_epi8('1'), c0 = _mm256_set1_epi8('0'), sp = _mm256_set1_epi8(' ');
+    size_t h = 0;
+    for (; h + 16 <= H && 2 * h + 32 <= hn; h += 16) {
+        const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(hl + 2 * h));
+        const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, c1));
+        const uint32_t m0 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, c0));
+        const uint32_t ms = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, sp));
+        if (((m0 | m1) & 0x55555555u) != 0x55555555u || (ms & 0xAAAAAAAAu) != 0xAAAAAAAAu) break;
+        row[h >> 5] |= _pext_u32(m1, 0x55555555u) << (h & 31);
+    }
+    return h;
+}
+static const bool kHaveAvx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+#else
+static size_t pack_alleles_avx2(const char *, size_t, size_t, uint32_t *) { return 0; }
+static const bool kHaveAvx2 = false;
+#endif
+
 int parse_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
                  PanelText *out) {
     LineReader hap, leg;
@@ -212,8 +238,8 @@ int parse_impute(const std::string &hap_fn, const std::string &legend_fn, const 
             return 1;
         }
         uint32_t *row = out->bits.data() + s * (size_t)out->Wh;
-        size_t h = 0;
-        // fast path: eight text bytes "a b c d " carry four alleles; check the pattern, pick bit 0 of
+        size_t h = kHaveAvx2 ? pack_alleles_avx2(hl, hn, H, row) : 0;
+        // next: eight text bytes "a b c d " carry four alleles; check the pattern, pick bit 0 of
         // the four digits and gather them with one multiply
         for (; h + 4 <= H && 2 * h + 8 <= hn; h += 4) {
             uint64_t x;

@@ -35,6 +35,8 @@ def lib():
             f = getattr(_lib, "ibdhost_" + name)
             f.restype = rt
             f.argtypes = [C.c_void_p]
+        _lib.ibdhost_pack_cached.restype = C.c_void_p
+        _lib.ibdhost_pack_cached.argtypes = [C.c_char_p] * 6 + [C.POINTER(C.c_int)]
         _lib.ibdhost_name.restype = C.c_char_p
         _lib.ibdhost_name.argtypes = [C.c_void_p, C.c_int32]
         _lib.ibdhost_free.argtypes = [C.c_void_p]
@@ -45,12 +47,24 @@ def _b(s):
     return None if s is None else s.encode()
 
 
+def pack_cached(hap, legend, indv, cache, pileup, chrom=None):
+    """IMPUTE panel through the binary cache: (arrays as pack() returns them, cache_hit)."""
+    L = lib()
+    hit = C.c_int(-1)
+    h = L.ibdhost_pack_cached(_b(hap), _b(legend), _b(indv), _b(cache), _b(pileup), _b(chrom), C.byref(hit))
+    return (_arrays(L, h) if h else None), hit.value
+
+
 def pack(mode, a, b, c, pileup, chrom=None, positions=None, af=None, min_qual=0.0):
     """Returns a dict of numpy copies of the packed arrays, or None if the packer reported an error."""
     L = lib()
     h = L.ibdhost_pack(mode, _b(a), _b(b), _b(c), _b(pileup), _b(chrom), _b(positions), _b(af), min_qual)
     if not h:
         return None
+    return _arrays(L, h)
+
+
+def _arrays(L, h):
     try:
         S, N, Wh = L.ibdhost_n_sites(h), L.ibdhost_n_indiv(h), L.ibdhost_words(h)
 

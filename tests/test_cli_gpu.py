@@ -135,3 +135,21 @@ def test_targets_sharded_over_two_devices(golden_dir, tmp_path):
             assert got.split("\n", 1)[1] == want.split("\n", 1)[1]
         else:
             _same_summary(got, want, exact=False)
+
+
+def test_panel_cache_runs_reproduce_the_golden_files(fixture_dir, tmp_path):
+    """--panel-cache: the run that writes the cache and the run that loads it (another pileup) both
+    reproduce the shipped golden files byte for byte."""
+    inp, gold = os.path.join(fixture_dir, "input"), os.path.join(fixture_dir, "output")
+    cache = str(tmp_path / "panel.cache")
+    for k, what in ((1, "written"), (2, "loaded")):
+        out = tmp_path / f"out{k}"
+        out.mkdir()
+        r = _run("ibdgem", ["-H", os.path.join(inp, "test.hap"), "-L", os.path.join(inp, "test.legend"), "-I",
+                            os.path.join(inp, "test.indv"), "-P", os.path.join(inp, f"test{k}.pileup"), "-N", f"sample{k}",
+                            "-O", str(out), "--panel-cache", cache])
+        assert f"panel cache {cache}: {what}" in r.stderr
+        for t in (1, 2, 3):
+            for kind in ("tab", "summary"):
+                name = f"sample{k}.sample{t}.{kind}.txt"
+                assert _body(out / name) == _body(os.path.join(gold, name))

@@ -126,3 +126,48 @@ def test_cli_fails_loudly_without_a_gpu(fixture_dir, tmp_path):
               "-P", os.path.join(inp, "test1.pileup"), "-N", "sample1", "-O", str(tmp_path)])
     assert r.returncode == 1 and "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
     assert not list(tmp_path.iterdir())  # nothing is written by a host-side stand-in
+
+
+def test_panel_cache_round_trip_and_invalidation(fixture_dir, tmp_path):
+    """--panel-cache: the first run parses the text and writes the cache, later runs (here against
+    another pileup) load it and pack the same arrays as the uncached packer; a changed input file or
+    a damaged cache is noticed and the cache rebuilt."""
+    import shutil
+    inp = os.path.join(fixture_dir, "input")
+    work = tmp_path / "panel"
+    work.mkdir()
+    for f in ("test.hap", "test.legend", "test.indv"):
+        shutil.copy(os.path.join(inp, f), work / f)
+    hap, leg, indv = (str(work / f) for f in ("test.hap", "test.legend", "test.indv"))
+    cache = str(tmp_path / "panel.cache")
+
+    def same(a, b):
+        assert a["names"] == b["names"] and (a["S"], a["N"], a["Wh"]) == (b["S"], b["N"], b["Wh"])
+        for key in ("pos", "n_ref", "n_alt", "keep", "dp", "bits"):
+            np.testing.assert_array_equal(a[key], b[key])
+
+    pu1, pu2 = os.path.join(inp, "test1.pileup"), os.path.join(inp, "test2.pileup")
+    got, hit = hostlib.pack_cached(hap, leg, indv, cache, pu1)
+    assert hit == 0 and os.path.exists(cache)
+    same(got, hostlib.pack(0, hap, leg, indv, pu1))
+    got, hit = hostlib.pack_cached(hap, leg, indv, cache, pu2)
+    assert hit == 1
+    same(got, hostlib.pack(0, hap, leg, indv, pu2))
+    _check_against_refio(got, refio.pack_impute(hap, leg, indv, pu2))
+    # the .hap changes (one allele flipped, same size, new mtime): the cache no longer matches
+    text = open(hap).read()
+    flipped = ("1" if text[0] == "0" else "0") + text[1:]
+    open(hap, "w").write(flipped)
+    st = os.stat(hap)
+    os.utime(hap, ns=(st.st_atime_ns, st.st_mtime_ns + 1_000_000_000))
+    got, hit = hostlib.pack_cached(hap, leg, indv, cache, pu1)
+    assert hit == 0
+    same(got, hostlib.pack(0, hap, leg, indv, pu1))
+    # a truncated cache is not trusted
+    data = open(cache, "rb").read()
+    open(cache, "wb").write(data[: len(data) // 2])
+    got, hit = hostlib.pack_cached(hap, leg, indv, cache, pu1)
+    assert hit == 0
+    same(got, hostlib.pack(0, hap, leg, indv, pu1))
+    got, hit = hostlib.pack_cached(hap, leg, indv, cache, pu1)
+    assert hit == 1
