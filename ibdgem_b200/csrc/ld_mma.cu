@@ -1378,16 +1378,24 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     std::vector<int> range_end;
     const bool in_flight = e->chunks_waited < (int)e->chunk_end.size() && e->chunk_end.size() > 1 &&
                            cudaEventQuery(e->chunk_ev[e->chunk_end.size() - 1]) == cudaErrorNotReady;
-    if (in_flight && c->tw_upto == 0) {
+    if (in_flight && c->tw_upto == 0) {  // (by_chunk below)
         int w = 0;
         for (size_t k = 0; k < e->chunk_end.size(); k++) {
             while (w < nW && e->h_wlast[(size_t)w] < e->chunk_end[k]) w++;
             range_end.push_back(k + 1 == e->chunk_end.size() ? nW : w);
         }
     } else {
+        // Panel resident: one range.  IBDGEM_LD_TAIL_DIV=d splits off the last 1/d of the windows so that the
+        // first range's columns of the score table travel to the host while the second is scored; measured
+        // at C3 it buys nothing (8.70 ms one range, 8.68 ms d = 8, 8.78 ms d = 5: a second round of launches
+        // costs what the hidden 0.4 ms copy saves), so it is off by default.
+        static int tail_div = -1;
+        if (tail_div < 0) { const char *st = getenv("IBDGEM_LD_TAIL_DIV"); tail_div = st ? atoi(st) : 0; }
+        if (e->h_wll_out && tail_div > 1 && nW >= 8 * tail_div) range_end.push_back(nW - nW / tail_div);
         range_end.push_back(nW);
     }
-    auto range_sites = [&](size_t k) { return range_end.size() == 1 ? e->S : e->chunk_end[k]; };
+    const bool by_chunk = in_flight && c->tw_upto == 0;
+    auto range_sites = [&](size_t k) { return by_chunk ? e->chunk_end[k] : e->S; };
     const int nrows = 2 * T;
     if (nU == 0) {  // every background member excluded: LIBD0 = LIBD1 = 0/0 (d_wll is NaN-filled)
         double *d_Rt;
