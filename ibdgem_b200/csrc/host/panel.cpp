@@ -5,7 +5,14 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <thread>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -206,6 +213,150 @@ static size_t pack_alleles_avx2(const char *, size_t, size_t, uint32_t *) { retu
 static const bool kHaveAvx2 = false;
 #endif
 
+// One .hap line -> one packed row.  Returns 0, or 1 with the reference-style message in *err.
+static int pack_hap_line(const char *hl, size_t hn, size_t H, size_t s, uint32_t *row, std::string *err) {
+    char msg[256];
+    if (hn < 2 * H - 1) {
+        snprintf(msg, sizeof msg, "[::] ERROR: .hap line %zu has %zu characters, %zu haplotypes need %zu.\n", s + 1, hn, H, 2 * H - 1);
+        *err = msg;
+        return 1;
+    }
+    size_t h = kHaveAvx2 ? pack_alleles_avx2(hl, hn, H, row) : 0;
+    // next: eight text bytes "a b c d " carry four alleles; check the pattern, pick bit 0 of
+    // the four digits and gather them with one multiply
+    for (; h + 4 <= H && 2 * h + 8 <= hn; h += 4) {
+        uint64_t x;
+        memcpy(&x, hl + 2 * h, 8);
+        if ((x & 0xFFFEFFFEFFFEFFFEull) != 0x2030203020302030ull) break;  // not "[01] [01] [01] [01] "
+        const uint64_t nib = (((x & 0x0001000100010001ull) * 0x0001000200040008ull) >> 48) & 0xFu;
+        row[h >> 5] |= (uint32_t)nib << (h & 31);
+    }
+    for (; h < H; h++) {
+        const char c = hl[2 * h];
+        if (c == '1') row[h >> 5] |= 1u << (h & 31);
+        else if (c != '0') {
+            snprintf(msg, sizeof msg, "[::] ERROR: .hap line %zu: allele '%c' of haplotype %zu is not 0 or 1.\n", s + 1, c, h);
+            *err = msg;
+            return 1;
+        }
+    }
+    return 0;
+}
+
+// One legend line -> the per-site text fields (src/ibdgem.c:589-592).
+static void push_legend_line(PanelText *out, const char *ll, size_t ln, std::string *lz) {
+    char id[129], ref[129], alt[129];
+    out->pos.push_back(0);
+    out->state.push_back(0);
+    out->id_off.push_back(0);
+    out->id_len.push_back(0);
+    out->ref.push_back('.');
+    out->alt.push_back('.');
+    lz->assign(ll, ln);
+    unsigned long pos;
+    if (sscanf(lz->c_str(), "%128s %lu %128s %128s", id, &pos, ref, alt) != 4) return;
+    out->pos.back() = pos;
+    out->state.back() = is_snp(ref, alt) ? 2 : 1;
+    out->id_off.back() = out->text.size();
+    out->id_len.back() = (uint32_t)strlen(id);
+    out->text.append(id, strlen(id) + 1);  // with its NUL
+    out->ref.back() = ref[0];
+    out->alt.back() = alt[0];
+}
+
+// Large plain .hap files: the file is mapped and its lines are packed by several threads (the rows are
+// independent; a line's index is the number of newlines before it).  Semantics are those of the
+// sequential loop below: lines pair up with legend lines in order, the shorter file ends the panel,
+// and the first bad line in file order is the one reported.
+static constexpr size_t MT_MIN_BYTES = (size_t)32 << 20;
+static constexpr unsigned MT_MAX_THREADS = 16;
+
+static int parse_hap_mapped(const std::string &hap_fn, size_t H, PanelText *out, size_t n_legend, bool *done) {
+    *done = false;
+    const int fd = open(hap_fn.c_str(), O_RDONLY);
+    if (fd < 0) return 0;  // the caller's sequential path reports it
+    struct stat st;
+    static size_t min_bytes = 0;
+    if (!min_bytes) {  // IBDGEM_PACK_MT_MIN_BYTES: tests push small fixtures through the threaded path
+        const char *sm = getenv("IBDGEM_PACK_MT_MIN_BYTES");
+        min_bytes = sm && atol(sm) > 0 ? (size_t)atol(sm) : MT_MIN_BYTES;
+    }
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < min_bytes || st.st_size == 0) {
+        close(fd);
+        return 0;
+    }
+    const size_t n = (size_t)st.st_size;
+    void *map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return 0;
+    madvise(map, n, MADV_SEQUENTIAL);
+    const char *data = static_cast<const char *>(map);
+    const unsigned nt = std::max(1u, std::min(MT_MAX_THREADS, std::thread::hardware_concurrency()));
+    std::vector<size_t> cut(nt + 1), newlines(nt, 0);
+    for (unsigned t = 0; t <= nt; t++) cut[t] = n / nt * t;
+    cut[nt] = n;
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                size_t c = 0;
+                for (const char *p = data + cut[t], *e = data + cut[t + 1]; p < e;) {
+                    const char *nl = static_cast<const char *>(memchr(p, '\n', (size_t)(e - p)));
+                    if (!nl) break;
+                    c++;
+                    p = nl + 1;
+                }
+                newlines[t] = c;
+            });
+        for (auto &x : th) x.join();
+    }
+    // first_line[t] = newlines before cut[t]: the index of the line that contains byte cut[t]
+    size_t n_lines = 0;
+    std::vector<size_t> first_line(nt);
+    for (unsigned t = 0; t < nt; t++) {
+        first_line[t] = n_lines;
+        n_lines += newlines[t];
+    }
+    if (n > 0 && data[n - 1] != '\n') n_lines++;  // last line without a newline
+    const size_t S = std::min(n_lines, n_legend);
+    out->S = (int64_t)S;
+    out->bits.assign(S * (size_t)out->Wh, 0u);
+    std::vector<std::string> errs(nt);
+    std::vector<size_t> err_line(nt, ~(size_t)0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t] {
+                size_t p = cut[t], idx = first_line[t];
+                if (t > 0 && data[p - 1] != '\n') {  // move to the first line that starts in this range
+                    const char *nl = static_cast<const char *>(memchr(data + p, '\n', cut[t + 1] - p));
+                    if (!nl) return;  // the range lies inside one line
+                    p = (size_t)(nl - data) + 1;
+                    idx++;
+                }
+                while (p < cut[t + 1] && idx < S) {
+                    const char *nl = static_cast<const char *>(memchr(data + p, '\n', n - p));
+                    const size_t hn = nl ? (size_t)(nl - (data + p)) + 1 : n - p;
+                    if (pack_hap_line(data + p, hn, H, idx, out->bits.data() + idx * (size_t)out->Wh, &errs[t])) {
+                        err_line[t] = idx;
+                        return;
+                    }
+                    p += hn;
+                    idx++;
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    munmap(map, n);
+    for (unsigned t = 0; t < nt; t++)  // ranges are in file order: the first recorded error is the first bad line
+        if (err_line[t] != ~(size_t)0) {
+            fputs(errs[t].c_str(), stderr);
+            return 1;
+        }
+    *done = true;
+    return 0;
+}
+
 int parse_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
                  PanelText *out) {
     LineReader hap, leg;
@@ -221,51 +372,42 @@ int parse_impute(const std::string &hap_fn, const std::string &legend_fn, const 
     const char *hl, *ll;
     size_t hn, ln;
     leg.next(&ll, &ln);  // header (src/ibdgem.c:554)
-    std::string lz;
-    char id[129], ref[129], alt[129];
-    while (hap.next(&hl, &hn) && leg.next(&ll, &ln)) {
-        const size_t s = (size_t)out->S;
-        out->pos.push_back(0);
-        out->state.push_back(0);
-        out->id_off.push_back(0);
-        out->id_len.push_back(0);
-        out->ref.push_back('.');
-        out->alt.push_back('.');
-        out->bits.resize(out->bits.size() + (size_t)out->Wh, 0u);
-        out->S++;
-        if (hn < 2 * H - 1) {
-            fprintf(stderr, "[::] ERROR: .hap line %zu has %zu characters, %zu haplotypes need %zu.\n", s + 1, hn, H, 2 * H - 1);
-            return 1;
+    std::string lz, err;
+    if (!ends_with_gz(hap_fn) && H > 0) {
+        // the legend is small: read all of it, then pack the mapped .hap lines in parallel
+        while (leg.next(&ll, &ln)) push_legend_line(out, ll, ln, &lz);
+        bool done = false;
+        if (parse_hap_mapped(hap_fn, H, out, out->pos.size(), &done)) return 1;
+        if (done) {
+            const size_t S = (size_t)out->S;  // the shorter file ends the panel
+            out->pos.resize(S); out->state.resize(S); out->id_off.resize(S); out->id_len.resize(S);
+            out->ref.resize(S); out->alt.resize(S);
+            return 0;
         }
-        uint32_t *row = out->bits.data() + s * (size_t)out->Wh;
-        size_t h = kHaveAvx2 ? pack_alleles_avx2(hl, hn, H, row) : 0;
-        // next: eight text bytes "a b c d " carry four alleles; check the pattern, pick bit 0 of
-        // the four digits and gather them with one multiply
-        for (; h + 4 <= H && 2 * h + 8 <= hn; h += 4) {
-            uint64_t x;
-            memcpy(&x, hl + 2 * h, 8);
-            if ((x & 0xFFFEFFFEFFFEFFFEull) != 0x2030203020302030ull) break;  // not "[01] [01] [01] [01] "
-            const uint64_t nib = (((x & 0x0001000100010001ull) * 0x0001000200040008ull) >> 48) & 0xFu;
-            row[h >> 5] |= (uint32_t)nib << (h & 31);
-        }
-        for (; h < H; h++) {
-            const char c = hl[2 * h];
-            if (c == '1') row[h >> 5] |= 1u << (h & 31);
-            else if (c != '0') {
-                fprintf(stderr, "[::] ERROR: .hap line %zu: allele '%c' of haplotype %zu is not 0 or 1.\n", s + 1, c, h);
+        // small file: the sequential loop, over the legend lines already read
+        const size_t n_leg = out->pos.size();
+        size_t s = 0;
+        for (; s < n_leg && hap.next(&hl, &hn); s++) {
+            out->bits.resize(out->bits.size() + (size_t)out->Wh, 0u);
+            out->S++;
+            if (pack_hap_line(hl, hn, H, s, out->bits.data() + s * (size_t)out->Wh, &err)) {
+                fputs(err.c_str(), stderr);
                 return 1;
             }
         }
-        lz.assign(ll, ln);
-        unsigned long pos;
-        if (sscanf(lz.c_str(), "%128s %lu %128s %128s", id, &pos, ref, alt) != 4) continue;  // src/ibdgem.c:589
-        out->pos[s] = pos;
-        out->state[s] = is_snp(ref, alt) ? 2 : 1;
-        out->id_off[s] = out->text.size();
-        out->id_len[s] = (uint32_t)strlen(id);
-        out->text.append(id, strlen(id) + 1);  // with its NUL
-        out->ref[s] = ref[0];
-        out->alt[s] = alt[0];
+        out->pos.resize(s); out->state.resize(s); out->id_off.resize(s); out->id_len.resize(s);
+        out->ref.resize(s); out->alt.resize(s);
+        return 0;
+    }
+    while (hap.next(&hl, &hn) && leg.next(&ll, &ln)) {
+        const size_t s = (size_t)out->S;
+        out->bits.resize(out->bits.size() + (size_t)out->Wh, 0u);
+        out->S++;
+        if (pack_hap_line(hl, hn, H, s, out->bits.data() + s * (size_t)out->Wh, &err)) {
+            fputs(err.c_str(), stderr);
+            return 1;
+        }
+        push_legend_line(out, ll, ln, &lz);
     }
     return 0;
 }
@@ -406,16 +548,27 @@ bool load_panel_cache(const std::string &cache_fn, const std::string &hap_fn, co
 int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, const std::string &indv_fn,
                        const std::string &cache_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out,
                        bool *hit) {
+    const bool timing = getenv("IBDGEM_PACK_TIMING") != nullptr;  // stage times on stderr
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     PanelText pt;
     const bool cached = load_panel_cache(cache_fn, hap_fn, legend_fn, indv_fn, &pt);
     if (hit) *hit = cached;
+    const double t1 = now();
+    double t2 = t1;
     if (!cached) {
         std::vector<std::string> names;
         if (read_indv(indv_fn, &names) || parse_impute(hap_fn, legend_fn, names, &pt)) return 1;
+        t2 = now();
         if (save_panel_cache(cache_fn, hap_fn, legend_fn, indv_fn, pt))
             fprintf(stderr, "[::] WARNING: could not write the panel cache %s.\n", cache_fn.c_str());
     }
-    return join_pileup(&pt, pu, opt, out);
+    const double t3 = now();
+    const int rc = join_pileup(&pt, pu, opt, out);
+    if (timing)
+        fprintf(stderr, "[pack] cache load %.3f s, text parse %.3f s, cache write %.3f s, pileup join %.3f s\n", t1 - t0, t2 - t1,
+                t3 - t2, now() - t3);
+    return rc;
 }
 
 int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out) {

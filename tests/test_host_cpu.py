@@ -171,3 +171,62 @@ def test_panel_cache_round_trip_and_invalidation(fixture_dir, tmp_path):
     same(got, hostlib.pack(0, hap, leg, indv, pu1))
     got, hit = hostlib.pack_cached(hap, leg, indv, cache, pu1)
     assert hit == 1
+
+
+_MT_SCRIPT = r"""
+import gzip, os, shutil, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import hostlib
+inp, work = sys.argv[2], sys.argv[3]
+rng = np.random.default_rng(5)
+N, S = 37, 900                      # 74 haplotypes: AVX2 groups, an 8-byte group and scalar leftovers
+hap = (rng.random((S, 2 * N)) < 0.3).astype(np.uint8)
+def write(tag, rows, legend_rows, trailing_newline=True, poison=None):
+    lines = [" ".join(map(str, r)) for r in hap[:rows]]
+    if poison is not None:
+        lines[poison] = lines[poison][:10] + "2" + lines[poison][11:]
+    text = "\n".join(lines) + ("\n" if trailing_newline else "")
+    p = os.path.join(work, tag)
+    open(p + ".hap", "w").write(text)
+    with gzip.open(p + ".seq.hap.gz", "wt") as fh:
+        fh.write(text)
+    with open(p + ".legend", "w") as fh:
+        fh.write("id position a0 a1\n")
+        for s in range(legend_rows):
+            fh.write(f"rs{s} {100 + 7 * s} A C\n" if s % 11 else f"rs{s} {100 + 7 * s} AT C\n")
+    with open(p + ".indv", "w") as fh:
+        fh.write("".join(f"i{i}\n" for i in range(N)))
+    with open(p + ".pileup", "w") as fh:
+        for s in range(0, legend_rows, 3):
+            fh.write(f"1\t{100 + 7 * s}\tA\t2\t.c\tII\t]]\n")
+    return p
+for tag, kw in (("plain", dict(rows=S, legend_rows=S)), ("nonl", dict(rows=S, legend_rows=S, trailing_newline=False)),
+                ("shortleg", dict(rows=S, legend_rows=S - 13)), ("shorthap", dict(rows=S - 29, legend_rows=S)),
+                ("bad", dict(rows=S, legend_rows=S, poison=611))):
+    p = write(tag, **kw)
+    mt = hostlib.pack(0, p + ".hap", p + ".legend", p + ".indv", p + ".pileup")           # mapped, threaded
+    seq = hostlib.pack(0, p + ".seq.hap.gz", p + ".legend", p + ".indv", p + ".pileup")   # gz: sequential reader
+    if tag == "bad":
+        assert mt is None and seq is None
+        continue
+    assert mt["S"] == seq["S"] == min(kw["rows"], kw["legend_rows"]), (tag, mt["S"], seq["S"])
+    for key in ("pos", "n_ref", "n_alt", "keep", "dp", "bits"):
+        assert np.array_equal(mt[key], seq[key]), (tag, key)
+    assert np.array_equal(mt["bits"][:, :3].view(np.uint8)[:, : (2 * N + 7) // 8],
+                          np.packbits(hap[: mt["S"]], axis=1, bitorder="little"))
+print("ok")
+"""
+
+
+def test_threaded_hap_parse_matches_sequential(fixture_dir, tmp_path):
+    """Large plain .hap files are mapped and packed by several threads; IBDGEM_PACK_MT_MIN_BYTES=1 sends
+    small files down that path.  Same arrays as the sequential reader (the .gz route) for a missing final
+    newline, a legend shorter / longer than the .hap, and the same refusal of a bad allele."""
+    import subprocess
+    import sys
+    env = dict(os.environ, IBDGEM_PACK_MT_MIN_BYTES="1")
+    r = subprocess.run([sys.executable, "-c", _MT_SCRIPT, hostlib.ROOT, os.path.join(fixture_dir, "input"), str(tmp_path)],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+    assert "allele '2' of haplotype 5" in r.stderr and ".hap line 612" in r.stderr
