@@ -142,9 +142,9 @@ __global__ void fill_nan_kernel(double *p, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K_SITE_TABLE: a warp takes 32 consecutive panel lines.  Phase 1 streams each packed row with
-// coalesced 128-bit loads and popcounts it for the allele frequency (find_f_impute,
-// src/ibd-parse.c:91-99); lane r keeps row r's count.  Phase 2 is lane-parallel, one site per
+// K_SITE_TABLE: a warp takes 32 consecutive panel lines.  Phase 1 streams the packed rows with
+// 128-bit loads (four lanes per row) and popcounts them for the allele frequency (find_f_impute,
+// src/ibd-parse.c:91-99); lane r ends up with row r's count.  Phase 2 is lane-parallel, one site per
 // lane: the AF-range and max-cov filters (src/ibdgem.c:616-626), IBD0, IBD1|g, IBD2|g
 // (src/ibd-math.c:84-142, src/ibdgem.c:632-651) and their logs.
 __global__ void __launch_bounds__(256)
@@ -163,19 +163,28 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
     const int n4 = vec4 ? (nfull >> 2) : 0;
     for (int64_t s0 = s_begin + warp0 * 32; s0 < S; s0 += nwarps * 32) {  // S = exclusive end of the range
         const int rows = (int)min((int64_t)32, S - s0);
+        // four lanes share a row (eight rows per pass): ten independent 16-byte loads per lane, two
+        // shuffles to join the quarters, one to hand row r's count to lane r
         int mycnt = 0;
-        for (int r = 0; r < rows; r++) {
-            const uint32_t *row = bits + (s0 + r) * Wh;
-            const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+        const int j = lane >> 2, q = lane & 3;
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int r = it * 8 + j;
             int cnt = 0;
-            for (int w = lane; w < n4; w += 32) {
-                const uint4 q = __ldg(row4 + w);
-                cnt += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+            if (r < rows) {
+                const uint32_t *row = bits + (s0 + r) * Wh;
+                const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+                for (int w = q; w < n4; w += 4) {
+                    const uint4 x = __ldg(row4 + w);
+                    cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+                }
+                for (int w = (n4 << 2) + q; w < nfull; w += 4) cnt += __popc(__ldg(row + w));
+                if (q == 0 && rem) cnt += __popc(__ldg(row + nfull) & ((1u << rem) - 1u));
             }
-            for (int w = (n4 << 2) + lane; w < nfull; w += 32) cnt += __popc(__ldg(row + w));
-            if (lane == 0 && rem) cnt += __popc(__ldg(row + nfull) & ((1u << rem) - 1u));
-            cnt = warp_sum_i(cnt);
-            if (lane == r) mycnt = cnt;
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+            const int got = __shfl_sync(0xffffffffu, cnt, 4 * (lane & 7));
+            if ((lane >> 3) == it) mycnt = got;
         }
         const int64_t s = s0 + lane;
         if (lane < rows) {
