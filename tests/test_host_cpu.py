@@ -230,3 +230,41 @@ def test_threaded_hap_parse_matches_sequential(fixture_dir, tmp_path):
                        capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
     assert "allele '2' of haplotype 5" in r.stderr and ".hap line 612" in r.stderr
+
+
+def test_pileup_fast_splitter_matches_sscanf_route(fixture_dir, tmp_path):
+    """Well-formed mpileup lines skip the two sscanf calls of line2pul; every other shape still goes
+    through them.  Same store from both routes on a file that mixes ordinary lines with blanks instead
+    of tabs, doubled tabs, signs, long numbers, coverage >= 128, indels, '^' markers, bad characters,
+    wrong counts, short lines and CRLF endings."""
+    rng = np.random.default_rng(11)
+    inp = os.path.join(fixture_dir, "input")
+    legend = open(os.path.join(inp, "test.legend")).read().splitlines()[1:]
+    positions = [int(l.split()[1]) for l in legend]
+    odd = ["1 {p} A 2 .. II ]]", "1\t\t{p}\tA\t2\t..\tII\t]]", "1\t+{p}\tA\t2\t.,\tII\t]]", "1\t{p}\tA\t130\t..\tII\t]]",
+           "1\t{p}\tA\t3\t.+2AC,^]g\tIII\t]]]", "1\t{p}\tA\t2\t.$-1c*\tII\t]]", "1\t{p}\tA\t2\t.x\tII\t]]", "1\t{p}\tA\t3\t..\tII\t]]",
+           "1\t{p}\tA\t2\t..\tIII\t]]]", "1\t{p}\tA\t2\t..", "1\t{p}\tAT\t2\t..\tII\t]]", "1\t0000000000{p}\tA\t1\t.\tI\t]",
+           "1\t{p}\tA\t2\t..\tII\t]]\r", "1\t{p}\tA\t2\t..\tII\t]] \t", "  1\t{p}\tA\t2\t,.\tII\t]]", "1\t{p}\tA\t0\t*\t*\t*",
+           "garbage", ""]
+    lines = []
+    for k, p in enumerate(positions):
+        if k % 3 == 0:
+            lines.append(odd[(k // 3) % len(odd)].format(p=p))
+        else:
+            n = int(rng.integers(1, 6))
+            reads = "".join(rng.choice(list(".,ACGTacgt*"), n))
+            lines.append(f"1\t{p}\tA\t{n}\t{reads}\t{'I' * n}\t{']' * n}")
+    pu = tmp_path / "odd.pileup"
+    pu.write_text("\n".join(lines) + "\n")
+    paths = [os.path.join(inp, f) for f in ("test.hap", "test.legend", "test.indv")]
+    fast = hostlib.pack(0, *paths, str(pu))
+    os.environ["IBDGEM_PILEUP_NO_FAST"] = "1"
+    try:
+        slow = hostlib.pack(0, *paths, str(pu))
+    finally:
+        del os.environ["IBDGEM_PILEUP_NO_FAST"]
+    assert fast is not None and slow is not None
+    assert len(fast["pileup_cov"]) == len(slow["pileup_cov"]) > len(positions) // 2
+    for key in ("pileup_cov", "pos", "n_ref", "n_alt", "keep", "dp"):
+        np.testing.assert_array_equal(fast[key], slow[key])
+    assert fast["keep"].sum() > 50
