@@ -1458,6 +1458,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
             if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_bookdone) == cudaSuccess) fprintf(tl, "bookkeeping_on_host %.4f %.4f\n", ms, ms);
             fprintf(tl, "---\n");
             fclose(tl);
+            cudaGetLastError();  // an event made before the timeline was switched on has no timestamp: not an engine error
         }
     }
 
