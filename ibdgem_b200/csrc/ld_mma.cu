@@ -56,6 +56,7 @@ struct LdCache {
 constexpr int KEY_PAD = -(1 << 30);   // key of padding / excluded columns
 constexpr int KEY_INIT = -(1 << 29);  // initial running maximum
 constexpr double SCREEN_NATS = 32.0;
+constexpr int MAX_GRID_Y = 65535;  // windows ride on gridDim.y of the transposition and expansion kernels
 constexpr size_t LD_OPERAND_BUDGET = (size_t)12 << 30;  // bytes of expanded int8 operands per window batch
 
 // ---------------------------------------------------------------------------------------------
@@ -1322,8 +1323,9 @@ static int cache_windows(ibdgem_engine *e, int w_hi) {
     {
         LaunchScope ls(e, K_LD_TRANSPOSE);
         const int words = (c->H + 31) / 32;
-        ld_transpose_kernel<<<dim3((words + 7) / 8, w_hi - c->tw_upto), 1024, 0, e->stream>>>(
-            c->tw_upto, e->d_bits, e->Wh, c->H, c->d_infsite, c->Wpad, c->WP32, c->d_tbits);
+        for (int w0 = c->tw_upto; w0 < w_hi; w0 += MAX_GRID_Y)  // windows ride on gridDim.y
+            ld_transpose_kernel<<<dim3((words + 7) / 8, std::min(MAX_GRID_Y, w_hi - w0)), 1024, 0, e->stream>>>(
+                w0, e->d_bits, e->Wh, c->H, c->d_infsite, c->Wpad, c->WP32, c->d_tbits);
     }
     IBD_CUDA(cudaGetLastError());
     c->tw_upto = w_hi;
@@ -1409,9 +1411,10 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         }
         {
             LaunchScope ls(e, K_LD_EXPAND_TGT);
-            ld_expand_tgt_kernel<<<dim3((unsigned)((T + 7) / 8), (unsigned)nW), 256, 0, e->stream>>>(
-                0, T, c->H, c->Wpad, c->WP32, outW, d_targets, c->d_tbits, c->d_nr, c->d_nk, c->d_C0, e->alpha, e->beta, e->kappa,
-                nullptr, d_Rt, d_wll);
+            for (int w0 = 0; w0 < nW; w0 += MAX_GRID_Y)
+                ld_expand_tgt_kernel<<<dim3((unsigned)((T + 7) / 8), (unsigned)std::min(MAX_GRID_Y, nW - w0)), 256, 0, e->stream>>>(
+                    w0, T, c->H, c->Wpad, c->WP32, outW, d_targets, c->d_tbits, c->d_nr, c->d_nk, c->d_C0, e->alpha, e->beta,
+                    e->kappa, nullptr, d_Rt, d_wll);
         }
         IBD_CUDA(cudaGetLastError());
         return 0;
@@ -1429,7 +1432,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         const char *sb = getenv("IBDGEM_LD_BUDGET_MB");
         budget = sb && atol(sb) > 0 ? (size_t)atol(sb) << 20 : LD_OPERAND_BUDGET;
     }
-    const int nWb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nW, budget / per_window));
+    const int nWb = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nW, budget / per_window, (size_t)MAX_GRID_Y}));
     int32_t *d_bgU, *d_ownU, *d_rowown, *d_akey;
     double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp, *d_Rt;
     unsigned char *d_A, *d_B;

@@ -389,3 +389,14 @@ def test_panel_in_caller_device_memory_declared_in_pieces():
         e.panel_rows_ready(S // 2)
         with pytest.raises(RuntimeError, match="declared ready"):
             e.score_ld(case.targets, case.bg, 3)
+
+
+def test_ld_more_windows_than_a_grid_dimension():
+    """70,000 windows of ten sites: the window index rides on gridDim.y (limit 65,535) in the
+    transposition and expansion kernels, so such calls are sliced."""
+    ec = _engine()
+    case = _synth_case(75, 760_000, 6, 10, True, range(2), pu_idx=-1, depth=3.0)
+    results = ec.run_engine(case, expanded=False)
+    assert results[0]["ld_path"] == 1 and results[0]["n_windows"] > 65535
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
