@@ -2,14 +2,18 @@
 // options, defaults, messages and stdout table as the reference (src/hiddengem.c:13-25, 171-288).
 // The recursion runs on the GPU in log space (hiddengem_viterbi_batch); the reference's x87
 // long-double running products are re-synthesised for printing from their logarithms.
-// Additive: -s may be given several times; the tables are scored in one batch and printed in order.
+// Additive: -s may be given several times; the tables are read in parallel, scored in one batch and
+// printed in order (formatted in parallel).
 #include <getopt.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/ibdgem_b200.h"
@@ -54,6 +58,23 @@ void put_score(char *dst, double L) {
     }
     const long e = (long)ex;
     sprintf(dst, "%se%c%02ld", m, e < 0 ? '-' : '+', e < 0 ? -e : e);
+}
+
+// fn(i) for i in [0, n) on up to eight threads (one when n == 1)
+template <class F>
+void parallel_for(size_t n, F fn) {
+    const size_t nt = std::max<size_t>(1, std::min<size_t>({n, 8, (size_t)std::thread::hardware_concurrency()}));
+    if (nt == 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (size_t k = 0; k < nt; k++)
+        pool.emplace_back([&] {
+            for (size_t i; (i = next.fetch_add(1)) < n;) fn(i);
+        });
+    for (auto &t : pool) t.join();
 }
 
 // init_summary, src/hiddengem.c:51-84: skip leading '#' lines, then every line that parses
@@ -111,10 +132,16 @@ int main(int argc, char *argv[]) {
     }
     for (int i = optind; i < argc; i++) fprintf(stderr, "Given extra argument %s.\n", argv[i]);
 
+    // the tables are independent files: read by a few threads, concatenated in command-line order
+    std::vector<std::vector<double>> per_file(files.size());
+    std::vector<int> read_rc(files.size(), 0);
+    parallel_for(files.size(), [&](size_t i) { read_rc[i] = read_summary(files[i], &per_file[i]); });
     std::vector<double> lik;
     std::vector<int64_t> off{0};
-    for (const std::string &fn : files) {
-        if (read_summary(fn, &lik)) exit(1);
+    for (size_t i = 0; i < files.size(); i++) {
+        if (read_rc[i]) exit(1);
+        lik.insert(lik.end(), per_file[i].begin(), per_file[i].end());
+        std::vector<double>().swap(per_file[i]);
         off.push_back((int64_t)(lik.size() / 3));
     }
     if (files.empty() || lik.empty()) {
@@ -135,21 +162,33 @@ int main(int argc, char *argv[]) {
         exit(1);
     }
     ibdgem_engine_destroy(e);
-    for (size_t t = 0; t + 1 < off.size(); t++) {
-        const int64_t a = off[t], b = off[t + 1];
-        const double n = (double)(b - a);
-        printf("Segment\tIBD0_Score\tIBD1_Score\tIBD2_Score\tInferred_State\n");
-        char s0[48], s1[48], s2[48];
-        for (int64_t i = a; i < b; i++) {
-            put_score(s0, score[(size_t)i * 3]);
-            put_score(s1, score[(size_t)i * 3 + 1]);
-            put_score(s2, score[(size_t)i * 3 + 2]);
-            printf("%d\t%s\t%s\t%s\t%d\n", (int)(i - a + 1), s0, s1, s2, (int)state[(size_t)i]);
-        }
-        const double c0 = (double)counts[t * 3], c1 = (double)counts[t * 3 + 1], c2 = (double)counts[t * 3 + 2];
-        printf("#%% IBD0 (n = %.0f): %.2f\n", c0, (c0 / n) * 100);
-        printf("#%% IBD1 (n = %.0f): %.2f\n", c1, (c1 / n) * 100);
-        printf("#%% IBD2 (n = %.0f): %.2f\n", c2, (c2 / n) * 100);
+    // one table's text does not depend on another's: formatted by a few threads, a wave of tables at a
+    // time, written in order
+    const size_t n_tables = off.size() - 1, wave = 64;
+    std::vector<std::string> text(wave);
+    for (size_t t0 = 0; t0 < n_tables; t0 += wave) {
+        const size_t nt = std::min(wave, n_tables - t0);
+        parallel_for(nt, [&](size_t k) {
+            const size_t t = t0 + k;
+            const int64_t a = off[t], b = off[t + 1];
+            const double n = (double)(b - a);
+            std::string &out = text[k];
+            out.clear();
+            out.reserve((size_t)(b - a) * 48 + 256);
+            out += "Segment\tIBD0_Score\tIBD1_Score\tIBD2_Score\tInferred_State\n";
+            char s0[48], s1[48], s2[48], row[192];
+            for (int64_t i = a; i < b; i++) {
+                put_score(s0, score[(size_t)i * 3]);
+                put_score(s1, score[(size_t)i * 3 + 1]);
+                put_score(s2, score[(size_t)i * 3 + 2]);
+                out.append(row, (size_t)snprintf(row, sizeof row, "%d\t%s\t%s\t%s\t%d\n", (int)(i - a + 1), s0, s1, s2, (int)state[(size_t)i]));
+            }
+            const double c0 = (double)counts[t * 3], c1 = (double)counts[t * 3 + 1], c2 = (double)counts[t * 3 + 2];
+            out.append(row, (size_t)snprintf(row, sizeof row, "#%% IBD0 (n = %.0f): %.2f\n", c0, (c0 / n) * 100));
+            out.append(row, (size_t)snprintf(row, sizeof row, "#%% IBD1 (n = %.0f): %.2f\n", c1, (c1 / n) * 100));
+            out.append(row, (size_t)snprintf(row, sizeof row, "#%% IBD2 (n = %.0f): %.2f\n", c2, (c2 / n) * 100));
+        });
+        for (size_t k = 0; k < nt; k++) fwrite(text[k].data(), 1, text[k].size(), stdout);
     }
     return 0;
 }

@@ -153,3 +153,16 @@ def test_panel_cache_runs_reproduce_the_golden_files(fixture_dir, tmp_path):
             for kind in ("tab", "summary"):
                 name = f"sample{k}.sample{t}.{kind}.txt"
                 assert _body(out / name) == _body(os.path.join(gold, name))
+
+
+def test_hiddengem_several_tables_in_one_call(golden_dir):
+    """-s given several times (additive): tables are read and formatted by several threads, scored in
+    one batch, and printed in command-line order — the same text as one call per table."""
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    files = [os.path.join(ca, "nonld_w10", f"UNKWN.{ind}.summary.txt") for ind in ("ind2", "ind3", "ind5", "ind3", "ind2")]
+    single = [_run("hiddengem", ["-s", f]).stdout for f in files[:3]]
+    args = []
+    for f in files:
+        args += ["-s", f]
+    together = _run("hiddengem", args).stdout
+    assert together == single[0] + single[1] + single[2] + single[1] + single[0]
