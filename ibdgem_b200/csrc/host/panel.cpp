@@ -207,9 +207,24 @@ __attribute__((target("avx2,bmi2"))) static size_t pack_alleles_avx2(const char 
     }
     return h;
 }
+// Eight VCF genotype columns of the plain shape "\ta|b" (or "a/b") in 32 bytes -> 16 haplotype bits.
+// False if any of the 32 bytes is not what that shape has there (is_gt, src/ibd-parse.c:150-173).
+__attribute__((target("avx2,bmi2"))) static bool vcf_group_avx2(const char *p, uint32_t *bits16) {
+    const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+    const uint32_t m1 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('1')));
+    const uint32_t m0 = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('0')));
+    const uint32_t mt = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('\t')));
+    const uint32_t ms = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('|'))) |
+                        (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(x, _mm256_set1_epi8('/')));
+    if ((mt & 0x11111111u) != 0x11111111u || ((m0 | m1) & 0xAAAAAAAAu) != 0xAAAAAAAAu || (ms & 0x44444444u) != 0x44444444u)
+        return false;
+    *bits16 = _pext_u32(m1, 0xAAAAAAAAu);
+    return true;
+}
 static const bool kHaveAvx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
 #else
 static size_t pack_alleles_avx2(const char *, size_t, size_t, uint32_t *) { return 0; }
+static bool vcf_group_avx2(const char *, uint32_t *) { return false; }
 static const bool kHaveAvx2 = false;
 #endif
 
@@ -638,6 +653,21 @@ int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions
         size_t k = 0;
         bool ok = true;
         while (k < N) {
+            if (kHaveAvx2 && k + 8 <= N) {
+                // eight plain "\ta|b" columns at once; anything else (longer fields, doubled tabs, bad
+                // characters) is left to the column-by-column code below
+                const size_t p = line[i] == '\t' ? i : i - 1;  // (i > 0 here: at least nine columns came before)
+                uint32_t got;
+                if (line[p] == '\t' && p + 32 <= e && vcf_group_avx2(line + p, &got)) {
+                    const uint64_t v = (uint64_t)got << ((2 * k) & 31);
+                    row[(2 * k) >> 5] |= (uint32_t)v;
+                    if (v >> 32) row[((2 * k) >> 5) + 1] |= (uint32_t)(v >> 32);
+                    k += 8;
+                    i = p + 32;
+                    while (i < e && line[i] != '\t') i++;  // the eighth column may carry more than the genotype
+                    continue;
+                }
+            }
             while (i < e && line[i] == '\t') i++;
             size_t j = i;
             while (j < e && line[j] != '\t') j++;

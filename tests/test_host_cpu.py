@@ -268,3 +268,38 @@ def test_pileup_fast_splitter_matches_sscanf_route(fixture_dir, tmp_path):
     for key in ("pileup_cov", "pos", "n_ref", "n_alt", "keep", "dp"):
         np.testing.assert_array_equal(fast[key], slow[key])
     assert fast["keep"].sum() > 50
+
+
+def test_vcf_genotype_groups_and_column_by_column_agree(tmp_path):
+    """pack_vcf takes eight plain "a|b" columns per AVX2 step and falls back to one column at a time for
+    anything else; the bits must be the genotypes whatever mix a line has: '/' separators, columns with
+    extra FORMAT fields, a line with a missing genotype (skipped, src/ibd-parse.c:150-173)."""
+    rng = np.random.default_rng(17)
+    N, S = 37, 400
+    hap = (rng.random((S, 2 * N)) < 0.35).astype(np.uint8)
+    lines = ["##fileformat=VCFv4.2",
+             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"i{i}" for i in range(N))]
+    bad = {123}
+    for s in range(S):
+        cols = []
+        for i in range(N):
+            sep = "|" if (s + i) % 5 else "/"
+            g = f"{hap[s, 2 * i]}{sep}{hap[s, 2 * i + 1]}"
+            if s % 7 == 3 and rng.random() < 0.2:
+                g += ":35:0.9"
+            if s in bad and i == 20:
+                g = "./."
+            cols.append(g)
+        lines.append(f"1\t{100 + 7 * s}\trs{s}\tA\tC\t50\tPASS\t.\tGT\t" + "\t".join(cols))
+    vcf = tmp_path / "p.vcf"
+    vcf.write_text("\n".join(lines) + "\n")
+    pu = tmp_path / "p.pileup"
+    pu.write_text("".join(f"1\t{100 + 7 * s}\tA\t2\t.c\tII\t]]\n" for s in range(S)))
+    got = hostlib.pack(1, str(vcf), None, None, str(pu))
+    assert got is not None and got["S"] == S and got["N"] == N
+    want = np.packbits(hap, axis=1, bitorder="little")
+    want[list(bad)] = 0
+    np.testing.assert_array_equal(got["bits"].view(np.uint8)[:, : want.shape[1]], want)
+    keep = np.ones(S, np.uint8)
+    keep[list(bad)] = 0
+    np.testing.assert_array_equal(got["keep"], keep)
