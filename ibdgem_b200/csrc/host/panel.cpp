@@ -656,7 +656,7 @@ int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions
             if (kHaveAvx2 && k + 8 <= N) {
                 // eight plain "\ta|b" columns at once; anything else (longer fields, doubled tabs, bad
                 // characters) is left to the column-by-column code below
-                const size_t p = line[i] == '\t' ? i : i - 1;  // (i > 0 here: at least nine columns came before)
+                const size_t p = (i < e && line[i] == '\t') ? i : i - 1;  // (i > 0 here: nine columns came before)
                 uint32_t got;
                 if (line[p] == '\t' && p + 32 <= e && vcf_group_avx2(line + p, &got)) {
                     const uint64_t v = (uint64_t)got << ((2 * k) & 31);
