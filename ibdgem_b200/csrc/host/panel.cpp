@@ -258,6 +258,35 @@ static int pack_hap_line(const char *hl, size_t hn, size_t H, size_t s, uint32_t
     return 0;
 }
 
+// "%128s %lu %128s %128s" on a line of the plain shape — four blank-separated tokens, the second one
+// to eighteen digits, none longer than 128 characters — without sscanf; false for any other line.
+static bool split_legend_fast(const char *p, const char *end, char *id, unsigned long *pos, char *ref, char *alt) {
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; };
+    if (memchr(p, 0, (size_t)(end - p))) return false;
+    const char *tb[4];
+    size_t tn[4];
+    for (int k = 0; k < 4; k++) {
+        while (p < end && blank(*p)) p++;
+        const char *q = p;
+        while (q < end && !blank(*q)) q++;
+        tb[k] = p;
+        tn[k] = (size_t)(q - p);
+        if (tn[k] < 1 || tn[k] > 128) return false;
+        p = q;
+    }
+    if (tn[1] > 18) return false;
+    unsigned long v = 0;
+    for (size_t i = 0; i < tn[1]; i++) {
+        if (tb[1][i] < '0' || tb[1][i] > '9') return false;
+        v = v * 10 + (unsigned long)(tb[1][i] - '0');
+    }
+    *pos = v;
+    memcpy(id, tb[0], tn[0]); id[tn[0]] = 0;
+    memcpy(ref, tb[2], tn[2]); ref[tn[2]] = 0;
+    memcpy(alt, tb[3], tn[3]); alt[tn[3]] = 0;
+    return true;
+}
+
 // One legend line -> the per-site text fields (src/ibdgem.c:589-592).
 static void push_legend_line(PanelText *out, const char *ll, size_t ln, std::string *lz) {
     char id[129], ref[129], alt[129];
@@ -267,9 +296,14 @@ static void push_legend_line(PanelText *out, const char *ll, size_t ln, std::str
     out->id_len.push_back(0);
     out->ref.push_back('.');
     out->alt.push_back('.');
-    lz->assign(ll, ln);
     unsigned long pos;
-    if (sscanf(lz->c_str(), "%128s %lu %128s %128s", id, &pos, ref, alt) != 4) return;
+    static const bool fast = getenv("IBDGEM_LEGEND_NO_FAST") == nullptr;  // tests compare both routes
+    if (fast && split_legend_fast(ll, ll + ln, id, &pos, ref, alt)) {
+        // same four values as the sscanf below
+    } else {
+        lz->assign(ll, ln);
+        if (sscanf(lz->c_str(), "%128s %lu %128s %128s", id, &pos, ref, alt) != 4) return;
+    }
     out->pos.back() = pos;
     out->state.back() = is_snp(ref, alt) ? 2 : 1;
     out->id_off.back() = out->text.size();

@@ -303,3 +303,44 @@ def test_vcf_genotype_groups_and_column_by_column_agree(tmp_path):
     keep = np.ones(S, np.uint8)
     keep[list(bad)] = 0
     np.testing.assert_array_equal(got["keep"], keep)
+
+
+_LEGEND_SCRIPT = r"""
+import hashlib, os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import hostlib
+w = sys.argv[2]
+g = hostlib.pack(0, w + "/o.hap", w + "/o.legend", w + "/o.indv", w + "/o.pileup")
+h = hashlib.sha256()
+for key in ("pos", "keep", "n_ref", "n_alt", "dp", "bits"):
+    h.update(g[key].tobytes())
+print(g["S"], int(g["keep"].sum()), h.hexdigest())
+"""
+
+
+def test_legend_fast_splitter_matches_sscanf_route(tmp_path):
+    """Legend lines of the plain shape skip sscanf; the others (signs, letters after the digits, tokens
+    over 128 characters, too few columns, tabs, leading blanks, CRLF, extra columns) go through it.
+    Same packed arrays from both routes."""
+    import subprocess
+    import sys
+    odd = ["rs{s} +{p} A C", "rs{s} {p}x A C", "rs{s} {p} A", "rs{s}\t{p}\tA\tC", "   rs{s}   {p}  A  C  extra  columns",
+           "rs{s} {p} A C\r", "L" * 130 + " {p} A C", "rs{s} {p} AC G", "rs{s} 00000000000000000000{p} A C", "", "rs{s} {p} A " + "G" * 129]
+    S = 330
+    leg = ["id position a0 a1"]
+    for s in range(S):
+        p = 100 + 7 * s
+        leg.append(odd[(s // 3) % len(odd)].format(s=s, p=p) if s % 3 == 0 else f"rs{s} {p} A C")
+    (tmp_path / "o.legend").write_text("\n".join(leg) + "\n")
+    (tmp_path / "o.hap").write_text("0 1 1 0 0 0\n" * S)
+    (tmp_path / "o.indv").write_text("a\nb\nc\n")
+    (tmp_path / "o.pileup").write_text("".join(f"1\t{100 + 7 * s}\tA\t2\t.c\tII\t]]\n" for s in range(S)))
+    outs = []
+    for env in ({}, {"IBDGEM_LEGEND_NO_FAST": "1"}):
+        r = subprocess.run([sys.executable, "-c", _LEGEND_SCRIPT, hostlib.ROOT, str(tmp_path)], capture_output=True, text=True,
+                           env=dict(os.environ, **env), timeout=120)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1]
+    n_sites, n_kept = int(outs[0].split()[0]), int(outs[0].split()[1])
+    assert n_sites == S and 200 < n_kept < S
