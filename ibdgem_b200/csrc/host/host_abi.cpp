@@ -1,5 +1,6 @@
 // host_abi.cpp — C entry points over the host packer (no CUDA), so the CPU test-suite can check
 // the parsers and the bit packing against the reference's fixtures without a GPU.
+#include <cstdio>
 #include <cstring>
 
 #include "panel.h"
@@ -60,6 +61,20 @@ void *ibdhost_pack_cached(const char *hap, const char *legend, const char *indv,
     }
     return h;
 }
+void *ibdhost_pack_vcf_cached(const char *vcf, const char *cache, const char *pileup, const char *chr, double min_qual,
+                              int *hit) {
+    Handle *h = new Handle();
+    PackOptions po;
+    po.min_qual = min_qual;
+    bool was_hit = false;
+    const bool ok = load_pileup(pileup, chr, &h->pu) == 0 && pack_vcf_cached(vcf, cache, h->pu, po, &h->panel, &was_hit) == 0;
+    if (hit) *hit = was_hit ? 1 : 0;
+    if (!ok) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
 void ibdhost_free(void *p) { delete static_cast<Handle *>(p); }
 int64_t ibdhost_n_sites(void *p) { return static_cast<Handle *>(p)->panel.S; }
 int32_t ibdhost_n_indiv(void *p) { return static_cast<Handle *>(p)->panel.N; }
@@ -76,6 +91,15 @@ const double *ibdhost_af_user(void *p) {
     return h->panel.af_user.empty() ? nullptr : h->panel.af_user.data();
 }
 const uint32_t *ibdhost_pileup_cov(void *p) { return static_cast<Handle *>(p)->pu.cov.data(); }
+// "chr\trsID\tREF\tALT" of a kept site, as the tab.txt writer would print them; 0 for other sites
+int ibdhost_site_label(void *p, int64_t site, char *buf, int cap) {
+    Handle *h = static_cast<Handle *>(p);
+    const PackedPanel &P = h->panel;
+    const size_t s = (size_t)site;
+    if (site < 0 || site >= P.S || !P.host_keep[s]) return 0;
+    return snprintf(buf, (size_t)cap, "%s\t%.*s\t%c\t%c", h->pu.chr_names[P.chr_id[s]].c_str(), (int)P.id_len[s],
+                    P.text.data() + P.id_off[s], P.ref[s], P.alt[s]);
+}
 const char *ibdhost_name(void *p, int32_t i) { return static_cast<Handle *>(p)->panel.names[(size_t)i].c_str(); }
 
 }  // extern "C"

@@ -3,7 +3,7 @@
 // (src/ibdgem.c:41-66, 779-1183); the arithmetic is done by libibdgem_b200.so through the C ABI
 // (include/ibdgem_b200.h) and there is no CPU fallback.  Additive options: --gpus N (shard the
 // targets over N devices), --batch N (targets per engine call), --no-tab (skip *.tab.txt),
-// --panel-cache FILE (binary cache of the parsed IMPUTE panel).
+// --panel-cache FILE (binary cache of the parsed IMPUTE or VCF panel).
 #include <getopt.h>
 #include <limits.h>
 #include <unistd.h>
@@ -513,7 +513,13 @@ int main(int argc, char *argv[]) {
     }
     PackedPanel panel;
     if (o.in_vcf) {
-        if (pack_vcf(o.vcf_fn, pu, po, &panel)) exit(1);
+        if (!o.cache_fn.empty()) {
+            bool hit = false;
+            if (pack_vcf_cached(o.vcf_fn, o.cache_fn, pu, po, &panel, &hit)) exit(1);
+            fprintf(stderr, "[::] panel cache %s: %s\n", o.cache_fn.c_str(), hit ? "loaded" : "written");
+        } else if (pack_vcf(o.vcf_fn, pu, po, &panel)) {
+            exit(1);
+        }
     } else {
         std::vector<std::string> names;
         {

@@ -32,27 +32,6 @@ bool is_snp(const char *ref, const char *alt) {  // src/ibdgem.c:113-119
     return strlen(ref) == 1 && strchr("ACGT", ref[0]) && strlen(alt) == 1 && strchr("ACGT", alt[0]);
 }
 
-void init_panel(PackedPanel *p, int32_t n_indiv) {
-    p->N = n_indiv;
-    const int64_t words = (2 * (int64_t)n_indiv + 31) / 32;
-    p->Wh = (words + 3) / 4 * 4;  // 16-byte rows for 128-bit loads on the device
-}
-
-void push_site(PackedPanel *p) {
-    p->pos.push_back(0);
-    p->n_ref.push_back(0);
-    p->n_alt.push_back(0);
-    p->host_keep.push_back(0);
-    p->dp.push_back(0);
-    p->chr_id.push_back(0);
-    p->id_off.push_back(0);
-    p->id_len.push_back(0);
-    p->ref.push_back('.');
-    p->alt.push_back('.');
-    p->bits.resize(p->bits.size() + (size_t)p->Wh, 0u);
-    p->S++;
-}
-
 // Everything about a kept line that comes from the pileup and the option tables.
 void fill_kept(PackedPanel *p, size_t s, const PileupStore &pu, int64_t pul, const char *id, char ref, char alt) {
     p->host_keep[s] = 1;
@@ -480,6 +459,7 @@ int join_pileup(PanelText *pt, const PileupStore &pu, const PackOptions &opt, Pa
     out->alt.assign(S, '.');
     for (size_t s = 0; s < S; s++) {
         if (pt->state[s] != 2) continue;  // is_snp, src/ibdgem.c:592
+        if (!pt->qual.empty() && pt->qual[s] < opt.min_qual) continue;  // VCF -q, src/ibdgem.c:297
         const uint64_t pos = pt->pos[s];
         const int64_t pul = pu.fetch(pos);
         if (pul < 0) continue;
@@ -511,10 +491,10 @@ struct CacheHeader {
     int64_t S;
     int64_t Wh;
     int32_t N;
-    uint32_t reserved;
+    uint32_t has_qual;  // VCF panels carry the QUAL column (the -q filter is applied at join time)
     uint64_t names_bytes, text_bytes;
 };
-const char kCacheMagic[8] = {'I', 'B', 'D', 'G', 'P', 'N', 'L', '1'};
+const char kCacheMagic[8] = {'I', 'B', 'D', 'G', 'P', 'N', 'L', '2'};
 
 bool file_key(const std::string &fn, uint64_t *size, uint64_t *mtime_ns) {
     struct stat st;
@@ -523,8 +503,13 @@ bool file_key(const std::string &fn, uint64_t *size, uint64_t *mtime_ns) {
     *mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
     return true;
 }
-bool make_key(const std::string &hap_fn, const std::string &legend_fn, const std::string &indv_fn, uint64_t key[6]) {
-    return file_key(hap_fn, &key[0], &key[1]) && file_key(legend_fn, &key[2], &key[3]) && file_key(indv_fn, &key[4], &key[5]);
+// up to three input files (.hap, .legend, .indv — or the VCF alone, the other slots zero)
+bool make_key(const std::vector<std::string> &inputs, uint64_t key[6]) {
+    memset(key, 0, 6 * sizeof(uint64_t));
+    if (inputs.empty() || inputs.size() > 3) return false;
+    for (size_t i = 0; i < inputs.size(); i++)
+        if (!file_key(inputs[i], &key[2 * i], &key[2 * i + 1])) return false;
+    return true;
 }
 template <class T>
 bool put(FILE *f, const std::vector<T> &v) { return v.empty() || fwrite(v.data(), sizeof(T), v.size(), f) == v.size(); }
@@ -536,11 +521,11 @@ bool get(FILE *f, std::vector<T> *v, size_t n) {
 
 }  // namespace
 
-int save_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
-                     const std::string &indv_fn, const PanelText &pt) {
+int save_panel_cache(const std::string &cache_fn, const std::vector<std::string> &inputs, const PanelText &pt) {
     CacheHeader h{};
     memcpy(h.magic, kCacheMagic, 8);
-    if (!make_key(hap_fn, legend_fn, indv_fn, h.key)) return 1;
+    if (!make_key(inputs, h.key)) return 1;
+    h.has_qual = pt.qual.empty() ? 0u : 1u;
     std::string names;
     for (const auto &n : pt.names) names.append(n.c_str(), n.size() + 1);
     h.S = pt.S; h.Wh = pt.Wh; h.N = pt.N;
@@ -551,6 +536,7 @@ int save_panel_cache(const std::string &cache_fn, const std::string &hap_fn, con
     if (!f) return 1;
     bool ok = fwrite(&h, sizeof h, 1, f) == 1 && (names.empty() || fwrite(names.data(), 1, names.size(), f) == names.size()) &&
               put(f, pt.pos) && put(f, pt.state) && put(f, pt.id_off) && put(f, pt.id_len) && put(f, pt.ref) && put(f, pt.alt) &&
+              put(f, pt.qual) &&
               (pt.text.empty() || fwrite(pt.text.data(), 1, pt.text.size(), f) == pt.text.size()) && put(f, pt.bits);
     ok = (fclose(f) == 0) && ok;
     if (!ok || rename(tmp.c_str(), cache_fn.c_str()) != 0) {
@@ -560,20 +546,20 @@ int save_panel_cache(const std::string &cache_fn, const std::string &hap_fn, con
     return 0;
 }
 
-bool load_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
-                      const std::string &indv_fn, PanelText *pt) {
+bool load_panel_cache(const std::string &cache_fn, const std::vector<std::string> &inputs, PanelText *pt) {
     FILE *f = fopen(cache_fn.c_str(), "rb");
     if (!f) return false;
     CacheHeader h;
     uint64_t key[6];
     bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, kCacheMagic, 8) == 0 &&
-              make_key(hap_fn, legend_fn, indv_fn, key) && memcmp(key, h.key, sizeof key) == 0 && h.S >= 0 && h.N > 0 &&
+              make_key(inputs, key) && memcmp(key, h.key, sizeof key) == 0 && h.S >= 0 && h.N > 0 &&
               h.Wh * 32 >= 2 * (int64_t)h.N;
     if (ok) {
         const size_t S = (size_t)h.S;
         std::vector<char> names, text;
         ok = get(f, &names, (size_t)h.names_bytes) && get(f, &pt->pos, S) && get(f, &pt->state, S) && get(f, &pt->id_off, S) &&
-             get(f, &pt->id_len, S) && get(f, &pt->ref, S) && get(f, &pt->alt, S) && get(f, &text, (size_t)h.text_bytes) &&
+             get(f, &pt->id_len, S) && get(f, &pt->ref, S) && get(f, &pt->alt, S) && get(f, &pt->qual, h.has_qual ? S : 0) &&
+             get(f, &text, (size_t)h.text_bytes) &&
              get(f, &pt->bits, S * (size_t)h.Wh) && fgetc(f) == EOF;
         if (ok) {
             pt->S = h.S; pt->N = h.N; pt->Wh = h.Wh;
@@ -601,7 +587,8 @@ int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, 
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     PanelText pt;
-    const bool cached = load_panel_cache(cache_fn, hap_fn, legend_fn, indv_fn, &pt);
+    const std::vector<std::string> inputs{hap_fn, legend_fn, indv_fn};
+    const bool cached = load_panel_cache(cache_fn, inputs, &pt);
     if (hit) *hit = cached;
     const double t1 = now();
     double t2 = t1;
@@ -609,7 +596,7 @@ int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, 
         std::vector<std::string> names;
         if (read_indv(indv_fn, &names) || parse_impute(hap_fn, legend_fn, names, &pt)) return 1;
         t2 = now();
-        if (save_panel_cache(cache_fn, hap_fn, legend_fn, indv_fn, pt))
+        if (save_panel_cache(cache_fn, inputs, pt))
             fprintf(stderr, "[::] WARNING: could not write the panel cache %s.\n", cache_fn.c_str());
     }
     const double t3 = now();
@@ -620,7 +607,7 @@ int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, 
     return rc;
 }
 
-int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out) {
+int parse_vcf(const std::string &vcf_fn, PanelText *out) {
     LineReader vcf;
     if (!vcf.open(vcf_fn)) return 1;
     const char *line;
@@ -649,12 +636,21 @@ int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions
             return 1;
         }
     }
-    init_panel(out, (int32_t)out->names.size());
+    out->N = (int32_t)out->names.size();
+    out->Wh = ((2 * (int64_t)out->N + 31) / 32 + 3) / 4 * 4;  // 16-byte rows for 128-bit loads on the device
     const size_t N = out->names.size();
     std::string id, ref, alt, qual;
     while (vcf.next(&line, &len)) {
         const size_t s = (size_t)out->S;
-        push_site(out);
+        out->pos.push_back(0);
+        out->state.push_back(0);
+        out->id_off.push_back(0);
+        out->id_len.push_back(0);
+        out->ref.push_back('.');
+        out->alt.push_back('.');
+        out->qual.push_back(0.0);
+        out->bits.resize(out->bits.size() + (size_t)out->Wh, 0u);
+        out->S++;
         size_t e = len;
         while (e > 0 && line[e - 1] == '\n') e--;
         // nine tab-separated leading fields, then the genotype columns (src/ibdgem.c:272-273)
@@ -720,20 +716,36 @@ int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions
             for (int64_t w = 0; w < out->Wh; w++) row[w] = 0;
             continue;
         }
-        if (!is_snp(ref.c_str(), alt.c_str())) continue;
-        if (atof(qual.c_str()) < opt.min_qual) continue;
-        const int64_t pul = pu.fetch(pos);
-        if (pul < 0) continue;
-        if (opt.positions && !opt.positions->count(pos)) continue;
-        fill_kept(out, s, pu, pul, id.c_str(), ref[0], alt[0]);
-    }
-    if (opt.af) {
-        out->af_user.assign((size_t)out->S, NAN);
-        for (int64_t s = 0; s < out->S; s++)
-            if (out->host_keep[(size_t)s])
-                if (const double *f = opt.af->fetch(out->pos[(size_t)s])) out->af_user[(size_t)s] = *f;
+        // what is left depends on the options and the pileup (join_pileup): SNP test, -q, pileup line, -p
+        out->state[s] = is_snp(ref.c_str(), alt.c_str()) ? 2 : 1;
+        out->qual[s] = atof(qual.c_str());
+        out->id_off[s] = out->text.size();
+        out->id_len[s] = (uint32_t)id.size();
+        out->text.append(id.c_str(), id.size() + 1);  // with its NUL
+        out->ref[s] = ref[0];
+        out->alt[s] = alt[0];
     }
     return 0;
+}
+
+int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out) {
+    PanelText pt;
+    if (parse_vcf(vcf_fn, &pt)) return 1;
+    return join_pileup(&pt, pu, opt, out);
+}
+
+int pack_vcf_cached(const std::string &vcf_fn, const std::string &cache_fn, const PileupStore &pu, const PackOptions &opt,
+                    PackedPanel *out, bool *hit) {
+    PanelText pt;
+    const std::vector<std::string> inputs{vcf_fn};
+    const bool cached = load_panel_cache(cache_fn, inputs, &pt);
+    if (hit) *hit = cached;
+    if (!cached) {
+        if (parse_vcf(vcf_fn, &pt)) return 1;
+        if (save_panel_cache(cache_fn, inputs, pt))
+            fprintf(stderr, "[::] WARNING: could not write the panel cache %s.\n", cache_fn.c_str());
+    }
+    return join_pileup(&pt, pu, opt, out);
 }
 
 }  // namespace ibdhost

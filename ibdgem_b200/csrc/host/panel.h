@@ -60,7 +60,7 @@ struct PackOptions {
 int pack_impute(const std::string &hap_fn, const std::string &legend_fn, const std::vector<std::string> &names,
                 const PileupStore &pu, const PackOptions &opt, PackedPanel *out);
 
-// The pileup-independent half of an IMPUTE panel — what the .hap / .legend / .indv text says — and
+// The pileup-independent half of a panel — what the .hap / .legend / .indv text (or the VCF) says — and
 // its binary cache (one panel is scored against many pileups; re-parsing 10 GB of
 // text per run is the reference's real wall-clock cost, src/ibdgem.c:573-574).
 struct PanelText {
@@ -69,10 +69,11 @@ struct PanelText {
     int64_t Wh = 0;
     std::vector<std::string> names;
     std::vector<uint64_t> pos;    // 0 where the legend line did not parse (src/ibdgem.c:589)
-    std::vector<uint8_t> state;   // 0 = legend line unparsable, 1 = parsed but not a SNP, 2 = SNP
+    std::vector<uint8_t> state;   // 0 = line unparsable / skipped, 1 = parsed but not a SNP, 2 = SNP
     std::vector<uint64_t> id_off; // rsID of every parsed line, NUL-terminated, in `text`
     std::vector<uint32_t> id_len;
     std::vector<char> ref, alt;   // first character of REF / ALT
+    std::vector<double> qual;     // VCF only: QUAL of the record (-q is applied when joining); empty for IMPUTE
     std::string text;
     std::vector<uint32_t> bits;   // [S][Wh]
 };
@@ -80,16 +81,17 @@ int parse_impute(const std::string &hap_fn, const std::string &legend_fn, const 
                  PanelText *out);
 // Joins the panel text with a pileup and the option tables; takes the bits out of `pt`.
 int join_pileup(PanelText *pt, const PileupStore &pu, const PackOptions &opt, PackedPanel *out);
-// Cache file = the PanelText arrays behind a header that names size and mtime of the three input
-// files; a cache whose header does not match them is ignored and rewritten.
-int save_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
-                     const std::string &indv_fn, const PanelText &pt);
-bool load_panel_cache(const std::string &cache_fn, const std::string &hap_fn, const std::string &legend_fn,
-                      const std::string &indv_fn, PanelText *pt);
+int parse_vcf(const std::string &vcf_fn, PanelText *out);
+// Cache file = the PanelText arrays behind a header that names size and mtime of the input files
+// (.hap, .legend, .indv — or the VCF); a cache whose header does not match them is ignored and rewritten.
+int save_panel_cache(const std::string &cache_fn, const std::vector<std::string> &inputs, const PanelText &pt);
+bool load_panel_cache(const std::string &cache_fn, const std::vector<std::string> &inputs, PanelText *pt);
 // pack_impute through the cache: *hit tells whether the text files were parsed (false) or not (true).
 int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, const std::string &indv_fn,
                        const std::string &cache_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out,
                        bool *hit);
+int pack_vcf_cached(const std::string &vcf_fn, const std::string &cache_fn, const PileupStore &pu, const PackOptions &opt,
+                    PackedPanel *out, bool *hit);
 int pack_vcf(const std::string &vcf_fn, const PileupStore &pu, const PackOptions &opt, PackedPanel *out);
 
 }  // namespace ibdhost

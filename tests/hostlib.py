@@ -37,6 +37,10 @@ def lib():
             f.argtypes = [C.c_void_p]
         _lib.ibdhost_pack_cached.restype = C.c_void_p
         _lib.ibdhost_pack_cached.argtypes = [C.c_char_p] * 6 + [C.POINTER(C.c_int)]
+        _lib.ibdhost_pack_vcf_cached.restype = C.c_void_p
+        _lib.ibdhost_pack_vcf_cached.argtypes = [C.c_char_p] * 4 + [C.c_double, C.POINTER(C.c_int)]
+        _lib.ibdhost_site_label.restype = C.c_int
+        _lib.ibdhost_site_label.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int]
         _lib.ibdhost_name.restype = C.c_char_p
         _lib.ibdhost_name.argtypes = [C.c_void_p, C.c_int32]
         _lib.ibdhost_free.argtypes = [C.c_void_p]
@@ -52,6 +56,13 @@ def pack_cached(hap, legend, indv, cache, pileup, chrom=None):
     L = lib()
     hit = C.c_int(-1)
     h = L.ibdhost_pack_cached(_b(hap), _b(legend), _b(indv), _b(cache), _b(pileup), _b(chrom), C.byref(hit))
+    return (_arrays(L, h) if h else None), hit.value
+
+
+def pack_vcf_cached(vcf, cache, pileup, chrom=None, min_qual=0.0):
+    L = lib()
+    hit = C.c_int(-1)
+    h = L.ibdhost_pack_vcf_cached(_b(vcf), _b(cache), _b(pileup), _b(chrom), min_qual, C.byref(hit))
     return (_arrays(L, h) if h else None), hit.value
 
 
@@ -76,6 +87,9 @@ def _arrays(L, h):
                    dp=arr(L.ibdhost_dp(h), C.c_uint32, S), bits=arr(L.ibdhost_bits(h), C.c_uint32, S * Wh).reshape(S, Wh),
                    names=[L.ibdhost_name(h, i).decode() for i in range(N)],
                    pileup_cov=arr(L.ibdhost_pileup_cov(h), C.c_uint32, L.ibdhost_n_pileup(h)))
+        buf = C.create_string_buffer(1024)
+        out["labels"] = [buf.value.decode() if L.ibdhost_site_label(h, s, buf, 1024) > 0 else None for s in range(S)] \
+            if S <= 100_000 else None  # chr, rsID, REF, ALT of the kept sites (small panels only)
         af_ptr = L.ibdhost_af_user(h)
         out["af_user"] = arr(af_ptr, C.c_double, S) if af_ptr else None
         return out

@@ -344,3 +344,33 @@ def test_legend_fast_splitter_matches_sscanf_route(tmp_path):
     assert outs[0] == outs[1]
     n_sites, n_kept = int(outs[0].split()[0]), int(outs[0].split()[1])
     assert n_sites == S and 200 < n_kept < S
+
+
+def test_vcf_panel_cache_applies_quality_filter_at_join_time(golden_dir, tmp_path):
+    """--panel-cache with VCF input: the cache holds the parsed records including QUAL, so a later run
+    with another -q (or another pileup) loads it and still filters like the uncached packer."""
+    import shutil
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    vcf = str(tmp_path / "panel.vcf")
+    shutil.copy(os.path.join(ca, "panel.vcf"), vcf)
+    pu = os.path.join(ca, "unk.pileup")
+    cache = str(tmp_path / "vcf.cache")
+
+    def same(a, b):
+        assert a["names"] == b["names"] and a["labels"] == b["labels"]
+        for key in ("pos", "n_ref", "n_alt", "keep", "dp", "bits"):
+            np.testing.assert_array_equal(a[key], b[key])
+
+    got, hit = hostlib.pack_vcf_cached(vcf, cache, pu)
+    assert hit == 0
+    same(got, hostlib.pack(1, vcf, None, None, pu))
+    got30, hit = hostlib.pack_vcf_cached(vcf, cache, pu, min_qual=30.0)
+    assert hit == 1
+    same(got30, hostlib.pack(1, vcf, None, None, pu, min_qual=30.0))
+    assert got30["keep"].sum() < got["keep"].sum()
+    # an IMPUTE cache is not mistaken for a VCF cache of other files
+    hap, leg, indv = (os.path.join(ca, f) for f in ("panel.hap", "panel.legend", "panel.indv"))
+    _, hit = hostlib.pack_cached(hap, leg, indv, cache, pu)
+    assert hit == 0
+    _, hit = hostlib.pack_vcf_cached(vcf, cache, pu)
+    assert hit == 0

@@ -18,18 +18,21 @@ DRIVER = r"""
 #include "panel.h"
 #include "pileup_store.h"
 using namespace ibdhost;
-int main(int argc, char **argv) {  // mode (0 impute, 1 vcf, 2 impute through the cache) files...
+int main(int argc, char **argv) {  // mode (0 impute, 1 vcf, 2 impute through the cache, 3 vcf through the cache) files...
     const int mode = atoi(argv[1]);
     PileupStore pu;
     PackOptions po;
     PackedPanel panel;
     int rc = 0;
-    if (load_pileup(argv[mode == 1 ? 3 : 5], nullptr, &pu)) return 3;
+    if (load_pileup(argv[(mode == 1 || mode == 3) ? 3 : 5], nullptr, &pu)) return 3;
     if (mode == 0) {
         std::vector<std::string> names;
         rc = read_indv(argv[4], &names) || pack_impute(argv[2], argv[3], names, pu, po, &panel);
     } else if (mode == 1) {
         rc = pack_vcf(argv[2], pu, po, &panel);
+    } else if (mode == 3) {
+        bool hit;
+        rc = pack_vcf_cached(argv[2], argv[4], pu, po, &panel, &hit);
     } else {
         bool hit;
         rc = pack_impute_cached(argv[2], argv[3], argv[4], argv[6], pu, po, &panel, &hit);
@@ -78,11 +81,12 @@ def main():
             lines.append(f"1\t{100 + 7 * s}\trs{s}\tA\tC\t50\tPASS\t.\tGT\t" + "\t".join(
                 f"{hap[s, 2 * i]}|{hap[s, 2 * i + 1]}" + (":9" if (s + i) % 11 == 0 else "") for i in range(N)))
         open("o.vcf", "w").write("\n".join(lines))
-        if os.path.exists("o.cache"):
-            os.remove("o.cache")
+        for f in ("o.cache", "v.cache"):
+            if os.path.exists(f):
+                os.remove(f)
         imp = ["o.hap", "o.legend", "o.indv", "o.pileup"]
         outs = {run(["0"] + imp), run(["0"] + imp, mt), run(["2"] + imp + ["o.cache"]), run(["2"] + imp + ["o.cache"]),
-                run(["1", "o.vcf", "o.pileup"])}
+                run(["1", "o.vcf", "o.pileup"]), run(["3", "o.vcf", "o.pileup", "v.cache"]), run(["3", "o.vcf", "o.pileup", "v.cache"])}
         assert len(outs) == 1, (N, outs)  # same bits and keep flags by every route
     open("t.hap", "w").write("0 1 0\n0 1")
     open("t.legend", "w").write("id position a0 a1\nrs1 100 A C\nrs2 107 A C\n")
