@@ -298,18 +298,21 @@ static void push_legend_line(PanelText *out, const char *ll, size_t ln, std::str
 // and the first bad line in file order is the one reported.
 static constexpr size_t MT_MIN_BYTES = (size_t)32 << 20;
 static constexpr unsigned MT_MAX_THREADS = 16;
+static size_t mt_min_bytes() {  // IBDGEM_PACK_MT_MIN_BYTES: tests push small fixtures through the threaded path
+    static size_t v = 0;
+    if (!v) {
+        const char *sm = getenv("IBDGEM_PACK_MT_MIN_BYTES");
+        v = sm && atol(sm) > 0 ? (size_t)atol(sm) : MT_MIN_BYTES;
+    }
+    return v;
+}
 
 static int parse_hap_mapped(const std::string &hap_fn, size_t H, PanelText *out, size_t n_legend, bool *done) {
     *done = false;
     const int fd = open(hap_fn.c_str(), O_RDONLY);
     if (fd < 0) return 0;  // the caller's sequential path reports it
     struct stat st;
-    static size_t min_bytes = 0;
-    if (!min_bytes) {  // IBDGEM_PACK_MT_MIN_BYTES: tests push small fixtures through the threaded path
-        const char *sm = getenv("IBDGEM_PACK_MT_MIN_BYTES");
-        min_bytes = sm && atol(sm) > 0 ? (size_t)atol(sm) : MT_MIN_BYTES;
-    }
-    if (fstat(fd, &st) != 0 || (size_t)st.st_size < min_bytes || st.st_size == 0) {
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < mt_min_bytes() || st.st_size == 0) {
         close(fd);
         return 0;
     }
@@ -607,39 +610,279 @@ int pack_impute_cached(const std::string &hap_fn, const std::string &legend_fn, 
     return rc;
 }
 
+// --- VCF ------------------------------------------------------------------------------------------
+namespace {
+
+// What one VCF record contributes to the panel text (the bits go straight into the record's row).
+struct VcfRecord {
+    uint64_t pos = 0;
+    uint8_t state = 0;
+    char ref = '.', alt = '.';
+    double qual = 0;
+    size_t id_off = 0;  // into the text blob the id was appended to
+    uint32_t id_len = 0;
+};
+
+struct VcfScratch {
+    std::string id, ref, alt, qual;
+};
+
+// One body line (src/ibdgem.c:272-331).  `text` receives the record's ID with a NUL when the record
+// reaches the SNP test; `msgs` the reference's diagnostics.
+void parse_vcf_line(const char *line, size_t len, size_t N, int64_t Wh, uint32_t *row, VcfRecord *rec, std::string *text,
+                    std::string *msgs, VcfScratch *sc) {
+    size_t e = len;
+    while (e > 0 && line[e - 1] == '\n') e--;
+    // nine tab-separated leading fields, then the genotype columns (src/ibdgem.c:272-273)
+    size_t fb[10], fe[10];
+    size_t i = 0;
+    int nf = 0;
+    while (nf < 9 && i <= e) {
+        size_t j = i;
+        while (j < e && line[j] != '\t') j++;
+        fb[nf] = i;
+        fe[nf] = j;
+        nf++;
+        if (j >= e) { i = e + 1; break; }
+        i = j + 1;
+    }
+    if (nf < 9 || i > e) return;  // fewer than 10 columns: "skipped"
+    char *endp = nullptr;
+    const std::string posz(line + fb[1], fe[1] - fb[1]);
+    const unsigned long pos = strtoul(posz.c_str(), &endp, 10);
+    if (endp == posz.c_str()) return;
+    rec->pos = pos;
+    std::string &id = sc->id, &ref = sc->ref, &alt = sc->alt, &qual = sc->qual;
+    id.assign(line + fb[2], fe[2] - fb[2]);
+    ref.assign(line + fb[3], fe[3] - fb[3]);
+    alt.assign(line + fb[4], fe[4] - fb[4]);
+    qual.assign(line + fb[5], fe[5] - fb[5]);
+    if (id.empty() || ref.empty() || alt.empty() || qual.empty() || fe[6] == fb[6] || fe[7] == fb[7]) return;
+    if (alt.find(',') != std::string::npos) return;  // is_biallelic, src/ibdgem.c:161-167
+    // genotypes of EVERY sample must look like [01][/|][01].* (src/ibd-parse.c:150-173)
+    size_t k = 0;
+    bool ok = true;
+    while (k < N) {
+        if (kHaveAvx2 && k + 8 <= N) {
+            // eight plain "\ta|b" columns at once; anything else (longer fields, doubled tabs, bad
+            // characters) is left to the column-by-column code below
+            const size_t p = (i < e && line[i] == '\t') ? i : i - 1;  // (i > 0 here: nine columns came before)
+            uint32_t got;
+            if (line[p] == '\t' && p + 32 <= e && vcf_group_avx2(line + p, &got)) {
+                const uint64_t v = (uint64_t)got << ((2 * k) & 31);
+                row[(2 * k) >> 5] |= (uint32_t)v;
+                if (v >> 32) row[((2 * k) >> 5) + 1] |= (uint32_t)(v >> 32);
+                k += 8;
+                i = p + 32;
+                while (i < e && line[i] != '\t') i++;  // the eighth column may carry more than the genotype
+                continue;
+            }
+        }
+        while (i < e && line[i] == '\t') i++;
+        size_t j = i;
+        while (j < e && line[j] != '\t') j++;
+        if (j - i < 3 || (line[i] != '0' && line[i] != '1') || (line[i + 1] != '/' && line[i + 1] != '|') ||
+            (line[i + 2] != '0' && line[i + 2] != '1')) {
+            ok = false;
+            break;
+        }
+        if (line[i] == '1') row[(2 * k) >> 5] |= 1u << ((2 * k) & 31);
+        if (line[i + 2] == '1') row[(2 * k + 1) >> 5] |= 1u << ((2 * k + 1) & 31);
+        k++;
+        i = j;
+    }
+    if (!ok) {
+        char m[128];
+        snprintf(m, sizeof m, "Failed to parse genotype fields at %lu. Skipping to next site.\n", pos);
+        msgs->append(m);
+        for (int64_t w = 0; w < Wh; w++) row[w] = 0;
+        return;
+    }
+    // what is left depends on the options and the pileup (join_pileup): SNP test, -q, pileup line, -p
+    rec->state = is_snp(ref.c_str(), alt.c_str()) ? 2 : 1;
+    rec->qual = atof(qual.c_str());
+    rec->id_off = text->size();
+    rec->id_len = (uint32_t)id.size();
+    text->append(id.c_str(), id.size() + 1);  // with its NUL
+    rec->ref = ref[0];
+    rec->alt = alt[0];
+}
+
+void store_record(PanelText *out, size_t s, const VcfRecord &r, size_t text_base) {
+    out->pos[s] = r.pos;
+    out->state[s] = r.state;
+    out->ref[s] = r.ref;
+    out->alt[s] = r.alt;
+    out->qual[s] = r.qual;
+    out->id_off[s] = r.state ? text_base + r.id_off : 0;
+    out->id_len[s] = r.id_len;
+}
+
+void size_records(PanelText *out, size_t S) {
+    out->S = (int64_t)S;
+    out->pos.assign(S, 0);
+    out->state.assign(S, 0);
+    out->id_off.assign(S, 0);
+    out->id_len.assign(S, 0);
+    out->ref.assign(S, '.');
+    out->alt.assign(S, '.');
+    out->qual.assign(S, 0.0);
+    out->bits.assign(S * (size_t)out->Wh, 0u);
+}
+
+// sample names of the "#CHROM" line, split on tabs like strtok (src/ibd-parse.c:113-147)
+int parse_vcf_header(const char *line, size_t len, PanelText *out) {
+    static const char kHead[] = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t";
+    const size_t hl = sizeof(kHead) - 1;
+    if (!line || len <= hl || memcmp(line, kHead, hl) != 0 || line[hl] == '\n') {
+        fprintf(stderr, "[::] ERROR parsing VCF header.\n");
+        return 1;
+    }
+    size_t e = len;
+    while (e > hl && line[e - 1] == '\n') e--;
+    size_t i = hl;
+    while (i < e) {
+        while (i < e && line[i] == '\t') i++;
+        size_t j = i;
+        while (j < e && line[j] != '\t') j++;
+        if (j > i) out->names.emplace_back(line + i, j - i);
+        i = j;
+    }
+    if (out->names.empty()) {
+        fprintf(stderr, "[::] ERROR: No samples found.\n");
+        return 1;
+    }
+    out->N = (int32_t)out->names.size();
+    out->Wh = ((2 * (int64_t)out->N + 31) / 32 + 3) / 4 * 4;  // 16-byte rows for 128-bit loads on the device
+    return 0;
+}
+
+// Large plain VCF files: mapped, the body lines parsed by several threads (records are independent; a
+// record's index is the number of newlines between the header and it).  IDs and diagnostics are
+// gathered per thread and joined in file order, so the result is that of the sequential reader.
+int parse_vcf_mapped(const std::string &vcf_fn, PanelText *out, bool *done) {
+    *done = false;
+    const int fd = open(vcf_fn.c_str(), O_RDONLY);
+    if (fd < 0) return 0;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || (size_t)st.st_size < mt_min_bytes() || st.st_size == 0) {
+        close(fd);
+        return 0;
+    }
+    const size_t n = (size_t)st.st_size;
+    void *map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return 0;
+    madvise(map, n, MADV_SEQUENTIAL);
+    const char *data = static_cast<const char *>(map);
+    // header: "##" lines, then the "#CHROM" line
+    size_t p = 0;
+    const char *hline = nullptr;
+    size_t hlen = 0;
+    while (p < n) {
+        const char *nl = static_cast<const char *>(memchr(data + p, '\n', n - p));
+        const size_t len = nl ? (size_t)(nl - (data + p)) + 1 : n - p;
+        if (len >= 2 && data[p] == '#' && data[p + 1] == '#') {
+            p += len;
+            continue;
+        }
+        hline = data + p;
+        hlen = len;
+        p += len;
+        break;
+    }
+    if (parse_vcf_header(hline, hlen, out)) {
+        munmap(map, n);
+        return 1;
+    }
+    const size_t body = p, N = out->names.size();
+    const unsigned nt = std::max(1u, std::min(MT_MAX_THREADS, std::thread::hardware_concurrency()));
+    std::vector<size_t> cut(nt + 1), newlines(nt, 0);
+    for (unsigned t = 0; t <= nt; t++) cut[t] = body + (n - body) / nt * t;
+    cut[nt] = n;
+    auto for_threads = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    for_threads([&](unsigned t) {
+        size_t c = 0;
+        for (const char *q = data + cut[t], *e = data + cut[t + 1]; q < e;) {
+            const char *nl = static_cast<const char *>(memchr(q, '\n', (size_t)(e - q)));
+            if (!nl) break;
+            c++;
+            q = nl + 1;
+        }
+        newlines[t] = c;
+    });
+    size_t S = 0;
+    std::vector<size_t> first_line(nt);  // newlines of the body before cut[t]
+    for (unsigned t = 0; t < nt; t++) {
+        first_line[t] = S;
+        S += newlines[t];
+    }
+    if (n > body && data[n - 1] != '\n') S++;  // last record without a newline
+    size_records(out, S);
+    struct Part {
+        std::string text, msgs;
+        std::vector<VcfRecord> recs;
+        size_t first = 0;
+    };
+    std::vector<Part> parts(nt);
+    for_threads([&](unsigned t) {
+        Part &pt = parts[t];
+        size_t q = cut[t], idx = first_line[t];
+        if (q > body && data[q - 1] != '\n') {  // move to the first line that starts in this range
+            const char *nl = static_cast<const char *>(memchr(data + q, '\n', cut[t + 1] - q));
+            if (!nl) return;
+            q = (size_t)(nl - data) + 1;
+            idx++;
+        }
+        pt.first = idx;
+        VcfScratch sc;
+        while (q < cut[t + 1] && idx < S) {
+            const char *nl = static_cast<const char *>(memchr(data + q, '\n', n - q));
+            const size_t len = nl ? (size_t)(nl - (data + q)) + 1 : n - q;
+            pt.recs.emplace_back();
+            parse_vcf_line(data + q, len, N, out->Wh, out->bits.data() + idx * (size_t)out->Wh, &pt.recs.back(), &pt.text, &pt.msgs, &sc);
+            q += len;
+            idx++;
+        }
+    });
+    munmap(map, n);
+    for (unsigned t = 0; t < nt; t++) {
+        const size_t base = out->text.size();
+        out->text += parts[t].text;
+        for (size_t k = 0; k < parts[t].recs.size(); k++) store_record(out, parts[t].first + k, parts[t].recs[k], base);
+        fputs(parts[t].msgs.c_str(), stderr);
+    }
+    *done = true;
+    return 0;
+}
+
+}  // namespace
+
 int parse_vcf(const std::string &vcf_fn, PanelText *out) {
+    if (!ends_with_gz(vcf_fn)) {
+        {   // same diagnostics as the sequential reader for a file that cannot be opened
+            LineReader probe;
+            if (!probe.open(vcf_fn)) return 1;
+        }
+        bool done = false;
+        if (parse_vcf_mapped(vcf_fn, out, &done)) return 1;
+        if (done) return 0;
+        *out = PanelText();
+    }
     LineReader vcf;
     if (!vcf.open(vcf_fn)) return 1;
     const char *line;
     size_t len;
     bool have = vcf.next(&line, &len);
     while (have && len >= 2 && line[0] == '#' && line[1] == '#') have = vcf.next(&line, &len);
-    static const char kHead[] = "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t";
-    const size_t hl = sizeof(kHead) - 1;
-    if (!have || len <= hl || memcmp(line, kHead, hl) != 0 || line[hl] == '\n') {
-        fprintf(stderr, "[::] ERROR parsing VCF header.\n");
-        return 1;
-    }
-    {  // sample names, split on tabs like strtok (src/ibd-parse.c:113-147)
-        size_t e = len;
-        while (e > hl && line[e - 1] == '\n') e--;
-        size_t i = hl;
-        while (i < e) {
-            while (i < e && line[i] == '\t') i++;
-            size_t j = i;
-            while (j < e && line[j] != '\t') j++;
-            if (j > i) out->names.emplace_back(line + i, j - i);
-            i = j;
-        }
-        if (out->names.empty()) {
-            fprintf(stderr, "[::] ERROR: No samples found.\n");
-            return 1;
-        }
-    }
-    out->N = (int32_t)out->names.size();
-    out->Wh = ((2 * (int64_t)out->N + 31) / 32 + 3) / 4 * 4;  // 16-byte rows for 128-bit loads on the device
+    if (parse_vcf_header(have ? line : nullptr, have ? len : 0, out)) return 1;
     const size_t N = out->names.size();
-    std::string id, ref, alt, qual;
+    VcfScratch sc;
+    std::string msgs;
     while (vcf.next(&line, &len)) {
         const size_t s = (size_t)out->S;
         out->pos.push_back(0);
@@ -651,79 +894,13 @@ int parse_vcf(const std::string &vcf_fn, PanelText *out) {
         out->qual.push_back(0.0);
         out->bits.resize(out->bits.size() + (size_t)out->Wh, 0u);
         out->S++;
-        size_t e = len;
-        while (e > 0 && line[e - 1] == '\n') e--;
-        // nine tab-separated leading fields, then the genotype columns (src/ibdgem.c:272-273)
-        size_t fb[10], fe[10];
-        size_t i = 0;
-        int nf = 0;
-        while (nf < 9 && i <= e) {
-            size_t j = i;
-            while (j < e && line[j] != '\t') j++;
-            fb[nf] = i;
-            fe[nf] = j;
-            nf++;
-            if (j >= e) { i = e + 1; break; }
-            i = j + 1;
+        VcfRecord rec;
+        parse_vcf_line(line, len, N, out->Wh, out->bits.data() + s * (size_t)out->Wh, &rec, &out->text, &msgs, &sc);
+        store_record(out, s, rec, 0);
+        if (!msgs.empty()) {
+            fputs(msgs.c_str(), stderr);
+            msgs.clear();
         }
-        if (nf < 9 || i > e) continue;  // fewer than 10 columns: "skipped"
-        char *endp = nullptr;
-        const std::string posz(line + fb[1], fe[1] - fb[1]);
-        const unsigned long pos = strtoul(posz.c_str(), &endp, 10);
-        if (endp == posz.c_str()) continue;
-        out->pos[s] = pos;
-        id.assign(line + fb[2], fe[2] - fb[2]);
-        ref.assign(line + fb[3], fe[3] - fb[3]);
-        alt.assign(line + fb[4], fe[4] - fb[4]);
-        qual.assign(line + fb[5], fe[5] - fb[5]);
-        if (id.empty() || ref.empty() || alt.empty() || qual.empty() || fe[6] == fb[6] || fe[7] == fb[7]) continue;
-        if (alt.find(',') != std::string::npos) continue;  // is_biallelic, src/ibdgem.c:161-167
-        // genotypes of EVERY sample must look like [01][/|][01].* (src/ibd-parse.c:150-173)
-        uint32_t *row = out->bits.data() + s * (size_t)out->Wh;
-        size_t k = 0;
-        bool ok = true;
-        while (k < N) {
-            if (kHaveAvx2 && k + 8 <= N) {
-                // eight plain "\ta|b" columns at once; anything else (longer fields, doubled tabs, bad
-                // characters) is left to the column-by-column code below
-                const size_t p = (i < e && line[i] == '\t') ? i : i - 1;  // (i > 0 here: nine columns came before)
-                uint32_t got;
-                if (line[p] == '\t' && p + 32 <= e && vcf_group_avx2(line + p, &got)) {
-                    const uint64_t v = (uint64_t)got << ((2 * k) & 31);
-                    row[(2 * k) >> 5] |= (uint32_t)v;
-                    if (v >> 32) row[((2 * k) >> 5) + 1] |= (uint32_t)(v >> 32);
-                    k += 8;
-                    i = p + 32;
-                    while (i < e && line[i] != '\t') i++;  // the eighth column may carry more than the genotype
-                    continue;
-                }
-            }
-            while (i < e && line[i] == '\t') i++;
-            size_t j = i;
-            while (j < e && line[j] != '\t') j++;
-            if (j - i < 3 || (line[i] != '0' && line[i] != '1') || (line[i + 1] != '/' && line[i + 1] != '|') ||
-                (line[i + 2] != '0' && line[i + 2] != '1')) {
-                ok = false;
-                break;
-            }
-            if (line[i] == '1') row[(2 * k) >> 5] |= 1u << ((2 * k) & 31);
-            if (line[i + 2] == '1') row[(2 * k + 1) >> 5] |= 1u << ((2 * k + 1) & 31);
-            k++;
-            i = j;
-        }
-        if (!ok) {
-            fprintf(stderr, "Failed to parse genotype fields at %lu. Skipping to next site.\n", pos);
-            for (int64_t w = 0; w < out->Wh; w++) row[w] = 0;
-            continue;
-        }
-        // what is left depends on the options and the pileup (join_pileup): SNP test, -q, pileup line, -p
-        out->state[s] = is_snp(ref.c_str(), alt.c_str()) ? 2 : 1;
-        out->qual[s] = atof(qual.c_str());
-        out->id_off[s] = out->text.size();
-        out->id_len[s] = (uint32_t)id.size();
-        out->text.append(id.c_str(), id.size() + 1);  // with its NUL
-        out->ref[s] = ref[0];
-        out->alt[s] = alt[0];
     }
     return 0;
 }

@@ -215,14 +215,46 @@ for tag, kw in (("plain", dict(rows=S, legend_rows=S)), ("nonl", dict(rows=S, le
         assert np.array_equal(mt[key], seq[key]), (tag, key)
     assert np.array_equal(mt["bits"][:, :3].view(np.uint8)[:, : (2 * N + 7) // 8],
                           np.packbits(hap[: mt["S"]], axis=1, bitorder="little"))
+# VCF: records of every kind the parser distinguishes, no final newline
+NV, SV = 19, 300
+hv = (rng.random((SV, 2 * NV)) < 0.3).astype(int)
+lines = ["##a", "##b", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(f"s{i}" for i in range(NV))]
+for s in range(SV):
+    p, ref, alt, q, idv = 100 + 7 * s, "A", "C", "50", f"rs{s}"
+    m = s % 13
+    if m == 1: alt = "C,G"
+    if m == 2: ref = "AT"
+    if m == 3: q = "5"
+    if m == 4: idv = ""
+    if m == 5: q = "."
+    cols = [f"{hv[s, 2 * i]}|{hv[s, 2 * i + 1]}" + (":1" if (s * i) % 17 == 3 else "") for i in range(NV)]
+    if m == 6: cols[7] = ".|."
+    if m == 7: cols = cols[:5]
+    line = f"1\t{p}\t{idv}\t{ref}\t{alt}\t{q}\tPASS\t.\tGT\t" + "\t".join(cols)
+    if m == 8: line = f"1\tx{p}\trs\tA\tC\t50\tPASS\t.\tGT\t" + "\t".join(cols)
+    if m == 9: line = f"1\t{p}\trs\tA\tC"
+    lines.append(line)
+text = "\n".join(lines)
+open(os.path.join(work, "v.vcf"), "w").write(text)
+with gzip.open(os.path.join(work, "v.seq.vcf.gz"), "wt") as fh:
+    fh.write(text)
+open(os.path.join(work, "v.pileup"), "w").write("".join(f"1\t{100 + 7 * s}\tA\t2\t.c\tII\t]]\n" for s in range(SV)))
+for q in (0.0, 20.0):
+    mt = hostlib.pack(1, os.path.join(work, "v.vcf"), None, None, os.path.join(work, "v.pileup"), min_qual=q)
+    seq = hostlib.pack(1, os.path.join(work, "v.seq.vcf.gz"), None, None, os.path.join(work, "v.pileup"), min_qual=q)
+    assert mt["S"] == seq["S"] == SV and mt["names"] == seq["names"] and mt["labels"] == seq["labels"]
+    for key in ("pos", "n_ref", "n_alt", "keep", "dp", "bits"):
+        assert np.array_equal(mt[key], seq[key]), ("vcf", key)
+    assert 50 < mt["keep"].sum() < SV
 print("ok")
 """
 
 
 def test_threaded_hap_parse_matches_sequential(fixture_dir, tmp_path):
-    """Large plain .hap files are mapped and packed by several threads; IBDGEM_PACK_MT_MIN_BYTES=1 sends
-    small files down that path.  Same arrays as the sequential reader (the .gz route) for a missing final
-    newline, a legend shorter / longer than the .hap, and the same refusal of a bad allele."""
+    """Large plain .hap and VCF files are mapped and packed by several threads; IBDGEM_PACK_MT_MIN_BYTES=1
+    sends small files down that path.  Same arrays as the sequential reader (the .gz route) for a missing
+    final newline, a legend shorter / longer than the .hap, the same refusal of a bad allele, and every
+    kind of VCF record the parser distinguishes."""
     import subprocess
     import sys
     env = dict(os.environ, IBDGEM_PACK_MT_MIN_BYTES="1")

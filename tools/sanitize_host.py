@@ -86,7 +86,8 @@ def main():
                 os.remove(f)
         imp = ["o.hap", "o.legend", "o.indv", "o.pileup"]
         outs = {run(["0"] + imp), run(["0"] + imp, mt), run(["2"] + imp + ["o.cache"]), run(["2"] + imp + ["o.cache"]),
-                run(["1", "o.vcf", "o.pileup"]), run(["3", "o.vcf", "o.pileup", "v.cache"]), run(["3", "o.vcf", "o.pileup", "v.cache"])}
+                run(["1", "o.vcf", "o.pileup"]), run(["1", "o.vcf", "o.pileup"], mt), run(["3", "o.vcf", "o.pileup", "v.cache"]),
+                run(["3", "o.vcf", "o.pileup", "v.cache"])}
         assert len(outs) == 1, (N, outs)  # same bits and keep flags by every route
     open("t.hap", "w").write("0 1 0\n0 1")
     open("t.legend", "w").write("id position a0 a1\nrs1 100 A C\nrs2 107 A C\n")
@@ -98,6 +99,7 @@ def main():
                              "1\t100\tr\tA\tC\t5\tP\t.\tGT\t0|1\t0|1\t0|1\t0|1\t0|1\t0|1\t0|1\t0|\n"
                              "1\t107\tr\tA\tC\t5\tP\t.\tGT\t\n1\t114\tr\tA\tC\t5\tP\t.\tGT")
     run(["1", "t.vcf", "o.pileup"])
+    run(["1", "t.vcf", "o.pileup"], mt)
     os.chdir(ROOT)
     shutil.rmtree(WORK, ignore_errors=True)
     for args, text in reports:
