@@ -24,12 +24,14 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-const char *const kKernelNames[K_COUNT] = {
+static const char *const kKernelNameList[] = {
     "site_table",     "scan_count",    "scan_offsets",  "scan_rank",    "window_nonld", "counters",
     "expand_sites",   "ld_general",    "ld_finalize",   "ld_compact",   "ld_c0",        "ld_transpose",
     "ld_stage",       "ld_expand_bg",  "ld_expand_tgt", "ld_windows",   "ld_ibd0",
     "ld_mma",         "viterbi",       "viterbi_norm",  "viterbi_back", "viterbi_out", "fill",
 };
+static_assert(sizeof(kKernelNameList) / sizeof(kKernelNameList[0]) == K_COUNT, "one name per KernelId, in enum order");
+const char *const *const kKernelNames = kKernelNameList;
 
 // ---------------------------------------------------------------------------------------------
 // instrumentation

@@ -52,7 +52,7 @@ enum KernelId {
     K_COUNT
 };
 
-extern const char *const kKernelNames[K_COUNT];
+extern const char *const *const kKernelNames;  // [K_COUNT], in enum order (engine.cu)
 
 struct LdCache;  // ld_mma.cu
 
