@@ -142,3 +142,20 @@ def test_two_rank_panel_replication(S, pieces):
         assert calls[0] == ("set", S, 40, 5)
         ready = [c[1] for c in calls[1:]]
         assert ready == sorted(ready) and ready[-1] == S and len(ready) <= pieces
+
+
+@pytest.mark.parametrize("S,pieces", [(10, 1), (1001, 4), (5, 8)])
+def test_panel_replication_single_process(S, pieces):
+    """Without a process group the helper degenerates to piece-wise copies of the whole panel."""
+    Wh = 3
+    h_bits = torch.arange(S * Wh, dtype=torch.int32).reshape(S, Wh)
+    per, padded = panel_pieces(S, 1, pieces)
+    assert per * pieces == padded >= S
+    d_panel = torch.full((padded, Wh), -1, dtype=torch.int32)
+    eng = _RecordingEngine()
+    replicate_panel(eng, h_bits, d_panel, n_indiv=40, pieces=pieces)
+    assert torch.equal(d_panel[:S], h_bits)
+    ready = [c[1] for c in eng.calls[1:]]
+    assert eng.calls[0] == ("set", S, 40, Wh) and ready == sorted(ready) and ready[-1] == S
+    with pytest.raises(ValueError):
+        replicate_panel(eng, h_bits, d_panel[: max(S - 1, 0)], n_indiv=40, pieces=pieces)
