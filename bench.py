@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sites", type=int, default=10_000, help="site sample for the CPU baseline")
     ap.add_argument("--cpu-targets", type=int, default=16, help="targets of the single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the secondary legs (C2, C4, -v, flat rows, CLI, int8 peak)")
     ap.add_argument("--force-general", action="store_true", help="A/B: CUDA-core --LD path")
     ap.add_argument("--panel-pieces", type=int, default=int(os.environ.get("IBDGEM_BENCH_PANEL_PIECES", "-1")),
                     help="N>1: the panel is replicated over NVLink in this many pieces (0 = every rank uploads all "
@@ -79,18 +80,19 @@ def write_reference_sample(dirpath, bits_np, H, n_ref, n_alt, pos, n_sites):
             fh.write("20\t%d\tN\t%d\t%s\t%s\t%s\n" % (int(pos[i]), c, b or "*", "I" * c or "*", "]" * c or "*"))
 
 
-def run_reference_procs(binary, dirpath, target_lists, window):
+def run_reference_procs(binary, dirpath, target_lists, window, ld=True, tag="out"):
     """One process per target list (the reference is single-threaded; independent processes
     sharded with -S are how it uses more than one core).  Returns wall seconds."""
     procs = []
     for k, tl in enumerate(target_lists):
         with open(os.path.join(dirpath, "targets_%d.txt" % k), "w") as fh:
             fh.write("".join("i%d\n" % t for t in tl))
-        os.makedirs(os.path.join(dirpath, "out_%d" % k), exist_ok=True)
+        os.makedirs(os.path.join(dirpath, "%s_%d" % (tag, k)), exist_ok=True)
     t0 = time.perf_counter()
     for k, tl in enumerate(target_lists):
-        procs.append(subprocess.Popen([binary, "-H", "p.hap", "-L", "p.legend", "-I", "p.indv", "-P", "u.pileup",
-                                       "--LD", "-w", str(window), "-S", "targets_%d.txt" % k, "-O", "out_%d" % k],
+        procs.append(subprocess.Popen([binary, "-H", "p.hap", "-L", "p.legend", "-I", "p.indv", "-P", "u.pileup"] +
+                                      (["--LD"] if ld else []) + ["-w", str(window), "-S", "targets_%d.txt" % k,
+                                                                  "-O", "%s_%d" % (tag, k)],
                                       cwd=dirpath, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
     for p in procs:
         if p.wait() != 0:
@@ -104,7 +106,7 @@ def host_sample(args, seed=1):
     return synth_panel_numpy(args.cpu_sites, args.samples, seed=seed)
 
 
-def cpu_baseline(args, sample=None, n_procs=1, targets_per_proc=None, tmp=None):
+def cpu_baseline(args, sample=None, n_procs=1, targets_per_proc=None, tmp=None, with_o2=False):
     """Times the reference's own CPU implementation of the path on a bounded sample: the first
     cpu_sites sites of the workload, targets_per_proc targets per process, full background."""
     d = sample if sample is not None else host_sample(args)
@@ -116,6 +118,7 @@ def cpu_baseline(args, sample=None, n_procs=1, targets_per_proc=None, tmp=None):
     own_tmp = tmp is None
     if own_tmp:
         tmp = tempfile.mkdtemp(prefix="ibdgem_cpu_")
+    extra = {}
     try:
         if os.path.exists(ref_bin):
             if not os.path.exists(os.path.join(tmp, "p.hap")):
@@ -125,6 +128,9 @@ def cpu_baseline(args, sample=None, n_procs=1, targets_per_proc=None, tmp=None):
             comps = n_procs * tpp * inf * (args.samples - 1) * 4
             kind = "reference"
             note = "oracle/_ref/ibdgem (unmodified reference, as-shipped flags -ggdb3 = -O0)"
+            if with_o2 and os.path.exists(ref_bin + ".O2"):  # state both builds
+                wall2 = run_reference_procs(ref_bin + ".O2", tmp, lists, args.window, tag="out_o2")
+                extra = {"value_O2": comps / wall2, "O2_note": "same sample, reference sources built with -O2: %.2f s wall" % wall2}
         else:
             import oracle
             from ibdgem_b200.synth import unpack_rows
@@ -140,9 +146,11 @@ def cpu_baseline(args, sample=None, n_procs=1, targets_per_proc=None, tmp=None):
     finally:
         if own_tmp:
             shutil.rmtree(tmp, ignore_errors=True)
-    return dict(value=comps / wall, unit=UNIT, cores=n_procs, kind=kind,
-                sample="%s; first %d sites x %d target(s) per process x %d process(es) x %d background, --LD -w %d, "
-                       "%.2f s wall" % (note, S1, tpp, n_procs, args.samples - 1, args.window, wall)), comps, wall
+    out = dict(value=comps / wall, unit=UNIT, cores=n_procs, kind=kind,
+               sample="%s; first %d sites x %d target(s) per process x %d process(es) x %d background, --LD -w %d, "
+                      "%.2f s wall" % (note, S1, tpp, n_procs, args.samples - 1, args.window, wall))
+    out.update(extra)
+    return out, comps, wall
 
 
 def reference_arm(args):
@@ -231,6 +239,48 @@ class ClockSampler:
         return out
 
 
+def aux_legs(args, torch, ib, eng, bits, pos, n_ref, n_alt, ref_tmp, ref_wall, peaks, achieved_tops):
+    """Secondary legs on one GPU (tools/bench_aux.py); a leg that fails is reported, not fatal."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_aux as ba
+    eng.close()  # the headline engine's operands (~8.5 GB) are not needed any more
+    torch.cuda.empty_cache()
+    S, N, T, W = args.sites, args.samples, args.targets, args.window
+    full = (S, N, T, W) == (1_000_000, 2504, 1000, 1000)
+    aux = {}
+
+    def leg(name, fn):
+        t0 = time.perf_counter()
+        try:
+            aux[name] = fn()
+        except Exception as ex:  # noqa: BLE001
+            aux[name] = {"failed": repr(ex)[:300]}
+        aux[name]["leg_wall_s"] = round(time.perf_counter() - t0, 2)
+
+    leg("int8_peak", lambda: ba.leg_int8_peak(torch))
+    if "burst_tops" in aux["int8_peak"]:
+        aux["int8_peak"]["ld_mma_frac_of_burst"] = achieved_tops / aux["int8_peak"]["burst_tops"]
+        aux["int8_peak"]["ld_mma_frac_of_sustained"] = achieved_tops / aux["int8_peak"]["sustained_tops"]
+    # C3 with the pileup's source outside the background: no row has a dominant column, ~6 % of the
+    # accumulator elements pass the screen (DESIGN.md 4.1) — the forensic common case
+    def flat():
+        r2, a2 = ba.make_counts(bits, N - 1, 3, 1)
+        return ba.leg_ld(torch, ib, bits, pos, r2, a2, N, T, W, args.steps, 0, np.arange(N - 1, dtype=np.int32),
+                         "C3 shape, reads drawn from individual %d, background = individuals 0..%d (source not in it)" % (N - 1, N - 2))
+    leg("flat_rows", flat)
+    # C3 with -v, the flag the reference recommends (README.md:180; src/ibdgem.c:584-587): per-target windows
+    leg("ld_v", lambda: ba.leg_ld(torch, ib, bits, pos, n_ref, n_alt, N, T, W, args.steps, 1, None,
+                                  "C3 shape with -v (variable sites only): per-target window maps"))
+    leg("c2", lambda: ba.leg_c2(torch, ib, bits, pos, N, args.steps, ref_tmp, args.cpu_sites))
+    if full:
+        leg("c4", lambda: ba.leg_c4(torch, ib, 3, 10_000, 10_000, ref_tmp))
+    else:
+        leg("c4", lambda: ba.leg_c4(torch, ib, 3, 500, 2_000, ref_tmp))
+    if ref_wall is not None:
+        leg("cli_e2e", lambda: ba.leg_cli(ref_tmp, W, ref_wall, args.cpu_targets))
+    return aux
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -257,7 +307,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # (NCCL_DEBUG is left to the caller: fd 1 already points at stderr, so INFO lines cannot reach the JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     S, N, T, W = args.sites, args.samples, args.targets, args.window
@@ -421,7 +471,9 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3 --LD scoring: %d sites x %d-sample phased panel, %d targets per GPU, "
-                                   "window %d, depth Poisson(2)+1 (BASELINE.json configs[2])" % (S, N, T, W),
+                                   "window %d, depth Poisson(2)+1 (BASELINE.json configs[2]); the pileup's reads are drawn "
+                                   "from individual 0, who IS in the background (SURVEY.md 8d) — the other case is "
+                                   "aux.flat_rows" % (S, N, T, W),
                        "sites": S, "samples": N, "targets_per_gpu": T, "window": W,
                        "parallelism": "targets sharded across %d GPU(s), panel replicated%s, one all_gather of "
                                       "window scores" % (world, (" (e2e: each rank uploads 1/%d of it over PCIe, "
@@ -439,9 +491,21 @@ def main():
         }
         if rank_ms:
             out["ms_per_step_by_rank"] = rank_ms  # value uses the maximum
-        if world == 1 and not args.no_cpu_baseline:
-            cb, _, _ = cpu_baseline(args)
-            out["cpu_baseline"] = cb
+        ref_tmp = tempfile.mkdtemp(prefix="ibdgem_cpu_")
+        try:
+            ref_wall = None
+            if world == 1 and not args.no_cpu_baseline:
+                cb, _, ref_wall = cpu_baseline(args, tmp=ref_tmp, with_o2=True)
+                out["cpu_baseline"] = cb
+            if world == 1 and not args.no_aux:
+                out["aux"] = aux_legs(args, torch, ib, eng, bits, pos, n_ref, n_alt, ref_tmp, ref_wall, peaks, achieved)
+                i8 = out["aux"].get("int8_peak", {})
+                if "burst_tops" in i8:  # the int8 tensor peak measured on THIS box, next to the 2 x bf16 inference
+                    roofline["int8_peak_measured_here"] = {"burst": i8["burst_tops"], "sustained": i8["sustained_tops"], "unit": "TOP/s"}
+                    roofline["frac_of_int8_burst"] = achieved / i8["burst_tops"]
+                    roofline["frac_of_int8_sustained"] = achieved / i8["sustained_tops"]
+        finally:
+            shutil.rmtree(ref_tmp, ignore_errors=True)
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
         print(json.dumps(out), flush=True)

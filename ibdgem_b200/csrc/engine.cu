@@ -244,6 +244,7 @@ site_status_kernel(int64_t S, const uint8_t *__restrict__ hostkeep, const uint8_
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITERS = 8;
 constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITERS;
+constexpr int ROW_SLICE = 32768;  // target rows per launch where they ride on gridDim.y
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_count_kernel(SiteView v, const int32_t *__restrict__ targets, uint32_t *__restrict__ blockcnt,
@@ -1019,14 +1020,17 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
     // per-range launches (a dozen per range) cost more than the shorter tail saves.  Tapered sizes
     // (IBDGEM_PANEL_TAPER < 1) measured no better: the scoring rate is too close to the copy rate for
     // shrinking chunks to stay ahead.
-    static int want_chunks = 0;
-    static double taper = 1.0;  // each chunk is `taper` times the size of the one before it
-    if (!want_chunks) {
-        const char *sc = getenv("IBDGEM_PANEL_CHUNKS"), *st = getenv("IBDGEM_PANEL_TAPER");
-        want_chunks = sc ? std::max(1, atoi(sc)) : PANEL_CHUNKS;
-        taper = st ? atof(st) : PANEL_TAPER;
-        if (!(taper > 0.1 && taper <= 1.0)) taper = 1.0;
-    }
+    // read once (C++11 static initialisers are thread-safe: `ibdgem --gpus N` calls this from one host
+    // thread per device)
+    static const int want_chunks = [] {
+        const char *sc = getenv("IBDGEM_PANEL_CHUNKS");
+        return sc ? std::max(1, atoi(sc)) : PANEL_CHUNKS;
+    }();
+    static const double taper = [] {  // each chunk is `taper` times the size of the one before it
+        const char *st = getenv("IBDGEM_PANEL_TAPER");
+        const double t = st ? atof(st) : PANEL_TAPER;
+        return (t > 0.1 && t <= 1.0) ? t : 1.0;
+    }();
     const size_t panel_bytes = (size_t)n_sites * (size_t)words_per_site * 4;
     const int nchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)want_chunks, panel_bytes / PANEL_CHUNK_MIN_BYTES));
     while ((int)e->chunk_ev.size() < nchunk) {
@@ -1143,18 +1147,27 @@ static int build_window_map(ibdgem_engine *e, const SiteView &v, const int32_t *
     const int nb = (int)((e->S + SCAN_CHUNK - 1) / SCAN_CHUNK);
     uint32_t *d_cnt;
     if (scratch(e, SC_BLOCKCNT, (size_t)rows * nb * 4, (void **)&d_cnt)) return 1;
-    {
-        LaunchScope ls(e, K_SCAN_COUNT);
-        scan_count_kernel<<<dim3(nb, rows), SCAN_THREADS, 0, e->stream>>>(v, d_targets, d_cnt, nb);
-    }
-    {
-        LaunchScope ls(e, K_SCAN_OFFSETS);
-        scan_offsets_kernel<<<rows, 256, 0, e->stream>>>(d_cnt, nb, e->prm.window_size, d_ktot, d_nwin);
-    }
-    {
-        LaunchScope ls(e, K_SCAN_RANK);
-        scan_rank_kernel<<<dim3(nb, rows), SCAN_THREADS, 0, e->stream>>>(
-            v, d_targets, d_cnt, nb, e->prm.window_size, d_ktot, d_wfirst, d_wlast, maxW, d_rank);
+    // rows ride on gridDim.y (limit 65,535): slices of ROW_SLICE rows
+    for (int r0 = 0; r0 < rows; r0 += ROW_SLICE) {
+        const int rc = std::min(ROW_SLICE, rows - r0);
+        SiteView vv = v;
+        if (vv.tgt_counts) vv.tgt_counts += (size_t)r0 * e->S * 2;
+        const int32_t *tg = d_targets ? d_targets + r0 : nullptr;
+        uint32_t *cnt = d_cnt + (size_t)r0 * nb;
+        {
+            LaunchScope ls(e, K_SCAN_COUNT);
+            scan_count_kernel<<<dim3(nb, rc), SCAN_THREADS, 0, e->stream>>>(vv, tg, cnt, nb);
+        }
+        {
+            LaunchScope ls(e, K_SCAN_OFFSETS);
+            scan_offsets_kernel<<<rc, 256, 0, e->stream>>>(cnt, nb, e->prm.window_size, d_ktot + r0, d_nwin + r0);
+        }
+        {
+            LaunchScope ls(e, K_SCAN_RANK);
+            scan_rank_kernel<<<dim3(nb, rc), SCAN_THREADS, 0, e->stream>>>(
+                vv, tg, cnt, nb, e->prm.window_size, d_ktot + r0, d_wfirst + (size_t)r0 * maxW, d_wlast + (size_t)r0 * maxW, maxW,
+                d_rank);
+        }
     }
     IBD_CUDA(cudaGetLastError());
     return 0;
@@ -1298,6 +1311,10 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
             scratch(e, SC_NWIN, (size_t)std::max(T, 1) * 4, (void **)&d_nwin) ||
             scratch(e, SC_KTOT, (size_t)std::max(T, 1) * 8, (void **)&d_ktot))
             return 1;
+        // -v ranks sites by the target's genotype, i.e. reads panel rows: the engine stream must depend on
+        // every panel chunk (and the per-site table) BEFORE the map is built, not only before the scoring
+        // kernels — a lazily prepared engine has so far only looked at the site arrays
+        if (ensure_table(e, S)) return 1;
         if (build_window_map(e, v, d_targets, T, mapW, d_wf, d_wl, d_nwin, d_ktot, nullptr)) return 1;
         m.wfirst = d_wf;
         m.wlast = d_wl;
@@ -1405,8 +1422,13 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         if (scratch(e, SC_COUNTERS, (size_t)crows * crow * 8, (void **)&d_cnt)) return 1;
         IBD_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)crows * crow * 8, e->stream));
         LaunchScope ls(e, K_COUNTERS);
-        counters_kernel<<<dim3((unsigned)((S + COUNTERS_CHUNK - 1) / COUNTERS_CHUNK), crows), 256, (size_t)crow * 8, e->stream>>>(
-            v, shared ? nullptr : d_targets, C, d_cnt);
+        for (int r0 = 0; r0 < crows; r0 += ROW_SLICE) {
+            const int rc = std::min(ROW_SLICE, crows - r0);
+            SiteView vv = v;
+            if (vv.tgt_counts) vv.tgt_counts += (size_t)r0 * S * 2;
+            counters_kernel<<<dim3((unsigned)((S + COUNTERS_CHUNK - 1) / COUNTERS_CHUNK), rc), 256, (size_t)crow * 8, e->stream>>>(
+                vv, shared ? nullptr : d_targets + r0, C, d_cnt + (size_t)r0 * crow);
+        }
     }
     // expanded per-site outputs
     uint8_t *d_st = nullptr;

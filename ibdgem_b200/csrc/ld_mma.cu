@@ -1158,12 +1158,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
+    static const EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+            return (EncodeTiledFn) nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
     return fn;
 }
 
@@ -1212,11 +1213,10 @@ static int launch_mma_cfg(int n_units, int sm_count, cudaStream_t st, const CUte
 // IBDGEM_MMA_VARIANT: 2 = CTA pairs (cta_group::2, 256 x 256 tiles; default), 1 = single CTA
 // (128 x 128 tiles; shared-memory bound, kept for A/B measurement)
 static int mma_variant() {
-    static int v = -1;
-    if (v < 0) {
+    static const int v = [] {
         const char *s = getenv("IBDGEM_MMA_VARIANT");
-        v = s ? atoi(s) : 2;
-    }
+        return s ? atoi(s) : 2;
+    }();
     return v;
 }
 static int mma_cg(int variant) { return variant == 1 ? 1 : 2; }
@@ -1230,12 +1230,11 @@ static int launch_mma(int variant, int n_units, int sm_count, cudaStream_t st, c
 // row's log-sum-exp by less than ncols * e^-D.  D = ln(ncols) + ln(1e7) keeps that below 1e-7 (the
 // window tolerance is 1e-6); IBDGEM_SCREEN_NATS overrides it.
 static double screen_nats(int ncols) {
-    static double forced = -1;
-    if (forced < 0) {
+    static const double forced = [] {  // validated before it is published
         const char *s = getenv("IBDGEM_SCREEN_NATS");
-        forced = s ? atof(s) : 0.0;
-        if (!(forced >= 8.0 && forced <= 700.0)) forced = 0.0;
-    }
+        const double f = s ? atof(s) : 0.0;
+        return (f >= 8.0 && f <= 700.0) ? f : 0.0;
+    }();
     if (forced > 0.0) return forced;
     return std::min(SCREEN_NATS, log((double)std::max(ncols, 2)) + 16.2);
 }
@@ -1391,8 +1390,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         // first range's columns of the score table travel to the host while the second is scored; measured
         // at C3 it buys nothing (8.70 ms one range, 8.68 ms d = 8, 8.78 ms d = 5: a second round of launches
         // costs what the hidden 0.4 ms copy saves), so it is off by default.
-        static int tail_div = -1;
-        if (tail_div < 0) { const char *st = getenv("IBDGEM_LD_TAIL_DIV"); tail_div = st ? atoi(st) : 0; }
+        static const int tail_div = [] { const char *st = getenv("IBDGEM_LD_TAIL_DIV"); return st ? atoi(st) : 0; }();
         if (e->h_wll_out && tail_div > 1 && nW >= 8 * tail_div) range_end.push_back(nW - nW / tail_div);
         range_end.push_back(nW);
     }
@@ -1427,11 +1425,11 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     const int MB = (nrows + mma::BM * CG - 1) / (mma::BM * CG);
 
     const size_t per_window = (size_t)(ncols + nrows) * c->Wpad;
-    static size_t budget = 0;
-    if (!budget) {  // IBDGEM_LD_BUDGET_MB: operand budget override (tests exercise the window batching with it)
+    // IBDGEM_LD_BUDGET_MB: operand budget override (tests exercise the window batching with it)
+    static const size_t budget = [] {
         const char *sb = getenv("IBDGEM_LD_BUDGET_MB");
-        budget = sb && atol(sb) > 0 ? (size_t)atol(sb) << 20 : LD_OPERAND_BUDGET;
-    }
+        return sb && atol(sb) > 0 ? (size_t)atol(sb) << 20 : LD_OPERAND_BUDGET;
+    }();
     const int nWb = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nW, budget / per_window, (size_t)MAX_GRID_Y}));
     int32_t *d_bgU, *d_ownU, *d_rowown, *d_akey;
     double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp, *d_Rt;
@@ -1525,13 +1523,11 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.row_own = d_rowown;
         p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
         {
-            static int dbg = -1;
-            if (dbg < 0) { const char *sdbg = getenv("IBDGEM_MMA_DEBUG"); dbg = sdbg ? atoi(sdbg) : 0; }
+            static const int dbg = [] { const char *sdbg = getenv("IBDGEM_MMA_DEBUG"); return sdbg ? atoi(sdbg) : 0; }();
             p.debug = dbg;
         }
         {
-            static int wt = -1;
-            if (wt < 0) { const char *sw = getenv("IBDGEM_MMA_WARM_TILES"); wt = sw ? atoi(sw) : 1; }
+            static const int wt = [] { const char *sw = getenv("IBDGEM_MMA_WARM_TILES"); return sw ? atoi(sw) : 1; }();
             p.warm_tiles = wt;
         }
         {
@@ -1539,8 +1535,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             if (scratch(e, SC_MMA_UNIT, 64, (void **)&d_unit)) return 1;
             IBD_CUDA(cudaMemsetAsync(d_unit, 0, 4, e->stream));
             p.unit_counter = d_unit;
-            static int pf = -1;
-            if (pf < 0) { const char *spf = getenv("IBDGEM_MMA_PF"); pf = spf ? atoi(spf) : mma::PF_TILES; }
+            static const int pf = [] { const char *spf = getenv("IBDGEM_MMA_PF"); return spf ? atoi(spf) : mma::PF_TILES; }();
             p.pf_tiles = pf;
         }
         p.trace = nullptr;

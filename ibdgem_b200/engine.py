@@ -186,6 +186,10 @@ class Engine:
                                                      C.c_int32(len(bg)), _ptr(bg), C.c_int32(pu_idx), None,
                                                      C.byref(cs)))
 
+    def score_nonld_raw(self, targets: np.ndarray, cs: "_CScores"):
+        self._check(self._lib.ibdgem_engine_score_nonld(self._h, C.c_int32(len(targets)), _ptr(targets), None,
+                                                        C.byref(cs)))
+
     def force_general_ld(self, on: bool):
         self._check(self._lib.ibdgem_engine_force_general_ld(self._h, C.c_int(1 if on else 0)))
 
@@ -206,6 +210,15 @@ class Engine:
                                                       C.c_double(p02), C.c_double(p12), _ptr(state), _ptr(score),
                                                       _ptr(counts)))
         return state, score, counts
+
+    def viterbi_batch_raw(self, lik_ptr: int, bin_offsets: np.ndarray, is_log: bool, state_ptr: int, score_ptr: int,
+                          counts_ptr: int, p01=1e-3, p02=1e-6, p12=1e-3):
+        """Caller-owned HOST buffers by address (pinned for asynchronous copies)."""
+        off = np.ascontiguousarray(bin_offsets, np.int64)
+        self._check(self._lib.hiddengem_viterbi_batch(self._h, C.c_int32(len(off) - 1), _ptr(off), C.c_void_p(lik_ptr),
+                                                      C.c_int32(1 if is_log else 0), C.c_double(p01), C.c_double(p02),
+                                                      C.c_double(p12), C.c_void_p(state_ptr), C.c_void_p(score_ptr),
+                                                      C.c_void_p(counts_ptr)))
 
     # -- instrumentation --------------------------------------------------------------------
     def enable_timing(self, on=True):
