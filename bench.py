@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-targets", type=int, default=16, help="targets of the single-core CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the secondary legs (C2, C4, -v, flat rows, CLI, int8 peak)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 leg (10k targets x 5k background, 15k-individual panel)")
     ap.add_argument("--force-general", action="store_true", help="A/B: CUDA-core --LD path")
     ap.add_argument("--panel-pieces", type=int, default=int(os.environ.get("IBDGEM_BENCH_PANEL_PIECES", "-1")),
                     help="N>1: the panel is replicated over NVLink in this many pieces (0 = every rank uploads all "
@@ -337,9 +338,22 @@ def main():
     o_ws, o_we = pinned((T, maxW), torch.int64), pinned((T, maxW), torch.int64)
     o_wn = pinned((T, maxW), torch.int32)
     o_ll = pinned((T, maxW, 3), torch.float64)
-    d_ll = torch.empty((T, maxW, 3), dtype=torch.float64, device=dev)
+    # The gathered score table [world * T][maxW][3] lives in rank 0's HBM and is mapped into every rank (CUDA
+    # IPC): each rank's engine stores its own block there, window range by window range, over NVLink — the
+    # gather needs no collective call and no rendezvous inside the step.  Fallback (IPC unavailable): one
+    # NCCL all_gather per step, as in round 1.
+    from ibdgem_b200.shard import PeerTable
+    table = PeerTable(world * T, maxW, local_rank)
+    d_ll = None
+    if table.ok:
+        if table.is_root:
+            table.tensor().fill_(float("nan"))
+        dst = table.block_ptr(rank * T)
+    else:
+        d_ll = torch.empty((T, maxW, 3), dtype=torch.float64, device=dev)
+        dst = d_ll.data_ptr()
     cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr(), o_we.data_ptr(), o_wn.data_ptr(), o_ll.data_ptr(),
-                  None, None, None, None, None, None, d_ll.data_ptr())
+                  None, None, None, None, None, None, dst)
 
     # N > 1: the packed panel is the same on every rank, so each rank copies 1/N of it over PCIe and the
     # ranks all_gather the pieces over NVLink (shard.replicate_panel) instead of N full uploads
@@ -366,9 +380,9 @@ def main():
         # invalidate() discards every derived device array of the previous step (nothing is cached
         # across steps except the allocations).
         eng.invalidate()
-        eng.score_ld_raw(targets, bg, -1, cs)
-        if world > 1:
-            gather_window_scores(d_ll, world * T)  # one NCCL all_gather of [T][maxW][3] fp64 per rank
+        eng.score_ld_raw(targets, bg, -1, cs)  # includes the store of this rank's block into the root's table
+        if world > 1 and d_ll is not None:
+            gather_window_scores(d_ll, world * T)  # fallback: one NCCL all_gather of [T][maxW][3] fp64 per rank
 
     def barrier():
         if world > 1:
@@ -398,6 +412,15 @@ def main():
     eng.prepare()
     for _ in range(max(args.warmup, 3)):
         score()
+    gather_check = None
+    if world > 1 and table.ok:
+        # outside the timed region: the root's table must equal an NCCL all_gather of every rank's host results
+        barrier()
+        every = gather_window_scores(o_ll.to(dev), world * T)
+        if rank == 0:
+            gather_check = bool(torch.equal(torch.nan_to_num(every, nan=-1.0), torch.nan_to_num(table.tensor(), nan=-1.0)))
+        del every
+        barrier()
     eng.reset_stats()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_total = timed(score, args.steps)
@@ -422,6 +445,40 @@ def main():
     h2d = (bits.nbytes // world if replicate else bits.nbytes) + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes
     d2h = o_nw.numel() * 4 + o_ws.numel() * 8 * 2 + o_wn.numel() * 4 + o_ll.numel() * 8
     e2e_value = comps_rank * world / (ms_e2e * 1e-3)
+
+    # ---- partition by windows: strong scaling of C3, and C5 (all ranks take part) -----------------
+    multi = {}
+    dev_bytes = eng.device_bytes()
+    if not args.no_aux:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_aux as ba
+        eng.close()
+        table.close()
+        torch.cuda.empty_cache()
+
+        def mleg(name, fn):
+            t0 = time.perf_counter()
+            try:
+                r = fn()
+            except Exception as ex:  # noqa: BLE001
+                r = {"failed": repr(ex)[:300]}
+            if rank == 0 and r is not None:
+                r["leg_wall_s"] = round(time.perf_counter() - t0, 2)
+                multi[name] = r
+
+        if world > 1:
+            mleg("strong_c3", lambda: ba.leg_window_sharded(
+                torch, ib, world, rank, d["bits"], pos, n_ref, n_alt, N, np.arange(T, dtype=np.int32), bg, W, args.steps,
+                "C3 in full on %d GPU(s): %d sites x %d-sample panel, %d targets in total, window %d" % (world, S, N, T, W)))
+        if (S, N, W) == (1_000_000, 2504, 1000) and not args.no_c5:
+            def c5():
+                d5 = ba.c5_inputs(torch, S, 15_000)
+                return ba.leg_window_sharded(
+                    torch, ib, world, rank, d5["bits"], d5["pos"].numpy().view(np.uint64), d5["n_ref"].numpy(), d5["n_alt"].numpy(),
+                    15_000, np.arange(10_000, dtype=np.int32), np.arange(10_000, 15_000, dtype=np.int32), W, max(2, min(args.steps, 3)),
+                    "C5 (BASELINE.json configs[4]): %d sites x 15,000-individual panel, 10,000 targets x 5,000 disjoint "
+                    "background individuals, window %d, reads drawn from background individual 10,000" % (S, W))
+            mleg("c5", c5)
 
     if rank == 0:
         launches = int(sum(n for _, n in stats.values()))
@@ -475,13 +532,13 @@ def main():
                                    "from individual 0, who IS in the background (SURVEY.md 8d) — the other case is "
                                    "aux.flat_rows" % (S, N, T, W),
                        "sites": S, "samples": N, "targets_per_gpu": T, "window": W,
-                       "parallelism": "targets sharded across %d GPU(s), panel replicated%s, one all_gather of "
-                                      "window scores" % (world, (" (e2e: each rank uploads 1/%d of it over PCIe, "
+                       "parallelism": "targets sharded across %d GPU(s), panel replicated%s, window scores gathered into "
+                                      "rank 0's HBM by peer stores over NVLink" % (world, (" (e2e: each rank uploads 1/%d of it over PCIe, "
                                                                  "%d all_gather pieces over NVLink)" % (world, args.panel_pieces))
                                                          if replicate else ""),
                        "ld_path": "tensor (tcgen05 int8 window GEMM + fused LSE)" if ld_path == 1 else "general CUDA-core",
                        "l2": "inputs larger than L2 (packed panel %.0f MB, operands %.1f GB)" % (
-                           bits.nbytes / 1e6, eng.device_bytes() / 1e9)},
+                           bits.nbytes / 1e6, dev_bytes / 1e9)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "bytes_are": "per rank",
@@ -491,6 +548,14 @@ def main():
         }
         if rank_ms:
             out["ms_per_step_by_rank"] = rank_ms  # value uses the maximum
+        if world > 1:
+            out["gather"] = {"how": ("every rank stores its [T][maxW][3] fp64 block into rank 0's HBM over NVLink (CUDA IPC "
+                                     "mapping, cudaMemcpy2DAsync per window range from inside the score call); no collective, "
+                                     "no rendezvous inside the step") if table.ok or gather_check is not None else
+                                    "fallback: one NCCL all_gather_into_tensor per step",
+                             "bytes_per_rank": int(T * (S // W) * 24), "equals_nccl_all_gather": gather_check}
+        if multi:
+            out.setdefault("aux", {}).update(multi)
         ref_tmp = tempfile.mkdtemp(prefix="ibdgem_cpu_")
         try:
             ref_wall = None
@@ -498,7 +563,8 @@ def main():
                 cb, _, ref_wall = cpu_baseline(args, tmp=ref_tmp, with_o2=True)
                 out["cpu_baseline"] = cb
             if world == 1 and not args.no_aux:
-                out["aux"] = aux_legs(args, torch, ib, eng, bits, pos, n_ref, n_alt, ref_tmp, ref_wall, peaks, achieved)
+                out.setdefault("aux", {}).update(
+                    aux_legs(args, torch, ib, eng, bits, pos, n_ref, n_alt, ref_tmp, ref_wall, peaks, achieved))
                 i8 = out["aux"].get("int8_peak", {})
                 if "burst_tops" in i8:  # the int8 tensor peak measured on THIS box, next to the 2 x bf16 inference
                     roofline["int8_peak_measured_here"] = {"burst": i8["burst_tops"], "sustained": i8["sustained_tops"], "unit": "TOP/s"}
@@ -511,6 +577,7 @@ def main():
         print(json.dumps(out), flush=True)
         os.dup2(2, 1)
     eng.close()
+    table.close()
     if world > 1:
         dist.destroy_process_group()
 

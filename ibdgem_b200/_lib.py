@@ -18,6 +18,8 @@ ABI_SYMBOLS = [
     "ibdgem_engine_score_ld", "ibdgem_engine_last_ld_path", "ibdgem_engine_force_general_ld",
     "hiddengem_viterbi_batch", "ibdgem_engine_enable_timing", "ibdgem_engine_reset_stats",
     "ibdgem_engine_num_kernels", "ibdgem_engine_kernel_stats", "ibdgem_engine_device_bytes",
+    "ibdgem_engine_set_window_shard", "ibdgem_engine_window_shard", "ibdgem_peer_alloc", "ibdgem_peer_open",
+    "ibdgem_peer_close",
 ]
 
 

@@ -742,6 +742,16 @@ int ensure_table(ibdgem_engine *e, int64_t s_end) {
     return 0;
 }
 
+void window_shard_bounds(const ibdgem_engine *e, int32_t *w_begin, int32_t *w_end, int64_t *s_begin, int64_t *s_end) {
+    const int64_t nW = e->nW_shared;
+    const int32_t wb = (int32_t)(nW * e->shard_index / e->shard_count), we = (int32_t)(nW * (e->shard_index + 1) / e->shard_count);
+    if (w_begin) *w_begin = wb;
+    if (w_end) *w_end = we;
+    // rows between two windows (uninformative sites) go with the later shard; the last shard runs to the end
+    if (s_begin) *s_begin = wb > 0 && wb <= (int32_t)e->h_wlast.size() ? e->h_wlast[(size_t)wb - 1] + 1 : 0;
+    if (s_end) *s_end = (e->shard_index + 1 >= e->shard_count || we <= 0 || we > (int32_t)e->h_wlast.size()) ? e->S : e->h_wlast[(size_t)we - 1] + 1;
+}
+
 }  // namespace ibdgem
 
 using namespace ibdgem;
@@ -1058,7 +1068,7 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
     e->chunks_waited = 0;
     e->have_panel = true;
     e->prepared = false;
-    e->table_upto = 0;
+    e->table_from = e->table_upto = 0;
     ld_tensor_invalidate(e);
     return 0;
 }
@@ -1093,7 +1103,7 @@ int ibdgem_engine_set_panel_device(ibdgem_engine *e, int64_t n_sites, int32_t n_
     e->chunks_waited = 0;
     e->have_panel = true;
     e->prepared = false;
-    e->table_upto = 0;
+    e->table_from = e->table_upto = 0;
     ld_tensor_invalidate(e);
     return 0;
 }
@@ -1191,7 +1201,7 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
             dev_alloc(e, (void **)&e->d_nwin_shared, 4) || dev_alloc(e, (void **)&e->d_ktot_shared, 8))
             return 1;
     }
-    e->table_upto = 0;
+    e->table_from = e->table_upto = 0;
     // With no -A table and the default AF range the filter verdicts do not depend on the panel:
     // the window map is built from the site arrays at once, and the per-site table (which reads the
     // panel) is evaluated chunk by chunk as the rows arrive (ensure_table).
@@ -1222,6 +1232,12 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     e->nW_shared = nwin;
     e->K_shared = ktot;
     e->h_wlast.assign(h_map + 2, h_map + 2 + std::max(nwin, 0));
+    e->table_from = 0;
+    if (e->shard_count > 1 && e->lazy_table) {  // a window shard evaluates the per-site table of its own rows only
+        int64_t sb = 0;
+        window_shard_bounds(e, nullptr, nullptr, &sb, nullptr);
+        e->table_from = e->table_upto = sb;
+    }
     e->prepared = true;
     ld_tensor_invalidate(e);
     resolve_timers(e);
@@ -1231,14 +1247,19 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
 int ibdgem_engine_invalidate(ibdgem_engine *e) {
     if (!e) return 1;
     e->prepared = false;
-    e->table_upto = 0;
+    e->table_from = e->table_upto = 0;
     ld_tensor_invalidate(e);
     return 0;
 }
 
 int ibdgem_engine_get_site_table(ibdgem_engine *e, double *f, uint8_t *status, double *lik7) {
     if (!e) return 1;
-    if (ibdgem_engine_prepare(e) || ensure_table(e, e->S)) return 1;
+    if (ibdgem_engine_prepare(e)) return 1;
+    if (e->table_from > 0) {  // a window shard skipped the rows before its own: the whole table is wanted now
+        e->table_from = 0;
+        e->table_from = e->table_upto = 0;
+    }
+    if (ensure_table(e, e->S)) return 1;
     IBD_CUDA(cudaSetDevice(e->device));
     if (f) IBD_CUDA(cudaMemcpyAsync(f, e->d_f, (size_t)e->S * 8, cudaMemcpyDeviceToHost, e->stream));
     if (status) IBD_CUDA(cudaMemcpyAsync(status, e->d_status, (size_t)e->S, cudaMemcpyDeviceToHost, e->stream));
@@ -1348,9 +1369,18 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     if (tensor && !e->ev_book) IBD_CUDA(cudaEventCreateWithFlags(&e->ev_book, cudaEventDisableTiming));
     // everything but the tensor path reads the per-site table and the whole panel up front; the
     // tensor path asks for them window range by window range (upload / scoring overlap)
-    if (!tensor && ensure_table(e, S)) return 1;
+    if (!tensor) {
+        if (e->shard_count > 1) {
+            set_error("[::] ERROR: a window shard (ibdgem_engine_set_window_shard) needs the shared-window tensor --LD path; "
+                      "shard the target list instead for non-LD, -v and -D runs.");
+            return 1;
+        }
+        if (ensure_table(e, S)) return 1;
+    }
     e->wll_streamed = false;
+    e->wll_dev_streamed = false;
     e->h_wll_out = out->w_loglik;
+    e->d_wll_out_device = static_cast<double *>(out->w_loglik_device);
     if (tensor) {
         // tensor path: fills window bookkeeping, LIBD0, LIBD1 and LIBD2 of every target
         if (ld_tensor_score(e, T, targets, d_targets, n_bg, bg, pu_idx, outW, d_wll, d_wn, d_ws, d_we, d_nwout)) return 1;
@@ -1412,7 +1442,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         }
     }
 
-    if (ensure_table(e, S)) return 1;  // no-op unless the tensor path left a tail
+    if (e->shard_count == 1 && ensure_table(e, S)) return 1;  // no-op unless the tensor path left a tail
     // counters
     const bool want_counters = out->processed || out->skipped || out->final_total_cov || out->final_dist;
     unsigned long long *d_cnt = nullptr;
@@ -1443,8 +1473,8 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     IBD_CUDA(cudaGetLastError());
 
     // results -> host
-    if (out->w_loglik_device)
-        IBD_CUDA(cudaMemcpyAsync(out->w_loglik_device, d_wll, nWT * 24, cudaMemcpyDeviceToDevice, e->stream));
+    if (out->w_loglik_device && !e->wll_dev_streamed)
+        IBD_CUDA(cudaMemcpyAsync(out->w_loglik_device, d_wll, nWT * 24, cudaMemcpyDefault, e->stream));
     if (out->w_loglik && !e->wll_streamed)
         IBD_CUDA(cudaMemcpyAsync(out->w_loglik, d_wll, nWT * 24, cudaMemcpyDeviceToHost, e->stream));
     if (e->t0_set) IBD_CUDA(cudaEventRecord(e->ev_wll, e->wll_streamed ? e->d2h_stream : e->stream));
@@ -1470,7 +1500,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     if (out->site_lik) IBD_CUDA(cudaMemcpyAsync(out->site_lik, d_sl, (size_t)T * S * 24, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
     if (e->book_ready) IBD_CUDA(cudaStreamSynchronize(e->copy_stream));
-    if (e->wll_streamed) IBD_CUDA(cudaStreamSynchronize(e->d2h_stream));
+    if (e->wll_streamed || e->wll_dev_streamed) IBD_CUDA(cudaStreamSynchronize(e->d2h_stream));
     e->book_ready = false;
     resolve_timers(e);
     if (e->t0_set) {
@@ -1513,6 +1543,71 @@ int ibdgem_engine_score_ld(ibdgem_engine *e, int32_t n_targets, const int32_t *t
                            const int32_t *bg, int32_t pu_idx, const uint8_t *tgt_counts,
                            ibdgem_scores *out) {
     return score_common(e, n_targets, targets, n_bg, bg, pu_idx, tgt_counts, out, true);
+}
+
+int ibdgem_engine_set_window_shard(ibdgem_engine *e, int32_t index, int32_t count) {
+    if (!e || count < 1 || index < 0 || index >= count) {
+        set_error("[::] ERROR in ibdgem_engine_set_window_shard(): need 0 <= index < count.");
+        return 1;
+    }
+    if (e->shard_index != index || e->shard_count != count) {
+        e->shard_index = index;
+        e->shard_count = count;
+        e->prepared = false;
+        e->table_from = e->table_upto = 0;
+        ld_tensor_invalidate(e);
+    }
+    return 0;
+}
+
+int ibdgem_engine_window_shard(ibdgem_engine *e, int32_t *w_begin, int32_t *w_end, int64_t *site_begin, int64_t *site_end) {
+    if (!e) return 1;
+    if (ibdgem_engine_prepare(e)) return 1;
+    window_shard_bounds(e, w_begin, w_end, site_begin, site_end);
+    return 0;
+}
+
+// Device buffers other processes of the node can write (CUDA IPC): the gather of window scores is a
+// plain device-to-device copy into the root's buffer over NVLink, issued by every rank's own engine
+// (ibdgem_scores.w_loglik_device), with no rendezvous between ranks inside the scoring loop.
+int ibdgem_peer_alloc(int32_t device, int64_t bytes, void **dptr, unsigned char *handle64) {
+    if (!dptr || !handle64 || bytes <= 0) {
+        set_error("[::] ERROR in ibdgem_peer_alloc(): bad arguments.");
+        return 1;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI passes IPC handles as 64 opaque bytes");
+    IBD_CUDA(cudaSetDevice(device));
+    IBD_CUDA(cudaMalloc(dptr, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t ce = cudaIpcGetMemHandle(&h, *dptr);
+    if (ce != cudaSuccess) {
+        cudaFree(*dptr);
+        *dptr = nullptr;
+        set_error("[::] ERROR in ibdgem_peer_alloc(): cudaIpcGetMemHandle: %s", cudaGetErrorString(ce));
+        return 1;
+    }
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int ibdgem_peer_open(int32_t device, const unsigned char *handle64, void **dptr) {
+    if (!dptr || !handle64) {
+        set_error("[::] ERROR in ibdgem_peer_open(): bad arguments.");
+        return 1;
+    }
+    IBD_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    IBD_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int ibdgem_peer_close(int32_t device, void *dptr, int32_t owner) {
+    if (!dptr) return 0;
+    IBD_CUDA(cudaSetDevice(device));
+    if (owner)
+        IBD_CUDA(cudaFree(dptr));
+    else
+        IBD_CUDA(cudaIpcCloseMemHandle(dptr));
+    return 0;
 }
 
 int ibdgem_engine_last_ld_path(ibdgem_engine *e) { return e ? e->last_ld_path : -1; }

@@ -108,7 +108,12 @@ struct ibdgem_engine {
     std::vector<cudaEvent_t> chunk_ev;       // one per chunk, recorded on copy_stream
     std::vector<int64_t> chunk_end;          // exclusive site end of each chunk
     int chunks_waited = 0;                   // chunks the engine stream already depends on
-    int64_t table_upto = 0;                  // site_table has run on [0, table_upto)
+    int64_t table_from = 0, table_upto = 0;  // site_table has run on [table_from, table_upto)
+    // Window shard (multi-GPU, shared windows): this engine scores windows [nW*index/count, nW*(index+1)/count)
+    // of every target and touches only the panel rows of those windows (ibdgem_engine_set_window_shard)
+    int32_t shard_index = 0, shard_count = 1;
+    double *d_wll_out_device = nullptr;      // the call's optional device destination (may be peer memory)
+    bool wll_dev_streamed = false;           // ld_tensor_score has already issued the copies to it
     bool lazy_table = false;                 // status does not need the panel (no -A, AF range [0, 1])
     std::vector<int64_t> h_wlast;            // host copy of the shared window map (last site per window)
 
@@ -192,5 +197,7 @@ constexpr int PANEL_CHUNKS = 16;         // upload / scoring pipeline depth
 constexpr double PANEL_TAPER = 1.0;       // chunk k is PANEL_TAPER^k of the first chunk
 constexpr size_t PANEL_CHUNK_MIN_BYTES = (size_t)16 << 20;  // ~0.3 ms of PCIe; smaller panels use fewer chunks
 void ld_tensor_invalidate(ibdgem_engine *e);
+// windows [w_begin, w_end) and panel rows [s_begin, s_end) of this engine's shard (everything when unsharded)
+void window_shard_bounds(const ibdgem_engine *e, int32_t *w_begin, int32_t *w_end, int64_t *s_begin, int64_t *s_end);
 
 }  // namespace ibdgem

@@ -493,7 +493,7 @@ ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K,
     if (j >= (int64_t)T * span) return;
     const int t = (int)(j / span), w = w_lo + (int)(j % span);
     const int64_t i = (int64_t)t * outW + w;
-    if (w == 0) nwout[t] = nW;
+    if (w == w_lo) nwout[t] = nW;
     if (w >= nW) return;
     const int64_t left = K - (int64_t)w * W;
     wn[i] = (int32_t)(left < W ? left : W);
@@ -1318,6 +1318,11 @@ static int build_cache(ibdgem_engine *e) {
 // wait for the panel rows of those windows (wait_panel_upto / ensure_table).
 static int cache_windows(ibdgem_engine *e, int w_hi) {
     LdCache *c = e->ld;
+    if (e->shard_count > 1 && c->tw_upto == 0) {  // a window shard never looks at the windows before its own
+        int32_t wb = 0;
+        window_shard_bounds(e, &wb, nullptr, nullptr, nullptr);
+        c->tw_upto = wb;
+    }
     if (c->tw_upto >= w_hi) return 0;
     {
         LaunchScope ls(e, K_LD_TRANSPOSE);
@@ -1394,8 +1399,17 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         if (e->h_wll_out && tail_div > 1 && nW >= 8 * tail_div) range_end.push_back(nW - nW / tail_div);
         range_end.push_back(nW);
     }
-    const bool by_chunk = in_flight && c->tw_upto == 0;
-    auto range_sites = [&](size_t k) { return by_chunk ? e->chunk_end[k] : e->S; };
+    bool by_chunk = in_flight && c->tw_upto == 0;
+    // a window shard scores its own windows only, as one range, and waits for (and tabulates) its own rows only
+    int32_t shard_wb = 0, shard_we = nW;
+    int64_t shard_se = e->S;
+    const bool sharded = e->shard_count > 1;
+    if (sharded) {
+        window_shard_bounds(e, &shard_wb, &shard_we, nullptr, &shard_se);
+        range_end.assign(1, shard_we);
+        by_chunk = false;
+    }
+    auto range_sites = [&](size_t k) { return by_chunk ? e->chunk_end[k] : shard_se; };
     const int nrows = 2 * T;
     if (nU == 0) {  // every background member excluded: LIBD0 = LIBD1 = 0/0 (d_wll is NaN-filled)
         double *d_Rt;
@@ -1469,12 +1483,16 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
                                                                static_cast<const uint32_t *>(h_misc), n);
     }
 
-    const bool stream_out = range_end.size() > 1 && e->h_wll_out != nullptr;
-    if (stream_out) {
+    const bool stream_out = (range_end.size() > 1 || sharded) && e->h_wll_out != nullptr;
+    // the optional device destination (the root's gather buffer, possibly peer memory over NVLink) is
+    // filled range by range too
+    const bool stream_dev = e->d_wll_out_device != nullptr;
+    if (stream_out || stream_dev) {
         if (!e->d2h_stream) IBD_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
-        e->wll_streamed = true;
+        e->wll_streamed = stream_out;
+        e->wll_dev_streamed = stream_dev;
     }
-    int w_lo = 0;
+    int w_lo = shard_wb;
     for (size_t rk = 0; rk < range_end.size(); rk++) {
     const int w_hi = range_end[rk];
     if (ensure_table(e, range_sites(rk))) return 1;  // waits for the chunk, evaluates its per-site table
@@ -1570,8 +1588,8 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         ld_ibd0_kernel<<<w_hi - w_lo, 256, q_smem, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
     }
-    if (stream_out) {
-        // the range's columns of d_wll [T][outW][3] are final: a strided copy to the host on its own stream
+    if (stream_out || stream_dev) {
+        // the range's columns of d_wll [T][outW][3] are final: strided copies on their own stream
         while (e->range_ev.size() <= rk) {
             cudaEvent_t ev;
             IBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1579,12 +1597,16 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         }
         IBD_CUDA(cudaEventRecord(e->range_ev[rk], e->stream));
         IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->range_ev[rk], 0));
-        IBD_CUDA(cudaMemcpy2DAsync(e->h_wll_out + (size_t)w_lo * 3, (size_t)outW * 24, d_wll + (size_t)w_lo * 3, (size_t)outW * 24,
-                                   (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDeviceToHost, e->d2h_stream));
+        if (stream_dev)
+            IBD_CUDA(cudaMemcpy2DAsync(e->d_wll_out_device + (size_t)w_lo * 3, (size_t)outW * 24, d_wll + (size_t)w_lo * 3,
+                                       (size_t)outW * 24, (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDefault, e->d2h_stream));
+        if (stream_out)
+            IBD_CUDA(cudaMemcpy2DAsync(e->h_wll_out + (size_t)w_lo * 3, (size_t)outW * 24, d_wll + (size_t)w_lo * 3, (size_t)outW * 24,
+                                       (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDeviceToHost, e->d2h_stream));
     }
     w_lo = w_hi;
     }  // window ranges
-    if (stream_out && outW > nW) {  // the unused columns nW .. outW-1 (NaN since the fill at the start of the call)
+    if (stream_out && outW > nW && !sharded) {  // the unused columns nW .. outW-1 (NaN since the fill at the start of the call)
         const size_t rk = range_end.size();
         while (e->range_ev.size() <= rk) {
             cudaEvent_t ev;

@@ -125,6 +125,16 @@ class Engine:
     def panel_rows_ready(self, row_end: int, stream: int = 0):
         self._check(self._lib.ibdgem_engine_panel_rows_ready(self._h, C.c_int64(row_end), C.c_void_p(stream or None)))
 
+    def set_window_shard(self, index: int, count: int):
+        """Multi-GPU partition by windows (shared window maps): see include/ibdgem_b200.h."""
+        self._check(self._lib.ibdgem_engine_set_window_shard(self._h, C.c_int32(index), C.c_int32(count)))
+
+    def window_shard(self):
+        """(w_begin, w_end, site_begin, site_end) of this engine's shard; prepares the window map."""
+        wb, we, sb, se = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()
+        self._check(self._lib.ibdgem_engine_window_shard(self._h, C.byref(wb), C.byref(we), C.byref(sb), C.byref(se)))
+        return wb.value, we.value, sb.value, se.value
+
     def sync_uploads(self):
         self._check(self._lib.ibdgem_engine_sync_uploads(self._h))
 

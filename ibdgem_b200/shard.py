@@ -24,6 +24,30 @@ def shard_targets(targets, world: int, rank: int) -> np.ndarray:
     return targets[lo:hi]
 
 
+def window_shard_bounds(n_windows: int, world: int, rank: int) -> tuple[int, int]:
+    """Windows [lo, hi) of rank `rank` under the partition by windows — the same arithmetic as
+    ibdgem_engine_set_window_shard (engine.cu window_shard_bounds)."""
+    return int(n_windows) * rank // world, int(n_windows) * (rank + 1) // world
+
+
+def gather_window_columns(local, group=None):
+    """Partition by windows, collective form (gloo / NCCL fallback of the peer-store gather): every rank
+    holds a full-size table [T, maxW, 3] in which only its own window columns are set (NaN elsewhere);
+    the ranks' tables are combined column-wise on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    out = parts[0].clone()
+    for p in parts[1:]:
+        out = torch.where(torch.isnan(out), p, out)
+    return out
+
+
 def gather_window_scores(local, n_targets_total: int, group=None):
     """all_gather of per-window scores.
 
@@ -97,6 +121,106 @@ def replicate_panel(engine, h_bits, d_panel, n_indiv: int, pieces: int = 1, stre
                 engine.panel_rows_ready(ready, stream.cuda_stream if (on_gpu and stream is not None) else 0)
             if ready >= S:
                 break
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of raw device memory (for torch.as_tensor)."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class PeerTable:
+    """The gathered window-score table [rows, maxW, 3] fp64 in the ROOT rank's HBM, mapped into every rank
+    of the node through CUDA IPC (ibdgem_peer_alloc / ibdgem_peer_open).  A rank hands `block_ptr(row0)`
+    (targets partition: its own block of rows) or `ptr` (window partition: every row, its own columns) to
+    the engine as ibdgem_scores.w_loglik_device; the engine's copies then ARE the gather — device to device
+    over NVLink, range by range, with no rendezvous between the ranks inside the scoring loop.
+
+    `ok` is False on every rank when any rank could not map the buffer (IPC unavailable in this
+    container): callers then fall back to gather_window_scores (one NCCL collective)."""
+
+    def __init__(self, rows: int, max_windows: int, device_index: int, group=None, root: int = 0):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from ._lib import load_library
+        self._lib = load_library()
+        self.shape = (int(rows), int(max_windows), 3)
+        self.nbytes = int(rows) * int(max_windows) * 24
+        self.device_index = device_index
+        self.root = root
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.is_root = self.rank == root
+        self.ptr = 0
+        handle = (C.c_ubyte * 64)()
+        good = 1
+        if self.is_root:
+            p = C.c_void_p()
+            if self._lib.ibdgem_peer_alloc(C.c_int32(device_index), C.c_int64(self.nbytes), C.byref(p), handle) != 0:
+                good = 0
+            else:
+                self.ptr = int(p.value)
+        if self.world > 1:
+            dev = torch.device("cuda", device_index)
+            t = torch.tensor(list(handle) + [good], dtype=torch.uint8, device=dev)
+            dist.broadcast(t, src=root, group=group)
+            good = int(t[64].item())
+            if good and not self.is_root:
+                h = (C.c_ubyte * 64)(*[int(x) for x in t[:64].tolist()])
+                p = C.c_void_p()
+                if self._lib.ibdgem_peer_open(C.c_int32(device_index), h, C.byref(p)) != 0:
+                    good = 0
+                else:
+                    self.ptr = int(p.value)
+            flag = torch.tensor([good], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            good = int(flag.item())
+        self.ok = bool(good)
+        if not self.ok:
+            self.close()
+
+    def block_ptr(self, row0: int) -> int:
+        return self.ptr + int(row0) * self.shape[1] * 24
+
+    def tensor(self):
+        """torch view of the table (root only)."""
+        import torch
+        if not (self.is_root and self.ptr):
+            raise RuntimeError("the gathered table lives on the root rank")
+        return torch.as_tensor(_DevArray(self.ptr, self.shape), device=torch.device("cuda", self.device_index))
+
+    def close(self):
+        import ctypes as C
+        if self.ptr:
+            self._lib.ibdgem_peer_close(C.c_int32(self.device_index), C.c_void_p(self.ptr), C.c_int32(1 if self.is_root else 0))
+            self.ptr = 0
+
+
+def upload_window_shard_rows(engine, h_bits, d_panel, n_indiv: int, stream=None):
+    """Window partition, end to end: the rank's engine has a window shard set (Engine.set_window_shard) and
+    the site arrays uploaded; this hands it `d_panel` (torch int32 [S, Wh] device buffer) and copies from
+    the pinned host panel `h_bits` ONLY the rows the shard reads, so every panel byte crosses PCIe once
+    per node.  Returns the number of bytes copied."""
+    import torch
+    S, Wh = int(h_bits.shape[0]), int(h_bits.shape[1])
+    engine.set_panel_device(d_panel.data_ptr(), S, n_indiv, Wh)
+    prm = engine.params
+    needs_panel_first = prm.min_af > 0.0 or prm.max_af < 1.0 or getattr(engine, "_sites", (None,) * 5)[4] is not None
+    ctx = torch.cuda.stream(stream) if stream is not None else _null_ctx()
+    if needs_panel_first:  # an AF filter decides which sites are kept: the window map itself needs every row
+        with ctx:
+            d_panel[:S].copy_(h_bits, non_blocking=True)
+        engine.panel_rows_ready(S, stream.cuda_stream if stream is not None else 0)
+        return S * Wh * 4
+    _, _, sb, se = engine.window_shard()  # builds the window map from the site arrays (no panel rows needed)
+    with ctx:
+        if se > sb:
+            d_panel[sb:se].copy_(h_bits[sb:se], non_blocking=True)
+    engine.panel_rows_ready(S, stream.cuda_stream if stream is not None else 0)
+    return (se - sb) * Wh * 4
 
 
 class _null_ctx:

@@ -62,9 +62,11 @@ typedef struct ibdgem_scores {
     uint64_t *final_dist;      /* [T][C] "# FINAL COVERAGE DISTRIBUTION" */
     uint8_t *site_status;      /* [T][S]    optional expanded per-target site status */
     double *site_lik;          /* [T][S][3] optional expanded LIBD0, LIBD1, LIBD2 of each tab row (linear) */
-    void *w_loglik_device;     /* optional DEVICE pointer: [T][maxW][3] doubles are also written here
-                                  (rows past n_windows are NaN) for a following NCCL gather or the
-                                  device-resident hiddengem front-end */
+    void *w_loglik_device;     /* optional DEVICE pointer: [T][maxW][3] doubles are also written here, for the
+                                  device-resident hiddengem front-end or as this rank's block of a gathered
+                                  table in another GPU's memory (ibdgem_peer_open).  The tensor --LD path
+                                  writes columns [0, n_windows) of every row, range by range; the other
+                                  paths write whole rows (columns past n_windows are NaN). */
 } ibdgem_scores;
 
 /* ---- lifetime --------------------------------------------------------------------------- */
@@ -135,6 +137,33 @@ int ibdgem_engine_invalidate(ibdgem_engine *e);
  *   lik7[S][7] = { IBD0, IBD1|g=0, IBD1|g=1, IBD1|g=2, P(D|00), P(D|01), P(D|11) } — the tab.txt
  *   likelihood columns of target t at site i are lik7[i][0], lik7[i][1+g], lik7[i][4+g]. */
 int ibdgem_engine_get_site_table(ibdgem_engine *e, double *f, uint8_t *status, double *lik7);
+
+/* ---- multi-GPU ---------------------------------------------------------------------------- */
+
+/* Two partitions of a run across the GPUs of a node (both follow from the independence of
+ * targets, src/ibdgem.c:522, and of windows, :558-578):
+ *   - by TARGETS: every rank scores its own slice of the target list (any mode).  Nothing to set here:
+ *     pass the slice to score_*.
+ *   - by WINDOWS (shared window maps only: --LD on the tensor path, no -v / -D): rank `index` of `count`
+ *     scores windows [nW*index/count, nW*(index+1)/count) of EVERY target.  Everything a rank does then
+ *     scales with 1/count — including the panel rows it needs: only rows [site_begin, site_end) reported
+ *     by ibdgem_engine_window_shard() are read, so a rank may place just those rows in a device buffer
+ *     handed over with ibdgem_engine_set_panel_device (the rest of the buffer is never touched).
+ *     Score calls write only the shard's columns of w_loglik / w_loglik_device; the bookkeeping arrays
+ *     and n_windows describe all windows on every rank. */
+int ibdgem_engine_set_window_shard(ibdgem_engine *e, int32_t index, int32_t count);
+int ibdgem_engine_window_shard(ibdgem_engine *e, int32_t *w_begin, int32_t *w_end, int64_t *site_begin,
+                               int64_t *site_end); /* prepares the window map if necessary */
+
+/* Gather of per-window scores over NVLink without a rendezvous inside the scoring loop: the root
+ * allocates the gathered table with ibdgem_peer_alloc (cudaMalloc + a 64-byte CUDA IPC handle), the other
+ * ranks of the node map it with ibdgem_peer_open, and every rank passes its own block (or, for window
+ * shards, the table itself) as ibdgem_scores.w_loglik_device: the engine then stores each finished window
+ * range straight into the root's memory while later ranges are still being scored.  The handle travels
+ * between processes by any means (the Python mirror broadcasts it with torch.distributed). */
+int ibdgem_peer_alloc(int32_t device, int64_t bytes, void **dptr, unsigned char *handle64);
+int ibdgem_peer_open(int32_t device, const unsigned char *handle64, void **dptr);
+int ibdgem_peer_close(int32_t device, void *dptr, int32_t owner);
 
 /* ---- scoring ----------------------------------------------------------------------------- */
 

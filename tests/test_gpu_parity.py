@@ -442,3 +442,56 @@ def test_variable_sites_scored_while_the_pinned_panel_is_still_arriving():
             np.testing.assert_array_equal(sc.w_nsites[k, :nw], o["w_nsites"])
             assert int(sc.processed[k]) == o["processed"] and int(sc.skipped[k]) == o["skipped"]
             np.testing.assert_allclose(sc.w_loglik[k, :nw], o["w_log"], rtol=0, atol=1e-6)
+
+
+def test_window_shards_reassemble_the_unsharded_table():
+    """Multi-GPU partition by windows, emulated on one GPU: each of 3 shards scores its own windows of every
+    target, reads only its own panel rows (the others hold garbage in the device buffer), and writes its
+    columns of a shared device table (ibdgem_scores.w_loglik_device).  The union is the unsharded result."""
+    import torch
+    import ibdgem_b200 as ib
+    from ibdgem_b200.shard import upload_window_shard_rows
+    ec = _engine()
+    case = _synth_case(81, 9000, 40, 100, True, range(7), pu_idx=3)
+    pk = case.pk
+    want = ec.run_engine(case, expanded=False)
+    bits = ib.pack_bits(pk.hap)
+    h_bits = torch.from_numpy(bits.view(np.int32)).pin_memory()
+    S, Wh = bits.shape
+    T = len(case.targets)
+    count = 3
+    maxW = S // 100 + 2
+    d_table = torch.full((T, maxW, 3), float("nan"), dtype=torch.float64, device="cuda")
+    merged = np.full((T, maxW, 3), np.nan)
+    covered = []
+    with ib.Engine(ib.Params(window_size=100)) as e:
+        for idx in range(count):
+            e.set_window_shard(idx, count)
+            e.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, None)
+            d_panel = torch.full((S, Wh), -1, dtype=torch.int32, device="cuda")  # rows outside the shard: all ones
+            nbytes = upload_window_shard_rows(e, h_bits, d_panel, len(pk.names))
+            wb, we, sb, se = e.window_shard()
+            assert nbytes == (se - sb) * Wh * 4 and 0 <= sb < se <= S
+            covered.append((wb, we, sb, se))
+            sc = e.score_ld(case.targets, case.bg, 3, max_windows=maxW, device_out=d_table.data_ptr())
+            assert e.last_ld_path() == 1
+            got = sc.w_loglik
+            assert np.isnan(got[:, :wb]).all() and np.isnan(got[:, we:]).all()  # only the shard's columns are written
+            merged[:, wb:we] = got[:, wb:we]
+            for k, w in enumerate(want):
+                assert int(sc.n_windows[k]) == w["n_windows"]
+                np.testing.assert_array_equal(sc.w_nsites[k, :w["n_windows"]], w["w_nsites"])
+                np.testing.assert_array_equal(sc.w_start[k, :w["n_windows"]], w["w_start"])
+        # non-tensor paths refuse a window shard instead of silently scoring everything
+        with pytest.raises(RuntimeError, match="window shard"):
+            e.score_nonld(case.targets)
+    # shards tile the windows and the panel rows exactly
+    assert covered[0][0] == 0 and covered[0][2] == 0 and covered[-1][3] == S
+    for a, b in zip(covered, covered[1:]):
+        assert a[1] == b[0] and a[3] == b[2]
+    table = d_table.cpu().numpy()
+    for k, w in enumerate(want):
+        nw = w["n_windows"]
+        assert covered[-1][1] == nw
+        np.testing.assert_allclose(merged[k, :nw], w["w_log"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(table[k, :nw], w["w_log"], rtol=0, atol=1e-9)

@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ibdgem_b200.shard import gather_window_scores, panel_pieces, replicate_panel, shard_bounds, shard_targets
+from ibdgem_b200.shard import (gather_window_columns, gather_window_scores, panel_pieces, replicate_panel, shard_bounds,
+                                shard_targets, window_shard_bounds)
 
 
 def test_shard_bounds_partition():
@@ -159,3 +160,58 @@ def test_panel_replication_single_process(S, pieces):
     assert eng.calls[0] == ("set", S, 40, Wh) and ready == sorted(ready) and ready[-1] == S
     with pytest.raises(ValueError):
         replicate_panel(eng, h_bits, d_panel[: max(S - 1, 0)], n_indiv=40, pieces=pieces)
+
+
+def test_window_shard_bounds_tile_the_windows():
+    for n in (0, 1, 7, 1000, 1001):
+        for world in (1, 2, 3, 8):
+            cuts = [window_shard_bounds(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert max(hi - lo for lo, hi in cuts) - min(hi - lo for lo, hi in cuts) <= 1
+
+
+def _window_worker(rank, world, port, q):
+    """Partition by windows: windows are independent, so a rank can score its own windows from the sites of
+    those windows alone (here with the CPU oracle), for every target."""
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        prm, pos, keep, n_ref, n_alt, hap, targets, bg = _case()
+        maxW = len(pos) // prm.window + 2
+        inf = np.flatnonzero((keep == 1) & ((n_ref.astype(int) + n_alt) >= 1))
+        nW = -(-len(inf) // prm.window)
+        lo, hi = window_shard_bounds(nW, world, rank)
+        s0 = 0 if lo == 0 else inf[lo * prm.window - 1] + 1  # rows between two windows go with the later shard
+        s1 = len(pos) if hi == nW else inf[hi * prm.window - 1] + 1
+        sl = slice(s0, s1)
+        local = np.full((len(targets), maxW, 3), np.nan)
+        for k, t in enumerate(targets):
+            o = oracle.compare_target(prm, pos[sl], keep[sl], n_ref[sl], n_alt[sl], hap[sl], int(t), bg)
+            assert o["n_windows"] == hi - lo
+            local[k, lo:hi] = o["w_log"]
+        full = gather_window_columns(torch.from_numpy(local))
+        q.put((rank, full.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_window_partition_matches_unsharded():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_window_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    want = _score(_case()[6])
+    for r in range(world):
+        np.testing.assert_array_equal(np.isnan(got[r]), np.isnan(want))
+        np.testing.assert_allclose(np.nan_to_num(got[r]), np.nan_to_num(want), rtol=0, atol=1e-9)

@@ -282,6 +282,122 @@ def leg_ld(torch, ib, bits, pos, n_ref, n_alt, N, T, W, steps, variable_sites_on
             "comparisons_per_s": sites_scored * len(bg) * 4 / (ms * 1e-3)}
 
 
+def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, targets, bg, W, steps, what):
+    """--LD with the WINDOWS of the run partitioned across the ranks (shared window maps): every rank scores
+    all targets on its 1/world of the windows, reads only its own panel rows, and stores its columns of the
+    score table straight into the root's HBM (PeerTable).  Strong scaling: the total work is fixed.
+    All ranks call this; rank 0 returns the record."""
+    import torch.distributed as dist
+    from ibdgem_b200.engine import _CScores
+    from ibdgem_b200.shard import PeerTable, upload_window_shard_rows
+    dev_i = torch.cuda.current_device()
+    dev = torch.device("cuda", dev_i)
+    bits = h_bits.numpy().view(np.uint32)
+    S, T = bits.shape[0], len(targets)
+    keep_t, keep = _pin_np(torch, np.ones(S, np.uint8))
+    maxW = S // W + 2
+    stream = torch.cuda.current_stream()
+    o_nw = _pinned(torch, (T,), torch.int32)
+    o_ll = _pinned(torch, (T, maxW, 3), torch.float64)
+    book = rank == 0  # the bookkeeping arrays are the same on every rank: only the root fetches them
+    o_ws = _pinned(torch, (T, maxW), torch.int64) if book else None
+    o_we = _pinned(torch, (T, maxW), torch.int64) if book else None
+    o_wn = _pinned(torch, (T, maxW), torch.int32) if book else None
+    table = PeerTable(T, maxW, dev_i)
+    if table.is_root and table.ok:
+        table.tensor().fill_(float("nan"))
+    cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr() if book else None, o_we.data_ptr() if book else None,
+                  o_wn.data_ptr() if book else None, o_ll.data_ptr(), None, None, None, None, None, None,
+                  table.ptr if table.ok else None)
+    d_panel = torch.empty((S, bits.shape[1]), dtype=torch.int32, device=dev)
+    up_stream = torch.cuda.Stream(device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with ib.Engine(ib.Params(window_size=W, device=dev_i)) as e:
+        e.set_stream(stream.cuda_stream)
+        e.set_window_shard(rank, world)
+        e.upload_sites(pos, n_ref, n_alt, keep)
+        e.upload_panel(bits, N)
+        e.sync_uploads()
+        e.enable_timing(True)
+
+        def score():
+            e.invalidate()
+            e.score_ld_raw(targets, bg, -1, cs)
+
+        for _ in range(3):
+            score()
+        assert e.last_ld_path() == 1
+        e.reset_stats()
+        ms = timed(score, steps)
+        st = {k: v[0] / steps for k, v in e.kernel_stats().items() if v[1]}
+        wb, we, sb, se = e.window_shard()
+        e.enable_timing(False)
+        h2d = [0]
+
+        def e2e():
+            e.upload_sites(pos, n_ref, n_alt, keep)
+            up_stream.wait_stream(stream)
+            h2d[0] = upload_window_shard_rows(e, h_bits, d_panel, N, stream=up_stream)
+            score()
+
+        for _ in range(2):
+            e2e()
+        n2 = max(2, min(steps, 3))
+        ms_e2e = timed(e2e, n2)
+    nW = int(o_nw[0])
+    ok_cols = bool(np.isfinite(o_ll.numpy()[:, wb:we]).all())
+    gathered_ok = None
+    if table.ok:
+        barrier()
+        if table.is_root:
+            g = table.tensor()[:, :nW].cpu().numpy()
+            gathered_ok = bool(np.isfinite(g).all()) and bool(np.array_equal(g[:, wb:we], o_ll.numpy()[:, wb:we]))
+        barrier()
+    table.close()
+    inf = int(((n_ref.astype(np.int64) + n_alt) >= 1).sum())
+    nbg = len(bg) - int(np.isin(np.asarray(bg), np.asarray(targets)).any())  # -1 when the target is in the background
+    comps = float(inf) * T * nbg * 4
+    if rank != 0:
+        return None
+    return {"workload": what, "partition": "windows: %d window shard(s) of %d windows, all %d targets on every rank; score "
+            "columns stored into the root's HBM over NVLink (CUDA IPC peer stores%s)" % (world, nW, T, "" if table.ok else
+            " UNAVAILABLE here: no gather was made"),
+            "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "comparisons_per_s": comps / (ms * 1e-3),
+            "kernels_ms_rank0": st, "rank0_windows": [wb, we], "rank0_rows": [sb, se],
+            "shard_columns_finite": ok_cols, "gathered_table_complete_and_equal": gathered_ok,
+            "gather_bytes_per_rank": int(T) * (we - wb) * 24,
+            "e2e": {"ms_per_step": ms_e2e, "comparisons_per_s": comps / (ms_e2e * 1e-3),
+                    "h2d_bytes_per_step_rank0": int(h2d[0] + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes),
+                    "d2h_bytes_per_step_rank0": int(T * (we - wb) * 24 + T * maxW * 20 + T * 4)}}
+
+
+def c5_inputs(torch, S, N, seed=5, src=None):
+    """15,000-individual panel for BASELINE.json configs[4]; the reads are drawn from background
+    individual 10,000."""
+    from ibdgem_b200.synth import synth_panel_torch
+    d = synth_panel_torch(S, N, seed=seed, src=10_000 if src is None else src, device=torch.device("cuda", torch.cuda.current_device()),
+                          chunk=20_000)
+    return d
+
+
 def leg_int8_peak(torch):
     """Dense int8 GEMM 8192^3 through cuBLASLt (torch._int_mm): burst (best of 10) and sustained (2 s)."""
     try:
