@@ -29,6 +29,7 @@ static const char *const kKernelNameList[] = {
     "expand_sites",   "ld_general",    "ld_finalize",   "ld_compact",   "ld_c0",        "ld_transpose",
     "ld_stage",       "ld_expand_bg",  "ld_expand_tgt", "ld_windows",   "ld_ibd0",
     "ld_mma",         "viterbi",       "viterbi_norm",  "viterbi_back", "viterbi_out", "fill",
+    "v_slots",        "v_wmap",        "v_tw",          "v_sort",       "v_expand_a",  "v_expand_b",   "ld_vmma",
 };
 static_assert(sizeof(kKernelNameList) / sizeof(kKernelNameList[0]) == K_COUNT, "one name per KernelId, in enum order");
 const char *const *const kKernelNames = kKernelNameList;
@@ -913,6 +914,7 @@ static void free_prepared(ibdgem_engine *e, int64_t S) {
     e->d_ktot_shared = nullptr;
     e->prepared = false;
     ld_tensor_release(e);
+    ld_vtensor_release(e);
 }
 
 int ibdgem_engine_destroy(ibdgem_engine *e) {
@@ -1070,6 +1072,7 @@ int ibdgem_engine_upload_panel(ibdgem_engine *e, int64_t n_sites, int32_t n_indi
     e->prepared = false;
     e->table_from = e->table_upto = 0;
     ld_tensor_invalidate(e);
+    ld_vtensor_invalidate(e);
     return 0;
 }
 
@@ -1105,6 +1108,7 @@ int ibdgem_engine_set_panel_device(ibdgem_engine *e, int64_t n_sites, int32_t n_
     e->prepared = false;
     e->table_from = e->table_upto = 0;
     ld_tensor_invalidate(e);
+    ld_vtensor_invalidate(e);
     return 0;
 }
 
@@ -1151,9 +1155,11 @@ static SiteView make_view(ibdgem_engine *e, const uint8_t *d_tgt_counts, int vfl
 }
 
 // Builds a window map for `rows` rows (targets==nullptr -> one shared row).
-static int build_window_map(ibdgem_engine *e, const SiteView &v, const int32_t *d_targets, int rows,
-                            int maxW, int64_t *d_wfirst, int64_t *d_wlast, int32_t *d_nwin,
-                            int64_t *d_ktot, uint32_t *d_rank) {
+extern "C++" {
+namespace ibdgem {
+int build_window_map(ibdgem_engine *e, const SiteView &v, const int32_t *d_targets, int rows,
+                     int maxW, int64_t *d_wfirst, int64_t *d_wlast, int32_t *d_nwin,
+                     int64_t *d_ktot, uint32_t *d_rank) {
     const int nb = (int)((e->S + SCAN_CHUNK - 1) / SCAN_CHUNK);
     uint32_t *d_cnt;
     if (scratch(e, SC_BLOCKCNT, (size_t)rows * nb * 4, (void **)&d_cnt)) return 1;
@@ -1182,6 +1188,8 @@ static int build_window_map(ibdgem_engine *e, const SiteView &v, const int32_t *
     IBD_CUDA(cudaGetLastError());
     return 0;
 }
+}  // namespace ibdgem
+}  // extern "C++"
 
 int ibdgem_engine_prepare(ibdgem_engine *e) {
     if (!e) return 1;
@@ -1240,6 +1248,7 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     }
     e->prepared = true;
     ld_tensor_invalidate(e);
+    ld_vtensor_invalidate(e);
     resolve_timers(e);
     return 0;
 }
@@ -1249,6 +1258,7 @@ int ibdgem_engine_invalidate(ibdgem_engine *e) {
     e->prepared = false;
     e->table_from = e->table_upto = 0;
     ld_tensor_invalidate(e);
+    ld_vtensor_invalidate(e);
     return 0;
 }
 
@@ -1315,6 +1325,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     SiteView v = make_view(e, d_tc, vflag);
 
     // window map
+    bool vtensor = false;
     WindowMapView m;
     int32_t *d_nwin;
     int64_t *d_ktot;
@@ -1325,6 +1336,13 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         m.nwin = d_nwin;
         m.rows = 1;
         m.maxW = (int)(S / e->prm.window_size + 2);
+    } else if (ld && !e->force_general && ld_vtensor_eligible(e, T, n_bg)) {
+        vtensor = true;  // the per-target-window tensor path builds its own window map (in rank space for -v)
+        d_nwin = nullptr;
+        m.wfirst = m.wlast = nullptr;
+        m.nwin = nullptr;
+        m.rows = T;
+        m.maxW = mapW;
     } else {
         int64_t *d_wf, *d_wl;
         if (scratch(e, SC_WFIRST, (size_t)T * mapW * 8, (void **)&d_wf) ||
@@ -1381,7 +1399,28 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     e->wll_dev_streamed = false;
     e->h_wll_out = out->w_loglik;
     e->d_wll_out_device = static_cast<double *>(out->w_loglik_device);
-    if (tensor) {
+    if (vtensor) {
+        const int rc = ld_vtensor_score(e, T, targets, d_targets, n_bg, bg, pu_idx, d_tc, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
+        if (rc == 1) return 1;
+        if (rc == 2) {  // not taken after all (e.g. every background member excluded): the general path, with its own map
+            vtensor = false;
+            int64_t *d_wf, *d_wl;
+            if (scratch(e, SC_WFIRST, (size_t)T * mapW * 8, (void **)&d_wf) ||
+                scratch(e, SC_WLAST, (size_t)T * mapW * 8, (void **)&d_wl) ||
+                scratch(e, SC_NWIN, (size_t)std::max(T, 1) * 4, (void **)&d_nwin) ||
+                scratch(e, SC_KTOT, (size_t)std::max(T, 1) * 8, (void **)&d_ktot))
+                return 1;
+            if (build_window_map(e, v, d_targets, T, mapW, d_wf, d_wl, d_nwin, d_ktot, nullptr)) return 1;
+            m.wfirst = d_wf;
+            m.wlast = d_wl;
+            m.nwin = d_nwin;
+        } else {
+            e->last_ld_path = 2;
+        }
+    }
+    if (vtensor) {
+        // done: window bookkeeping, LIBD0, LIBD1 and LIBD2 of every target are in place
+    } else if (tensor) {
         // tensor path: fills window bookkeeping, LIBD0, LIBD1 and LIBD2 of every target
         if (ld_tensor_score(e, T, targets, d_targets, n_bg, bg, pu_idx, outW, d_wll, d_wn, d_ws, d_we, d_nwout)) return 1;
         e->last_ld_path = 1;
@@ -1400,7 +1439,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         IBD_CUDA(cudaGetLastError());
     }
 
-    if (ld && !tensor) {
+    if (ld && !tensor && !vtensor) {
         std::vector<int32_t> h_nref(T);
         for (int t = 0; t < T; t++) {
             int c = 0;
@@ -1556,6 +1595,7 @@ int ibdgem_engine_set_window_shard(ibdgem_engine *e, int32_t index, int32_t coun
         e->prepared = false;
         e->table_from = e->table_upto = 0;
         ld_tensor_invalidate(e);
+        ld_vtensor_invalidate(e);
     }
     return 0;
 }

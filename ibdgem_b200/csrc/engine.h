@@ -49,12 +49,21 @@ enum KernelId {
     K_VITERBI_BACK,     // H3 back-trace + state counts
     K_VITERBI_OUT,      // scores / states back to table-major
     K_FILL,             // NaN fill of device score buffers
+    K_V_SLOTS,          // per-target-window tensor path: slots of the K axis (informative kept sites)
+    K_V_WMAP,           // -v window map in rank space (one warp per target)
+    K_V_TW,             // per (target, window) scalars: C0, R, LIBD2, bookkeeping
+    K_V_SORT,           // (target, window) pairs sorted by start, tiles and their K hulls
+    K_V_EXPAND_A,       // row operand slabs (n a0, n a1, v nref, v nalt)
+    K_V_EXPAND_B,       // column operand slabs (r0, r1, r0 & r1)
+    K_LD_VMMA,          // tcgen05 GEMM over per-target windows + fused log-sum-exp -> LIBD0, LIBD1
     K_COUNT
 };
 
 extern const char *const *const kKernelNames;  // [K_COUNT], in enum order (engine.cu)
 
 struct LdCache;  // ld_mma.cu
+struct VCache;   // ld_vmma.cu
+struct SiteView;
 
 struct PendingTimer {
     int id;
@@ -131,6 +140,7 @@ struct ibdgem_engine {
 
     // tensor path caches (built lazily on first eligible score_ld)
     ibdgem::LdCache *ld = nullptr;
+    ibdgem::VCache *vc = nullptr;  // per-target-window tensor path (ld_vmma.cu)
 
     // scratch
     void *h_pin = nullptr;  // pinned staging for the small per-call host <-> device tables (grow-only)
@@ -174,7 +184,8 @@ enum ScratchSlot {
     SC_TARGETS = 0, SC_BG, SC_TGT_COUNTS, SC_BLOCKCNT, SC_WFIRST, SC_WLAST, SC_NWIN, SC_KTOT, SC_WLL,
     SC_WN, SC_WS, SC_WE, SC_COUNTERS, SC_SITE_STATUS, SC_SITE_LIK, SC_LD_PART, SC_NREFPANEL,
     SC_HG_LIK, SC_HG_OFF, SC_HG_STATE, SC_HG_SCORE, SC_HG_COUNTS, SC_HG_NRMT, SC_HG_SCORET, SC_HG_FROMT, SC_HG_LAST,
-    SC_MMA_TGT, SC_MMA_BG, SC_MMA_ROWLSE, SC_MMA_BGIDX, SC_MMA_MISC, SC_MMA_UNIT, SC_SLOTS
+    SC_MMA_TGT, SC_MMA_BG, SC_MMA_ROWLSE, SC_MMA_BGIDX, SC_MMA_MISC, SC_MMA_UNIT,
+    SC_V_KS, SC_V_KE, SC_V_TWBASE, SC_V_TWI, SC_V_TWD, SC_V_ORDER, SC_V_HIST, SC_V_TILES, SC_V_MISC, SC_SLOTS
 };
 int scratch(ibdgem_engine *e, int slot, size_t bytes, void **out);
 
@@ -197,6 +208,18 @@ constexpr int PANEL_CHUNKS = 16;         // upload / scoring pipeline depth
 constexpr double PANEL_TAPER = 1.0;       // chunk k is PANEL_TAPER^k of the first chunk
 constexpr size_t PANEL_CHUNK_MIN_BYTES = (size_t)16 << 20;  // ~0.3 ms of PCIe; smaller panels use fewer chunks
 void ld_tensor_invalidate(ibdgem_engine *e);
+// site-major bits -> [block][haplotype][WP32 words] for `nwin` blocks of Wpad slots listed in `infsite` (ld_mma.cu)
+int ld_transpose_launch(ibdgem_engine *e, int w_begin, int w_end, const int32_t *infsite, int Wpad, int WP32, int H, uint32_t *tbits);
+// per-target-window tensor path (ld_vmma.cu): -v / -D
+bool ld_vtensor_eligible(ibdgem_engine *e, int32_t n_targets, int32_t n_bg);
+int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const int32_t *d_targets, int32_t n_bg, const int32_t *h_bg,
+                     int32_t pu_idx, const uint8_t *d_tgt_counts, int32_t outW, double *d_wll, int32_t *d_wn, uint64_t *d_ws,
+                     uint64_t *d_we, int32_t *d_nwout);  // 0 = done, 2 = not taken, 1 = error
+void ld_vtensor_release(ibdgem_engine *e);
+void ld_vtensor_invalidate(ibdgem_engine *e);
+// window map for `rows` rows (targets == nullptr: one shared row), engine.cu
+int build_window_map(ibdgem_engine *e, const SiteView &v, const int32_t *d_targets, int rows, int maxW, int64_t *d_wfirst,
+                     int64_t *d_wlast, int32_t *d_nwin, int64_t *d_ktot, uint32_t *d_rank);
 // windows [w_begin, w_end) and panel rows [s_begin, s_end) of this engine's shard (everything when unsharded)
 void window_shard_bounds(const ibdgem_engine *e, int32_t *w_begin, int32_t *w_end, int64_t *s_begin, int64_t *s_end);
 

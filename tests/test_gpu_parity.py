@@ -72,7 +72,7 @@ def test_fixture_ld_against_reference(golden_dir, fixture_dir, k):
 
 
 def _synth_case(seed, S, N, window, ld, targets, bg=None, pu_idx=-1, opt_v=0, depth=2.0, eps=0.02,
-                max_cov=20):
+                max_cov=20, cull_p=1.0):
     import oracle
     rng = np.random.default_rng(seed)
     af = np.clip(rng.beta(0.5, 2.0, S), 0.01, 0.99)
@@ -86,7 +86,8 @@ def _synth_case(seed, S, N, window, ld, targets, bg=None, pu_idx=-1, opt_v=0, de
     pk = refio.Packed([f"i{i}" for i in range(N)], hap, pos, keep, n_ref.astype(np.uint8),
                       n_alt.astype(np.uint8), d.astype(np.uint32), ["1"] * S, ["."] * S, ["A"] * S,
                       ["G"] * S, None)
-    prm = oracle.Params(epsilon=eps, max_cov=max_cov, window=window, ld_mode=int(ld), opt_v=opt_v, pu_idx=pu_idx)
+    prm = oracle.Params(epsilon=eps, max_cov=max_cov, window=window, ld_mode=int(ld), opt_v=opt_v, pu_idx=pu_idx,
+                        cull_p=cull_p)
     return refcases.Case(pk, prm, list(targets), np.asarray(bg if bg is not None else range(N), np.int32),
                          None, "UNKWN", "")
 
@@ -495,3 +496,103 @@ def test_window_shards_reassemble_the_unsharded_table():
         assert covered[-1][1] == nw
         np.testing.assert_allclose(merged[k, :nw], w["w_log"], rtol=0, atol=1e-9)
         np.testing.assert_allclose(table[k, :nw], w["w_log"], rtol=0, atol=1e-9)
+
+
+# ---- per-target windows on the tensor cores (-v, -D): ld_vmma.cu, ld_path == 2 ------------------
+@pytest.mark.parametrize("window,S,N,T", [(10, 2500, 30, 7), (100, 9000, 40, 33), (1000, 30000, 100, 70), (37, 4000, 170, 90)])
+def test_ld_variable_sites_tensor_path_vs_oracle(window, S, N, T):
+    """-v --LD: every target has its own windows; rows of the GEMM are (target, window) pairs.  Shapes cover
+    one and several row tiles (64 pairs each), one to three column tiles (80 individuals each), hulls of one
+    and of many k-blocks, and windows shorter than a 32-slot word."""
+    ec = _engine()
+    case = _synth_case(100 + window, S, N, window, True, range(T), pu_idx=2, opt_v=1)
+    results = ec.run_engine(case, expanded=False)
+    assert results[0]["ld_path"] == 2
+    assert results[0]["kernel_stats"]["ld_vmma"][1] >= 1
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
+
+
+def test_ld_variable_sites_general_path_still_matches():
+    ec = _engine()
+    case = _synth_case(141, 3000, 30, 50, True, range(6), pu_idx=2, opt_v=1)
+    results = ec.run_engine(case, force_general=True, expanded=False)
+    assert results[0]["ld_path"] == 0
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
+
+
+@pytest.mark.parametrize("opt_v", [0, 1])
+def test_ld_downsampled_counts_tensor_path_vs_oracle(opt_v):
+    """-D (with and without -v): per-target thinned counts, drawn with glibc rand() in the reference's order;
+    windows, row operands and the class sums all follow the target's own counts."""
+    ec = _engine()
+    case = _synth_case(150 + opt_v, 2500, 90, 40, True, range(9), pu_idx=1, opt_v=opt_v, depth=5.0, cull_p=0.5)
+    results = ec.run_engine(case, expanded=True)
+    assert results[0]["ld_path"] == 2
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
+
+
+def test_ld_variable_sites_background_subsets_duplicates_and_disjoint_targets():
+    ec = _engine()
+    bg = [0, 3, 3, 5, 7, 8, 9, 11, 12, 20, 21, 22, 2] + list(range(30, 130))
+    case = _synth_case(160, 6000, 140, 120, True, [2, 3, 20, 23, 135, 139], bg=bg, pu_idx=5, opt_v=1)
+    results = ec.run_engine(case, expanded=False)
+    assert results[0]["ld_path"] == 2
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
+
+
+def test_ld_variable_sites_row_tiles_in_batches_under_a_small_budget():
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "import numpy as np, enginecase as ec, refcases\n"
+        "from test_gpu_parity import _synth_case\n"
+        "case = _synth_case(170, 20000, 60, 100, True, range(40), pu_idx=3, opt_v=1)\n"
+        "res = ec.run_engine(case, expanded=False)\n"
+        "assert res[0]['ld_path'] == 2 and res[0]['kernel_stats']['ld_vmma'][1] >= 3, res[0]['kernel_stats']['ld_vmma']\n"
+        "for r, o in zip(res, refcases.oracle_run(case)): ec.assert_matches_oracle(r, o)\n"
+        "print('ok')\n")
+    env = dict(os.environ, IBDGEM_V_BUDGET_MB="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_c3_variable_sites_full_size_spot_checks_against_oracle():
+    """C3 with -v at full size (1,000,000 sites x 2,504 samples x 1,000 targets, window 1,000 VARIABLE sites):
+    a window of a target depends only on the sites between its first and last member, so any (target, window)
+    cell can be re-scored by the CPU oracle from that slice of the inputs."""
+    import torch
+    import ibdgem_b200 as ib
+    import oracle
+    from ibdgem_b200.synth import synth_panel_torch, unpack_rows
+    S, N, T, W = 1_000_000, 2504, 1000, 1000
+    d = synth_panel_torch(S, N, seed=1, device="cuda")
+    bits = d["bits"].numpy().view(np.uint32)
+    pos = d["pos"].numpy().view(np.uint64)
+    n_ref, n_alt, keep = d["n_ref"].numpy(), d["n_alt"].numpy(), d["keep"].numpy()
+    targets = np.arange(T, dtype=np.int32)
+    bg = np.arange(N, dtype=np.int32)
+    with ib.Engine(ib.Params(window_size=W, variable_sites_only=1)) as e:
+        e.upload_sites(pos, n_ref, n_alt, keep)
+        e.upload_panel(bits, N)
+        sc = e.score_ld(targets, bg, -1)
+        assert e.last_ld_path() == 2
+    prm = oracle.Params(window=W, ld_mode=1, opt_v=1)
+    for t in (0, 333, T - 1):
+        nw = int(sc.n_windows[t])
+        assert 250 < nw < 400
+        assert int(sc.w_nsites[t, :nw - 1].min()) == W and np.all(np.diff(sc.w_start[t, :nw].astype(np.int64)) > 0)
+        assert np.isfinite(sc.w_loglik[t, :nw]).all()
+        for w in (0, nw // 2, nw - 1):
+            s0 = int((int(sc.w_start[t, w]) - 1000) // 60)
+            s1 = int((int(sc.w_end[t, w]) - 1000) // 60) + 1
+            sl = slice(s0, s1)
+            hap = unpack_rows(bits, 2 * N, np.arange(s0, s1))
+            o = oracle.compare_target(prm, pos[sl], keep[sl], n_ref[sl], n_alt[sl], hap, int(t), bg)
+            assert o["n_windows"] == 1 and int(o["w_nsites"][0]) == int(sc.w_nsites[t, w])
+            np.testing.assert_allclose(sc.w_loglik[t, w], o["w_log"][0], rtol=0, atol=1e-6)
