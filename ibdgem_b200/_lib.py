@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "hiddengem_viterbi_batch", "ibdgem_engine_enable_timing", "ibdgem_engine_reset_stats",
     "ibdgem_engine_num_kernels", "ibdgem_engine_kernel_stats", "ibdgem_engine_device_bytes",
     "ibdgem_engine_set_window_shard", "ibdgem_engine_window_shard", "ibdgem_peer_alloc", "ibdgem_peer_open",
-    "ibdgem_peer_close",
+    "ibdgem_peer_close", "hiddengem_viterbi_batch_device", "hiddengem_last_flagged",
 ]
 
 
@@ -49,6 +49,7 @@ def load_library():
     lib = C.CDLL(LIB_PATH)
     lib.ibdgem_last_error.restype = C.c_char_p
     lib.ibdgem_engine_device_bytes.restype = C.c_int64
+    lib.hiddengem_last_flagged.restype = C.c_int64
     for name in ABI_SYMBOLS:
         getattr(lib, name)  # raises AttributeError if the ABI is incomplete
     _lib = lib

@@ -226,15 +226,40 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
 // Site status without the panel: when no -A table is given and the AF range is the default [0, 1]
 // the AF filter of src/ibdgem.c:616 cannot fire (f = count / 2N), so keep / status follow from the
 // site arrays alone and the window map can be built before the panel has arrived.
+// The same pass accumulates the counters of a target that -v / -D do not filter (processed, skipped, total
+// final coverage, coverage histogram: src/ibdgem.c:585-630, 761-768) — one read of the site arrays instead of two.
 __global__ void __launch_bounds__(256)
 site_status_kernel(int64_t S, const uint8_t *__restrict__ hostkeep, const uint8_t *__restrict__ nref,
-                   const uint8_t *__restrict__ nalt, int max_cov, uint8_t *__restrict__ keep, uint8_t *__restrict__ status) {
-    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    const int r = nref[s], a = nalt[s];
-    const bool k = hostkeep[s] && (r + a <= max_cov);
-    keep[s] = k ? 1 : 0;
-    status[s] = k ? ((r + a >= 1) ? 1 : 2) : 0;
+                   const uint8_t *__restrict__ nalt, int max_cov, uint8_t *__restrict__ keep, uint8_t *__restrict__ status,
+                   int C, unsigned long long *__restrict__ cnt /*[C+3], pre-zeroed*/) {
+    extern __shared__ unsigned int shist[];  // [C + 3]: a block sees at most 2^32 - 1 sites
+    for (int i = threadIdx.x; i < C + 3; i += blockDim.x) shist[i] = 0;
+    __syncthreads();
+    unsigned proc = 0, skip = 0, cov = 0;
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < S; s += (int64_t)gridDim.x * blockDim.x) {
+        const int r = nref[s], a = nalt[s];
+        const bool k = hostkeep[s] && (r + a <= max_cov);
+        keep[s] = k ? 1 : 0;
+        status[s] = k ? ((r + a >= 1) ? 1 : 2) : 0;
+        if (k) {
+            proc++;
+            cov += (unsigned)(r + a);
+            atomicAdd(&shist[3 + min(r + a, C - 1)], 1u);
+        } else {
+            skip++;
+        }
+    }
+    proc = (unsigned)warp_sum_i((int)proc);
+    skip = (unsigned)warp_sum_i((int)skip);
+    cov = (unsigned)warp_sum_i((int)cov);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&shist[0], proc);
+        atomicAdd(&shist[1], skip);
+        atomicAdd(&shist[2], cov);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C + 3; i += blockDim.x)
+        if (shist[i]) atomicAdd(&cnt[i], (unsigned long long)shist[i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -454,12 +479,21 @@ window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restric
         for (int i = threadIdx.x; i < cnt * 7; i += blockDim.x) sl[i / 7][i % 7] = lnlik7[ssite[i / 7] * 7 + i % 7];
         __syncthreads();
         if (t < T) {
-            for (int j = 0; j < cnt; j++) {
-                const uint32_t pr = hap_pair(v.bits + ssite[j] * v.Wh, indiv);
-                const int g = (int)(pr & 1u) + (int)(pr >> 1);
-                a0 += sl[j][0];
-                a1 += sl[j][1 + g];
-                a2 += sl[j][4 + g];
+            // genotype loads are issued eight at a time: one dependent global load per site made this loop
+            // a chain of L2 round trips (the kernel sat at 12 % of HBM)
+            for (int j0 = 0; j0 < cnt; j0 += 8) {
+                uint32_t pr[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) pr[q] = (j0 + q < cnt) ? hap_pair(v.bits + ssite[j0 + q] * v.Wh, indiv) : 0u;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (j0 + q < cnt) {
+                        const int g = (int)(pr[q] & 1u) + (int)(pr[q] >> 1);
+                        a0 += sl[j0 + q][0];
+                        a1 += sl[j0 + q][1 + g];
+                        a2 += sl[j0 + q][4 + g];
+                    }
+                }
             }
             n += cnt;
         }
@@ -928,6 +962,7 @@ int ibdgem_engine_destroy(ibdgem_engine *e) {
     if (e->have_sites) free_sites(e);
     dev_free(e, e->d_P, e->h_P.size() * 8);
     dev_free(e, e->d_lnP, e->h_lnP.size() * 8);
+    dev_free(e, e->d_shared_cnt, (size_t)(e->C + 3) * 8);
     for (auto *b : e->scratch)
         if (b) {
             if (b->p) cudaFree(b->p);
@@ -1214,10 +1249,15 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     // the window map is built from the site arrays at once, and the per-site table (which reads the
     // panel) is evaluated chunk by chunk as the rows arrive (ensure_table).
     e->lazy_table = !e->d_afuser && e->prm.min_af <= 0.0 && e->prm.max_af >= 1.0;
+    e->shared_cnt_valid = false;
     if (e->lazy_table) {
+        if (!e->d_shared_cnt && dev_alloc(e, (void **)&e->d_shared_cnt, (size_t)(e->C + 3) * 8)) return 1;
+        IBD_CUDA(cudaMemsetAsync(e->d_shared_cnt, 0, (size_t)(e->C + 3) * 8, e->stream));
         LaunchScope ls(e, K_SITE_TABLE);
-        site_status_kernel<<<(unsigned)((S + 255) / 256), 256, 0, e->stream>>>(S, e->d_hostkeep, e->d_nref, e->d_nalt,
-                                                                              (int)e->prm.max_cov, e->d_keep, e->d_status);
+        const unsigned nblk = (unsigned)std::min<int64_t>((S + 255) / 256, (int64_t)e->sm_count * 8);
+        site_status_kernel<<<nblk, 256, (size_t)(e->C + 3) * 4, e->stream>>>(S, e->d_hostkeep, e->d_nref, e->d_nalt, (int)e->prm.max_cov,
+                                                                           e->d_keep, e->d_status, e->C, e->d_shared_cnt);
+        e->shared_cnt_valid = true;
     } else if (ensure_table(e, S)) {
         return 1;
     }
@@ -1487,7 +1527,9 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     unsigned long long *d_cnt = nullptr;
     const int crow = C + 3;
     const int crows = shared ? 1 : T;
-    if (want_counters) {
+    if (want_counters && shared && e->shared_cnt_valid) {
+        d_cnt = e->d_shared_cnt;  // counted by site_status_kernel in prepare()
+    } else if (want_counters) {
         if (scratch(e, SC_COUNTERS, (size_t)crows * crow * 8, (void **)&d_cnt)) return 1;
         IBD_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)crows * crow * 8, e->stream));
         LaunchScope ls(e, K_COUNTERS);

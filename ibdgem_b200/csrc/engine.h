@@ -137,6 +137,10 @@ struct ibdgem_engine {
     int64_t *d_ktot_shared = nullptr;
     int32_t nW_shared = 0;
     int64_t K_shared = 0;
+    // processed / skipped / coverage histogram of a target that -v / -D do not filter ([C + 3], see counters_kernel),
+    // accumulated by site_status_kernel in the same pass that decides keep / status (lazy prepare only)
+    unsigned long long *d_shared_cnt = nullptr;
+    bool shared_cnt_valid = false;
 
     // tensor path caches (built lazily on first eligible score_ld)
     ibdgem::LdCache *ld = nullptr;
@@ -160,6 +164,7 @@ struct ibdgem_engine {
     cudaEvent_t ev_t0 = nullptr, ev_wll = nullptr, ev_bookdone = nullptr;
     bool t0_set = false;
 
+    int64_t hg_flagged = 0;  // tables of the last hiddengem call re-evaluated on the host (near-tie guard)
     int last_ld_path = -1;
     int force_general = 0;
 };

@@ -8,8 +8,10 @@
 // src/hiddengem.c:91-99).  Zeros become -inf and NaN rows (0/0, src/hiddengem.c:74-76)
 // propagate exactly as they do through the products.
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "engine.h"
 
@@ -23,19 +25,38 @@ __device__ __forceinline__ int argmax3(double c0, double c1, double c2) {
     return b;
 }
 
+// Near-tie guard.  The reference multiplies x87 long doubles (src/hiddengem.c:110-141); sums of fp64 logs carry a
+// rounding error of up to ~i * 2^-53 * |score| after i bins, so an arg-max whose winner leads the runner-up by less
+// than that could come out differently.  Such tables (and, on the text path, tables whose scores leave the range
+// of a normal long double, where the reference's products lose bits and then vanish) are flagged and re-evaluated
+// on the host in long double.  NaN / -inf candidates never flag: their comparisons are exact in both worlds.
+constexpr double LN_LDBL_MIN = -11355.137111933024;  // ln(3.3621e-4932)
+__device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int best, int64_t i) {
+    const double w = best == 0 ? c0 : (best == 1 ? c1 : c2);
+    const double r = best == 0 ? fmax(c1, c2) : (best == 1 ? fmax(c0, c2) : fmax(c0, c1));
+    const double tol = 4.0 * (double)(i + 1) * 1.1102230246251565e-16 * fabs(w) + 1e-12;
+    return (w - r) < tol;  // false for NaN and for inf - inf
+}
+// a finite score below the smallest normal long double: the reference's product is a denormal (or zero) there
+__device__ __forceinline__ bool below_ldbl(double s0, double s1, double s2) {
+    return (s0 < LN_LDBL_MIN && s0 > -INFINITY) || (s1 < LN_LDBL_MIN && s1 > -INFINITY) || (s2 < LN_LDBL_MIN && s2 > -INFINITY);
+}
+
 __global__ void __launch_bounds__(128)
-viterbi_kernel(int n_tables, const int64_t *__restrict__ off, const double *__restrict__ lik, int is_log,
+viterbi_kernel(int n_tables, const int64_t *__restrict__ start, const int64_t *__restrict__ len, const double *__restrict__ lik, int is_log,
                double lp01, double lp02, double lp12, uint8_t *__restrict__ state,
-               double *__restrict__ score, long long *__restrict__ counts) {
+               double *__restrict__ score, long long *__restrict__ counts, uint8_t *__restrict__ flag) {
     const int tb = blockIdx.x * blockDim.x + threadIdx.x;
     if (tb >= n_tables) return;
-    const int64_t b0 = off[tb], b1 = off[tb + 1];
-    const int64_t n = b1 - b0;
+    const int64_t b0 = start[tb];
+    const int64_t n = len[tb];
     if (n <= 0) {
         counts[tb * 3 + 0] = counts[tb * 3 + 1] = counts[tb * 3 + 2] = 0;
+        flag[tb] = 0;
         return;
     }
     double s0 = 0, s1 = 0, s2 = 0;
+    bool tie = false;
     for (int64_t i = 0; i < n; i++) {
         const double *L = lik + (b0 + i) * 3;
         double n0, n1, n2;
@@ -59,21 +80,23 @@ viterbi_kernel(int n_tables, const int64_t *__restrict__ off, const double *__re
             from = 0 | (1 << 2) | (2 << 4);
         } else {
             // candidates (prev_k + ln nrm_s) + ln pen(k, s), diagonal has no penalty factor
-            const int k0 = argmax3(s0 + n0, (s1 + n0) + lp01, (s2 + n0) + lp02);
-            const int k1 = argmax3((s0 + n1) + lp01, s1 + n1, (s2 + n1) + lp12);
-            const int k2 = argmax3((s0 + n2) + lp02, (s1 + n2) + lp12, s2 + n2);
-            const double p[3] = {s0, s1, s2};
-            const double t0 = (k0 == 0) ? p[0] + n0 : (p[k0] + n0) + (k0 == 1 ? lp01 : lp02);
-            const double t1 = (k1 == 1) ? p[1] + n1 : (p[k1] + n1) + (k1 == 0 ? lp01 : lp12);
-            const double t2 = (k2 == 2) ? p[2] + n2 : (p[k2] + n2) + (k2 == 0 ? lp02 : lp12);
-            s0 = t0; s1 = t1; s2 = t2;
+            const double a0 = s0 + n0, a1 = (s1 + n0) + lp01, a2 = (s2 + n0) + lp02;
+            const double b0_ = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
+            const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
+            const int k0 = argmax3(a0, a1, a2), k1 = argmax3(b0_, b1, b2), k2 = argmax3(c0, c1, c2);
+            tie |= near_tie(a0, a1, a2, k0, i) | near_tie(b0_, b1, b2, k1, i) | near_tie(c0, c1, c2, k2, i);
+            s0 = k0 == 0 ? a0 : (k0 == 1 ? a1 : a2);
+            s1 = k1 == 0 ? b0_ : (k1 == 1 ? b1 : b2);
+            s2 = k2 == 0 ? c0 : (k2 == 1 ? c1 : c2);
             from = (uint8_t)(k0 | (k1 << 2) | (k2 << 4));
         }
+        if (!is_log) tie |= below_ldbl(s0, s1, s2);
         state[b0 + i] = from;
         double *o = score + (b0 + i) * 3;
         o[0] = s0; o[1] = s1; o[2] = s2;
     }
     int cur = argmax3(s0, s1, s2);  // src/hiddengem.c:246-249
+    tie |= near_tie(s0, s1, s2, cur, n);
     long long c[3] = {0, 0, 0};
     for (int64_t i = n - 1; i >= 0; i--) {  // src/hiddengem.c:252-257
         const uint8_t from = state[b0 + i];
@@ -84,6 +107,7 @@ viterbi_kernel(int n_tables, const int64_t *__restrict__ off, const double *__re
     counts[tb * 3 + 0] = c[0];
     counts[tb * 3 + 1] = c[1];
     counts[tb * 3 + 2] = c[2];
+    flag[tb] = tie ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -114,15 +138,15 @@ __device__ __forceinline__ void ln_nrm(const double *L, int is_log, double &n0, 
 // (1) block = 32 tables x 32 bins.  Reads are contiguous runs of 32 bins of one table; writes are
 // runs of 32 tables of one (bin, state).
 __global__ void __launch_bounds__(1024)
-viterbi_norm_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ off, const double *__restrict__ lik,
-                    int is_log, double *__restrict__ nrmT /*[maxbins][3][n_tables]*/) {
+viterbi_norm_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ start, const int64_t *__restrict__ len,
+                    const double *__restrict__ lik, int is_log, double *__restrict__ nrmT /*[maxbins][3][n_tables]*/) {
     __shared__ double tile[3][32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int t_in = blockIdx.x * 32 + ty;
     const int64_t i_in = (int64_t)blockIdx.y * 32 + tx;
     double n0 = 0, n1 = 0, n2 = 0;
     if (t_in < n_tables) {
-        const int64_t b0 = off[t_in], n = off[t_in + 1] - b0;
+        const int64_t b0 = start[t_in], n = len[t_in];
         if (i_in < n) {
             const double *L = lik + (b0 + i_in) * 3;
             const double v[3] = {L[0], L[1], L[2]};
@@ -144,12 +168,14 @@ viterbi_norm_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ o
 // (2) thread = table
 constexpr int VIT_UNROLL = 8;
 __global__ void __launch_bounds__(64)
-viterbi_forward_kernel(int n_tables, const int64_t *__restrict__ off, const double *__restrict__ nrmT, double lp01,
+viterbi_forward_kernel(int n_tables, const int64_t *__restrict__ len, int is_log, const double *__restrict__ nrmT, double lp01,
                        double lp02, double lp12, uint8_t *__restrict__ fromT /*[maxbins][n_tables]*/,
-                       double *__restrict__ scoreT /*[maxbins][3][n_tables]*/, double *__restrict__ last /*[n_tables][3]*/) {
+                       double *__restrict__ scoreT /*[maxbins][3][n_tables]*/, double *__restrict__ last /*[n_tables][3]*/,
+                       uint8_t *__restrict__ flag) {
     const int tb = blockIdx.x * blockDim.x + threadIdx.x;
     if (tb >= n_tables) return;
-    const int64_t n = off[tb + 1] - off[tb];
+    const int64_t n = len[tb];
+    bool tie = false;
     const size_t nT = (size_t)n_tables;
     double s0 = 0, s1 = 0, s2 = 0;
     // two register batches: the loads of batch k + 1 are in flight while batch k runs the recurrence
@@ -180,17 +206,17 @@ viterbi_forward_kernel(int n_tables, const int64_t *__restrict__ off, const doub
                 s0 = n0; s1 = n1; s2 = n2;
                 from = 0 | (1 << 2) | (2 << 4);
             } else {
-                const int k0 = argmax3(s0 + n0, (s1 + n0) + lp01, (s2 + n0) + lp02);
-                const int k1 = argmax3((s0 + n1) + lp01, s1 + n1, (s2 + n1) + lp12);
-                const int k2 = argmax3((s0 + n2) + lp02, (s1 + n2) + lp12, s2 + n2);
-                const double p0 = s0, p1 = s1, p2 = s2;
-                const double q0 = k0 == 0 ? p0 : (k0 == 1 ? p1 : p2), q1 = k1 == 0 ? p0 : (k1 == 1 ? p1 : p2),
-                             q2 = k2 == 0 ? p0 : (k2 == 1 ? p1 : p2);
-                s0 = (k0 == 0) ? q0 + n0 : (q0 + n0) + (k0 == 1 ? lp01 : lp02);
-                s1 = (k1 == 1) ? q1 + n1 : (q1 + n1) + (k1 == 0 ? lp01 : lp12);
-                s2 = (k2 == 2) ? q2 + n2 : (q2 + n2) + (k2 == 0 ? lp02 : lp12);
+                const double a0 = s0 + n0, a1 = (s1 + n0) + lp01, a2 = (s2 + n0) + lp02;
+                const double b0 = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
+                const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
+                const int k0 = argmax3(a0, a1, a2), k1 = argmax3(b0, b1, b2), k2 = argmax3(c0, c1, c2);
+                tie |= near_tie(a0, a1, a2, k0, i) | near_tie(b0, b1, b2, k1, i) | near_tie(c0, c1, c2, k2, i);
+                s0 = k0 == 0 ? a0 : (k0 == 1 ? a1 : a2);
+                s1 = k1 == 0 ? b0 : (k1 == 1 ? b1 : b2);
+                s2 = k2 == 0 ? c0 : (k2 == 1 ? c1 : c2);
                 from = (uint8_t)(k0 | (k1 << 2) | (k2 << 4));
             }
+            if (!is_log) tie |= below_ldbl(s0, s1, s2);
             fromT[(size_t)i * nT + tb] = from;
             __stcs(scoreT + ((size_t)i * 3 + 0) * nT + tb, s0);
             __stcs(scoreT + ((size_t)i * 3 + 1) * nT + tb, s1);
@@ -200,15 +226,17 @@ viterbi_forward_kernel(int n_tables, const int64_t *__restrict__ off, const doub
     last[(size_t)tb * 3 + 0] = s0;
     last[(size_t)tb * 3 + 1] = s1;
     last[(size_t)tb * 3 + 2] = s2;
+    if (n > 0) tie |= near_tie(s0, s1, s2, argmax3(s0, s1, s2), n);
+    flag[tb] = tie ? 1 : 0;
 }
 
 // (3) back-trace; the state overwrites the back-pointer byte in place
 __global__ void __launch_bounds__(64)
-viterbi_back_kernel(int n_tables, const int64_t *__restrict__ off, uint8_t *__restrict__ fromT, const double *__restrict__ last,
+viterbi_back_kernel(int n_tables, const int64_t *__restrict__ len, uint8_t *__restrict__ fromT, const double *__restrict__ last,
                     long long *__restrict__ counts) {
     const int tb = blockIdx.x * blockDim.x + threadIdx.x;
     if (tb >= n_tables) return;
-    const int64_t n = off[tb + 1] - off[tb];
+    const int64_t n = len[tb];
     const size_t nT = (size_t)n_tables;
     long long c0 = 0, c1 = 0, c2 = 0;
     if (n > 0) {
@@ -236,7 +264,7 @@ viterbi_back_kernel(int n_tables, const int64_t *__restrict__ off, uint8_t *__re
 
 // (4) bin-major -> the caller's table-major layout
 __global__ void __launch_bounds__(1024)
-viterbi_out_kernel(int n_tables, const int64_t *__restrict__ off, const uint8_t *__restrict__ stateT,
+viterbi_out_kernel(int n_tables, const int64_t *__restrict__ start, const int64_t *__restrict__ len, const uint8_t *__restrict__ stateT,
                    const double *__restrict__ scoreT, uint8_t *__restrict__ state, double *__restrict__ score) {
     __shared__ double tile[3][32][33];
     __shared__ uint8_t st[32][33];
@@ -244,7 +272,7 @@ viterbi_out_kernel(int n_tables, const int64_t *__restrict__ off, const uint8_t 
     const int t_in = blockIdx.x * 32 + tx;
     const int64_t i_in = (int64_t)blockIdx.y * 32 + ty;
     const size_t nT = (size_t)n_tables;
-    if (t_in < n_tables && i_in < off[t_in + 1] - off[t_in]) {
+    if (t_in < n_tables && i_in < len[t_in]) {
 #pragma unroll
         for (int s = 0; s < 3; s++) tile[s][ty][tx] = __ldcs(scoreT + ((size_t)i_in * 3 + s) * nT + t_in);
         st[ty][tx] = stateT[(size_t)i_in * nT + t_in];
@@ -253,7 +281,7 @@ viterbi_out_kernel(int n_tables, const int64_t *__restrict__ off, const uint8_t 
     const int t_out = blockIdx.x * 32 + ty;
     const int64_t i_out = (int64_t)blockIdx.y * 32 + tx;
     if (t_out < n_tables) {
-        const int64_t b0 = off[t_out], n = off[t_out + 1] - b0;
+        const int64_t b0 = start[t_out], n = len[t_out];
         if (i_out < n) {
             double *o = score + (b0 + i_out) * 3;
             o[0] = tile[0][tx][ty];
@@ -268,6 +296,124 @@ viterbi_out_kernel(int n_tables, const int64_t *__restrict__ off, const uint8_t 
 
 using namespace ibdgem;
 
+// ---------------------------------------------------------------------------------------------
+// host side
+namespace {
+
+// The reference's own recurrence for one table, in x87 long double (src/hiddengem.c:74-76, 108-147, 246-257): the
+// arbiter for tables the device flagged (near-tie at an arg-max, or scores outside the normal long double range).
+// is_log = 1 (the engine's natural-log window scores) runs the same recurrence on long double logarithms.
+void viterbi_long_double(const double *lik, int64_t n, int is_log, double p01, double p02, double p12, uint8_t *state,
+                         double *score_log, int64_t counts[3]) {
+    counts[0] = counts[1] = counts[2] = 0;
+    if (n <= 0) return;
+    std::vector<uint8_t> from((size_t)n);
+    long double s[3] = {0, 0, 0};
+    const long double pen[3][3] = {{1.0L, (long double)p01, (long double)p02},
+                                   {(long double)p01, 1.0L, (long double)p12},
+                                   {(long double)p02, (long double)p12, 1.0L}};
+    long double lpen[3][3];
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) lpen[a][b] = a == b ? 0.0L : logl(pen[a][b]);
+    for (int64_t i = 0; i < n; i++) {
+        const double *L = lik + i * 3;
+        long double nrm[3];
+        if (is_log) {
+            const long double m = fmaxl(L[0], fmaxl(L[1], L[2]));
+            if (m == -INFINITY) {
+                nrm[0] = nrm[1] = nrm[2] = NAN;
+            } else {
+                const long double z = m + logl(expl(L[0] - m) + expl(L[1] - m) + expl(L[2] - m));
+                for (int k = 0; k < 3; k++) nrm[k] = (long double)L[k] - z;
+            }
+        } else {
+            volatile double tot = L[0] + L[1];
+            tot = tot + L[2];
+            for (int k = 0; k < 3; k++) {
+                volatile double q = L[k] / tot;  // fp64 quotient, as the reference stores it
+                nrm[k] = q;
+            }
+        }
+        if (i == 0) {
+            for (int k = 0; k < 3; k++) s[k] = nrm[k];
+            from[0] = (uint8_t)(0 | (1 << 2) | (2 << 4));
+        } else {
+            long double ns[3];
+            uint8_t f = 0;
+            for (int j = 0; j < 3; j++) {
+                long double c[3];
+                for (int k = 0; k < 3; k++) {
+                    if (is_log)
+                        c[k] = k == j ? s[k] + nrm[j] : (s[k] + nrm[j]) + lpen[k][j];
+                    else
+                        c[k] = k == j ? s[k] * nrm[j] : s[k] * nrm[j] * pen[k][j];
+                }
+                int best = 0;
+                for (int k = 0; k < 3; k++)
+                    if (c[k] > c[best]) best = k;  // find_max_idx: strict >, lowest index wins, NaN never wins
+                ns[j] = c[best];
+                f |= (uint8_t)(best << (2 * j));
+            }
+            for (int k = 0; k < 3; k++) s[k] = ns[k];
+            from[(size_t)i] = f;
+        }
+        for (int k = 0; k < 3; k++) score_log[i * 3 + k] = is_log ? (double)s[k] : (double)logl(s[k]);
+    }
+    int cur = 0;
+    for (int k = 0; k < 3; k++)
+        if (s[k] > s[cur]) cur = k;
+    for (int64_t i = n - 1; i >= 0; i--) {
+        state[i] = (uint8_t)cur;
+        counts[cur]++;
+        cur = (from[(size_t)i] >> (2 * cur)) & 3;
+    }
+}
+
+// One batch of tables, everything in device memory.  start / len describe where each table's bins sit in lik /
+// state / score; counts and flag are per table.  Kernels only (no host synchronisation).
+int viterbi_on_device(ibdgem_engine *e, int n_tables, int64_t maxbins, int64_t total_bins, const int64_t *d_start, const int64_t *d_len,
+                      const double *d_lik, int is_log, double p01, double p02, double p12, uint8_t *d_state, double *d_score,
+                      long long *d_counts, uint8_t *d_flag) {
+    const bool batched = n_tables >= 64 && (double)maxbins * n_tables <= 2.0 * (double)total_bins;
+    if (batched) {
+        double *d_nrmT, *d_scoreT, *d_last;
+        uint8_t *d_fromT;
+        const size_t cells = (size_t)maxbins * n_tables;
+        if (scratch(e, SC_HG_NRMT, cells * 24, (void **)&d_nrmT) || scratch(e, SC_HG_SCORET, cells * 24, (void **)&d_scoreT) ||
+            scratch(e, SC_HG_FROMT, cells, (void **)&d_fromT) || scratch(e, SC_HG_LAST, (size_t)n_tables * 24, (void **)&d_last))
+            return 1;
+        const dim3 tiles((unsigned)((n_tables + 31) / 32), (unsigned)((maxbins + 31) / 32));
+        {
+            LaunchScope ls(e, K_VITERBI_NORM);
+            viterbi_norm_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, maxbins, d_start, d_len, d_lik, is_log, d_nrmT);
+        }
+        {
+            LaunchScope ls(e, K_VITERBI);
+            viterbi_forward_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_len, is_log, d_nrmT, log(p01), log(p02), log(p12),
+                                                                             d_fromT, d_scoreT, d_last, d_flag);
+        }
+        {
+            LaunchScope ls(e, K_VITERBI_BACK);
+            viterbi_back_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_len, d_fromT, d_last, d_counts);
+        }
+        {
+            LaunchScope ls(e, K_VITERBI_OUT);
+            viterbi_out_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, d_start, d_len, d_fromT, d_scoreT, d_state, d_score);
+        }
+    } else {
+        LaunchScope ls(e, K_VITERBI);
+        viterbi_kernel<<<(n_tables + 127) / 128, 128, 0, e->stream>>>(n_tables, d_start, d_len, d_lik, is_log, log(p01), log(p02), log(p12),
+                                                                     d_state, d_score, d_counts, d_flag);
+    }
+    IBD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// Host buffers in, host buffers out.  The tables go through in batches: while batch b is scored, batch b + 1 is on its
+// way up and the results of batch b - 1 on their way down (three streams; page-locked buffers make the copies
+// asynchronous, pageable ones are simply staged by the driver).
 extern "C" int hiddengem_viterbi_batch(ibdgem_engine *e, int32_t n_tables, const int64_t *bin_offsets,
                                        const double *lik, int32_t is_log, double p01, double p02,
                                        double p12, uint8_t *state, double *score_log,
@@ -283,53 +429,166 @@ extern "C" int hiddengem_viterbi_batch(ibdgem_engine *e, int32_t n_tables, const
         return 1;
     }
     double *d_lik, *d_score;
-    int64_t *d_off;
-    uint8_t *d_state;
+    int64_t *d_start;
+    uint8_t *d_state, *d_flag;
     long long *d_counts;
-    if (scratch(e, SC_HG_LIK, (size_t)nb * 24, (void **)&d_lik) || scratch(e, SC_HG_OFF, (size_t)(n_tables + 1) * 8, (void **)&d_off) ||
-        scratch(e, SC_HG_STATE, (size_t)nb, (void **)&d_state) || scratch(e, SC_HG_SCORE, (size_t)nb * 24, (void **)&d_score) ||
+    if (scratch(e, SC_HG_LIK, (size_t)nb * 24, (void **)&d_lik) || scratch(e, SC_HG_OFF, (size_t)n_tables * 16, (void **)&d_start) ||
+        scratch(e, SC_HG_STATE, (size_t)nb + (size_t)n_tables, (void **)&d_state) || scratch(e, SC_HG_SCORE, (size_t)nb * 24, (void **)&d_score) ||
         scratch(e, SC_HG_COUNTS, (size_t)n_tables * 24, (void **)&d_counts))
         return 1;
-    IBD_CUDA(cudaMemcpyAsync(d_lik, lik, (size_t)nb * 24, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_off, bin_offsets, (size_t)(n_tables + 1) * 8, cudaMemcpyHostToDevice, e->stream));
-    int64_t maxbins = 0;
-    for (int t = 0; t < n_tables; t++) maxbins = std::max<int64_t>(maxbins, bin_offsets[t + 1] - bin_offsets[t]);
-    const bool batched = n_tables >= 64 && (double)maxbins * n_tables <= 2.0 * (double)nb;
-    if (batched) {
-        double *d_nrmT, *d_scoreT, *d_last;
-        uint8_t *d_fromT;
-        const size_t cells = (size_t)maxbins * n_tables;
-        if (scratch(e, SC_HG_NRMT, cells * 24, (void **)&d_nrmT) || scratch(e, SC_HG_SCORET, cells * 24, (void **)&d_scoreT) ||
-            scratch(e, SC_HG_FROMT, cells, (void **)&d_fromT) || scratch(e, SC_HG_LAST, (size_t)n_tables * 24, (void **)&d_last))
-            return 1;
-        const dim3 tiles((unsigned)((n_tables + 31) / 32), (unsigned)((maxbins + 31) / 32));
-        {
-            LaunchScope ls(e, K_VITERBI_NORM);
-            viterbi_norm_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, maxbins, d_off, d_lik, is_log, d_nrmT);
-        }
-        {
-            LaunchScope ls(e, K_VITERBI);
-            viterbi_forward_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_off, d_nrmT, log(p01), log(p02), log(p12),
-                                                                             d_fromT, d_scoreT, d_last);
-        }
-        {
-            LaunchScope ls(e, K_VITERBI_BACK);
-            viterbi_back_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_off, d_fromT, d_last, d_counts);
-        }
-        {
-            LaunchScope ls(e, K_VITERBI_OUT);
-            viterbi_out_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, d_off, d_fromT, d_scoreT, d_state, d_score);
-        }
-    } else {
-        LaunchScope ls(e, K_VITERBI);
-        viterbi_kernel<<<(n_tables + 127) / 128, 128, 0, e->stream>>>(n_tables, d_off, d_lik, is_log, log(p01), log(p02),
-                                                                     log(p12), d_state, d_score, d_counts);
+    d_flag = d_state + nb;
+    int64_t *d_len = d_start + n_tables;
+    std::vector<int64_t> h_sl((size_t)n_tables * 2);
+    for (int t = 0; t < n_tables; t++) {
+        h_sl[(size_t)t] = bin_offsets[t];
+        h_sl[(size_t)n_tables + t] = bin_offsets[t + 1] - bin_offsets[t];
     }
+    if (!e->copy_stream) {
+        IBD_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        IBD_CUDA(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
+    }
+    if (!e->d2h_stream) IBD_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    IBD_CUDA(cudaMemcpyAsync(d_start, h_sl.data(), h_sl.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    // earlier work on the engine stream may still use the scratch buffers: the side streams start after it
+    IBD_CUDA(cudaEventRecord(e->ev_order, e->stream));
+    IBD_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_order, 0));
+    IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->ev_order, 0));
+    // batches of whole tables, ~192 MB of likelihoods each (3.5 ms of PCIe), at least 64 tables so the batched kernels apply
+    const int64_t target_bins = (int64_t)8 << 20;
+    std::vector<int> cuts{0};
+    for (int t = 0; t < n_tables;) {
+        int t1 = t;
+        while (t1 < n_tables && (t1 - t < 64 || bin_offsets[t1] - bin_offsets[t] < target_bins)) t1++;
+        if (n_tables - t1 < 64) t1 = n_tables;  // no runt batch at the end
+        cuts.push_back(t1);
+        t = t1;
+    }
+    const size_t nbatch = cuts.size() - 1;
+    std::vector<cudaEvent_t> ev_up(nbatch), ev_done(nbatch);
+    for (size_t b = 0; b < nbatch; b++) {
+        IBD_CUDA(cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming));
+        IBD_CUDA(cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming));
+    }
+    int rc = 0;
+    for (size_t b = 0; b < nbatch && !rc; b++) {
+        const int t0 = cuts[b], t1 = cuts[b + 1];
+        const int64_t b0 = bin_offsets[t0], b1 = bin_offsets[t1];
+        IBD_CUDA(cudaMemcpyAsync(d_lik + b0 * 3, lik + b0 * 3, (size_t)(b1 - b0) * 24, cudaMemcpyHostToDevice, e->copy_stream));
+        IBD_CUDA(cudaEventRecord(ev_up[b], e->copy_stream));
+    }
+    for (size_t b = 0; b < nbatch && !rc; b++) {
+        const int t0 = cuts[b], t1 = cuts[b + 1];
+        const int64_t b0 = bin_offsets[t0], b1 = bin_offsets[t1];
+        int64_t maxbins = 0;
+        for (int t = t0; t < t1; t++) maxbins = std::max<int64_t>(maxbins, bin_offsets[t + 1] - bin_offsets[t]);
+        IBD_CUDA(cudaStreamWaitEvent(e->stream, ev_up[b], 0));
+        rc = viterbi_on_device(e, t1 - t0, maxbins, b1 - b0, d_start + t0, d_len + t0, d_lik, is_log, p01, p02, p12, d_state, d_score,
+                               d_counts + (size_t)t0 * 3, d_flag + t0);
+        if (rc) break;
+        IBD_CUDA(cudaEventRecord(ev_done[b], e->stream));
+        IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, ev_done[b], 0));
+        if (state) IBD_CUDA(cudaMemcpyAsync(state + b0, d_state + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, e->d2h_stream));
+        if (score_log) IBD_CUDA(cudaMemcpyAsync(score_log + b0 * 3, d_score + b0 * 3, (size_t)(b1 - b0) * 24, cudaMemcpyDeviceToHost, e->d2h_stream));
+    }
+    std::vector<uint8_t> h_flag((size_t)n_tables, 0);
+    std::vector<long long> h_counts((size_t)n_tables * 3);
+    if (!rc) {
+        IBD_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts, (size_t)n_tables * 24, cudaMemcpyDeviceToHost, e->stream));
+        IBD_CUDA(cudaMemcpyAsync(h_flag.data(), d_flag, (size_t)n_tables, cudaMemcpyDeviceToHost, e->stream));
+    }
+    cudaStreamSynchronize(e->copy_stream);
+    cudaStreamSynchronize(e->stream);
+    cudaStreamSynchronize(e->d2h_stream);
+    for (size_t b = 0; b < nbatch; b++) {
+        cudaEventDestroy(ev_up[b]);
+        cudaEventDestroy(ev_done[b]);
+    }
+    if (rc) return 1;
     IBD_CUDA(cudaGetLastError());
-    if (state) IBD_CUDA(cudaMemcpyAsync(state, d_state, (size_t)nb, cudaMemcpyDeviceToHost, e->stream));
-    if (score_log) IBD_CUDA(cudaMemcpyAsync(score_log, d_score, (size_t)nb * 24, cudaMemcpyDeviceToHost, e->stream));
-    if (state_counts) IBD_CUDA(cudaMemcpyAsync(state_counts, d_counts, (size_t)n_tables * 24, cudaMemcpyDeviceToHost, e->stream));
-    IBD_CUDA(cudaStreamSynchronize(e->stream));
     resolve_timers(e);
+    // flagged tables: the reference's long double recurrence decides
+    e->hg_flagged = 0;
+    std::vector<uint8_t> st_tmp;
+    std::vector<double> sc_tmp;
+    for (int t = 0; t < n_tables; t++) {
+        int64_t c[3] = {h_counts[(size_t)t * 3], h_counts[(size_t)t * 3 + 1], h_counts[(size_t)t * 3 + 2]};
+        if (h_flag[(size_t)t]) {
+            const int64_t b0 = bin_offsets[t], n = bin_offsets[t + 1] - b0;
+            st_tmp.resize((size_t)n);
+            sc_tmp.resize((size_t)n * 3);
+            viterbi_long_double(lik + b0 * 3, n, is_log, p01, p02, p12, st_tmp.data(), sc_tmp.data(), c);
+            if (state) memcpy(state + b0, st_tmp.data(), (size_t)n);
+            if (score_log) memcpy(score_log + b0 * 3, sc_tmp.data(), (size_t)n * 24);
+            e->hg_flagged++;
+        }
+        if (state_counts) {
+            state_counts[(size_t)t * 3] = c[0];
+            state_counts[(size_t)t * 3 + 1] = c[1];
+            state_counts[(size_t)t * 3 + 2] = c[2];
+        }
+    }
     return 0;
 }
+
+// Device buffers in, device buffers out: the hiddengem front-end for scores that never left the GPU.
+//   table_stride = 0: tables are packed, table t holds bins [bin_offsets[t], bin_offsets[t+1]) of d_lik / d_state / d_score;
+//   table_stride > 0: table t starts at bin t * table_stride (the layout of ibdgem_scores.w_loglik_device with
+//                     table_stride = max_windows) and has bin_offsets[t+1] - bin_offsets[t] bins.
+// bin_offsets is a HOST array.  Flagged tables (near-ties) are re-evaluated on the host in long double and patched
+// back into the device buffers.
+extern "C" int hiddengem_viterbi_batch_device(ibdgem_engine *e, int32_t n_tables, const int64_t *bin_offsets, int64_t table_stride,
+                                              const double *d_lik, int32_t is_log, double p01, double p02, double p12,
+                                              uint8_t *d_state, double *d_score_log, int64_t *d_state_counts) {
+    if (!e || n_tables <= 0 || !bin_offsets || !d_lik || !d_state || !d_score_log || !d_state_counts || table_stride < 0) {
+        set_error("[::] ERROR in hiddengem_viterbi_batch_device(): bad arguments.");
+        return 1;
+    }
+    IBD_CUDA(cudaSetDevice(e->device));
+    std::vector<int64_t> h_sl((size_t)n_tables * 2);
+    int64_t maxbins = 0, total = 0;
+    for (int t = 0; t < n_tables; t++) {
+        const int64_t n = bin_offsets[t + 1] - bin_offsets[t];
+        if (n < 0 || (table_stride > 0 && n > table_stride)) {
+            set_error("[::] ERROR in hiddengem_viterbi_batch_device(): table %d has %lld bins (stride %lld).", t, (long long)n, (long long)table_stride);
+            return 1;
+        }
+        h_sl[(size_t)t] = table_stride > 0 ? (int64_t)t * table_stride : bin_offsets[t];
+        h_sl[(size_t)n_tables + t] = n;
+        maxbins = std::max(maxbins, n);
+        total += n;
+    }
+    if (total <= 0) {
+        set_error("[::] ERROR parsing likelihood data; make sure input is valid.");
+        return 1;
+    }
+    int64_t *d_start;
+    uint8_t *d_flag;
+    if (scratch(e, SC_HG_OFF, (size_t)n_tables * 16, (void **)&d_start) || scratch(e, SC_HG_STATE, (size_t)n_tables, (void **)&d_flag)) return 1;
+    IBD_CUDA(cudaMemcpyAsync(d_start, h_sl.data(), h_sl.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    static_assert(sizeof(long long) == sizeof(int64_t), "state counts are 64-bit");
+    if (viterbi_on_device(e, n_tables, maxbins, total, d_start, d_start + n_tables, d_lik, is_log, p01, p02, p12, d_state, d_score_log,
+                          reinterpret_cast<long long *>(d_state_counts), d_flag))
+        return 1;
+    std::vector<uint8_t> h_flag((size_t)n_tables);
+    IBD_CUDA(cudaMemcpyAsync(h_flag.data(), d_flag, (size_t)n_tables, cudaMemcpyDeviceToHost, e->stream));
+    IBD_CUDA(cudaStreamSynchronize(e->stream));
+    resolve_timers(e);
+    e->hg_flagged = 0;
+    for (int t = 0; t < n_tables; t++) {
+        if (!h_flag[(size_t)t]) continue;
+        const int64_t b0 = h_sl[(size_t)t], n = h_sl[(size_t)n_tables + t];
+        std::vector<double> l((size_t)n * 3), sc((size_t)n * 3);
+        std::vector<uint8_t> st((size_t)n);
+        int64_t c[3];
+        IBD_CUDA(cudaMemcpy(l.data(), d_lik + b0 * 3, (size_t)n * 24, cudaMemcpyDeviceToHost));
+        viterbi_long_double(l.data(), n, is_log, p01, p02, p12, st.data(), sc.data(), c);
+        IBD_CUDA(cudaMemcpy(d_state + b0, st.data(), (size_t)n, cudaMemcpyHostToDevice));
+        IBD_CUDA(cudaMemcpy(d_score_log + b0 * 3, sc.data(), (size_t)n * 24, cudaMemcpyHostToDevice));
+        IBD_CUDA(cudaMemcpy(d_state_counts + (size_t)t * 3, c, 24, cudaMemcpyHostToDevice));
+        e->hg_flagged++;
+    }
+    return 0;
+}
+
+// Tables of the last hiddengem call that were re-evaluated on the host in long double (near-tie guard).
+extern "C" int64_t hiddengem_last_flagged(ibdgem_engine *e) { return e ? e->hg_flagged : -1; }

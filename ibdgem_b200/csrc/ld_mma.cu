@@ -1221,12 +1221,14 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     if (w_hi == w_lo) continue;
     if (cache_windows(e, w_hi)) return 1;
     {
+        // (a window shard still reports the bookkeeping of ALL windows: it is the same on every rank)
         LaunchScope ls(e, K_LD_WINDOWS);
-        const int64_t n = (int64_t)T * (w_hi - w_lo);
+        const int b_lo = sharded ? 0 : w_lo, b_hi = sharded ? nW : w_hi;
+        const int64_t n = (int64_t)T * (b_hi - b_lo);
         ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-            w_lo, w_hi, T, nW, outW, c->W, c->K, e->d_wfirst, e->d_wlast, e->d_pos, d_wn, d_ws, d_we, d_nwout);
+            b_lo, b_hi, T, nW, outW, c->W, c->K, e->d_wfirst, e->d_wlast, e->d_pos, d_wn, d_ws, d_we, d_nwout);
     }
-    if (w_hi == nW && e->ev_book) {  // START / END / NUM_SITES of every window are final: their copy to the
+    if ((w_hi == nW || sharded) && e->ev_book) {  // START / END / NUM_SITES of every window are final: their copy to the
         IBD_CUDA(cudaEventRecord(e->ev_book, e->stream));  // host can overlap the GEMM (score_common)
         e->book_ready = true;
     }

@@ -230,6 +230,19 @@ class Engine:
                                                       C.c_double(p12), C.c_void_p(state_ptr), C.c_void_p(score_ptr),
                                                       C.c_void_p(counts_ptr)))
 
+    def viterbi_batch_device(self, d_lik_ptr: int, bin_offsets: np.ndarray, is_log: bool, d_state_ptr: int, d_score_ptr: int,
+                             d_counts_ptr: int, table_stride: int = 0, p01=1e-3, p02=1e-6, p12=1e-3):
+        """Device buffers in, device buffers out (hiddengem_viterbi_batch_device); bin_offsets stays on the host."""
+        off = np.ascontiguousarray(bin_offsets, np.int64)
+        self._check(self._lib.hiddengem_viterbi_batch_device(
+            self._h, C.c_int32(len(off) - 1), _ptr(off), C.c_int64(table_stride), C.c_void_p(d_lik_ptr),
+            C.c_int32(1 if is_log else 0), C.c_double(p01), C.c_double(p02), C.c_double(p12), C.c_void_p(d_state_ptr),
+            C.c_void_p(d_score_ptr), C.c_void_p(d_counts_ptr)))
+
+    def viterbi_last_flagged(self) -> int:
+        """Tables of the last hiddengem call re-evaluated on the host in long double (near-tie guard)."""
+        return int(self._lib.hiddengem_last_flagged(self._h))
+
     # -- instrumentation --------------------------------------------------------------------
     def enable_timing(self, on=True):
         self._check(self._lib.ibdgem_engine_enable_timing(self._h, C.c_int(1 if on else 0)))

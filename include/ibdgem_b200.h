@@ -207,6 +207,21 @@ int hiddengem_viterbi_batch(ibdgem_engine *e, int32_t n_tables, const int64_t *b
                             const double *lik, int32_t is_log, double p01, double p02, double p12,
                             uint8_t *state, double *score_log, int64_t *state_counts);
 
+/* The same on DEVICE buffers (window scores that never left the GPU are not re-parsed from 7-digit
+ * text, src/hiddengem.c:66-76).  d_lik / d_state / d_score_log / d_state_counts are device pointers on the engine's
+ * GPU; bin_offsets is a HOST array of n_tables + 1 prefix offsets.
+ *   table_stride = 0   tables are packed: table t holds bins [bin_offsets[t], bin_offsets[t+1]) of every array;
+ *   table_stride > 0   table t starts at bin t * table_stride and has bin_offsets[t+1] - bin_offsets[t] bins — with
+ *                      table_stride = max_windows and is_log = 1 this consumes ibdgem_scores.w_loglik_device as is. */
+int hiddengem_viterbi_batch_device(ibdgem_engine *e, int32_t n_tables, const int64_t *bin_offsets, int64_t table_stride,
+                                   const double *d_lik, int32_t is_log, double p01, double p02, double p12,
+                                   uint8_t *d_state, double *d_score_log, int64_t *d_state_counts);
+/* Near-tie guard: the recursion runs on sums of fp64 logarithms where the reference multiplies x87 long doubles
+ * (src/hiddengem.c:43, 110-141).  A table in which some arg-max is decided by less than the rounding error those sums
+ * can have accumulated — or, on the text path, whose scores leave the range of a normal long double — is re-evaluated
+ * on the host with the reference's own long double recurrence.  Returns how many tables of the last call were. */
+int64_t hiddengem_last_flagged(ibdgem_engine *e);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 
 /* When enabled every kernel launch is bracketed by CUDA events on the engine stream. */
