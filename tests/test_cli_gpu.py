@@ -169,3 +169,72 @@ def test_hiddengem_several_tables_in_one_call(golden_dir):
         args += ["-s", f]
     together = _run("hiddengem", args).stdout
     assert together == single[0] + single[1] + single[2] + single[1] + single[0]
+
+
+def _write_summary(path, l):
+    with open(path, "w") as fh:
+        fh.write("# SEGMENT\tSTART\tEND\tLIBD0\tLIBD1\tLIBD2\tNUM_SITES\n")
+        for i, (a, b, c) in enumerate(l):
+            fh.write("%d\t%d\t%d\t%e\t%e\t%e\t100\n" % (i + 1, 1000 + 6000 * i, 6940 + 6000 * i, a, b, c))
+
+
+def _ref_hiddengem(path, args):
+    import oracle
+    ref = os.path.join(oracle.REF_DIR, "hiddengem")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/hiddengem is not built")
+    r = subprocess.run([ref, "-s", path] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def _states(text):
+    rows = [ln.split("\t") for ln in text.splitlines()[1:] if not ln.startswith("#")]
+    return [r[4] for r in rows], [ln for ln in text.splitlines() if ln.startswith("#")]
+
+
+@pytest.mark.parametrize("pen", [["--p01", "0.5", "--p02", "0.25", "--p12", "0.5"], ["--p01", "1", "--p02", "1", "--p12", "1"], []])
+def test_hiddengem_adversarial_ties_against_the_reference_binary(tmp_path, pen):
+    """Likelihoods from a small dyadic set and power-of-two penalties: the reference's long double products are
+    exact, so its arg-max sees many EXACT ties (lowest index wins), where sums of fp64 logarithms differ in the
+    last bits.  The near-tie guard must hand such tables to the long double recurrence: Inferred_State and the
+    state counts are compared with the unmodified reference binary run here."""
+    import numpy as np
+    rng = np.random.default_rng(17)
+    vals = np.array([2.0 ** -k for k in range(4, 12)] + [3 * 2.0 ** -9, 5 * 2.0 ** -10])
+    files = []
+    for k, n in enumerate((40, 300, 2500)):
+        l = vals[rng.integers(0, len(vals), (n, 3))]
+        if k == 1:
+            l[7] = l[8] = [2.0 ** -6] * 3  # identical columns: every candidate ties
+        p = str(tmp_path / f"tie{k}.summary.txt")
+        _write_summary(p, l)
+        files.append(p)
+    for p in files:
+        want = _ref_hiddengem(p, pen)
+        got = _run("hiddengem", ["-s", p] + pen).stdout
+        ws, wc = _states(want)
+        gs, gc = _states(got)
+        assert gs == ws and gc == wc
+
+
+def test_hiddengem_long_table_past_the_long_double_range(tmp_path):
+    """12,000 nearly flat bins: the reference's running products pass below LDBL_MIN around bin 10,300, lose bits and
+    end at 0.00000e+00 with every later tie resolved to state 0.  Tables whose scores leave the normal long double
+    range are re-evaluated with the reference's own recurrence, so states and counts still agree."""
+    import numpy as np
+    rng = np.random.default_rng(23)
+    n = 12000
+    l = 1e-3 * (1.0 + 0.01 * rng.random((n, 3)))
+    seg = np.repeat(rng.integers(0, 3, n // 100 + 1), 100)[:n]
+    l[np.arange(n), seg] *= 1.05
+    p = str(tmp_path / "long.summary.txt")
+    _write_summary(p, l)
+    want = _ref_hiddengem(p, [])
+    got = _run("hiddengem", ["-s", p]).stdout
+    ws, wc = _states(want)
+    gs, gc = _states(got)
+    assert "0.00000e+00" in want  # the reference did underflow
+    assert gs == ws and gc == wc
+    exact = sum(a == b for a, b in zip(got.splitlines(), want.splitlines()))
+    assert exact >= 0.9 * n

@@ -596,3 +596,70 @@ def test_c3_variable_sites_full_size_spot_checks_against_oracle():
             o = oracle.compare_target(prm, pos[sl], keep[sl], n_ref[sl], n_alt[sl], hap, int(t), bg)
             assert o["n_windows"] == 1 and int(o["w_nsites"][0]) == int(sc.w_nsites[t, w])
             np.testing.assert_allclose(sc.w_loglik[t, w], o["w_log"][0], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_tables", [5, 96])
+def test_hiddengem_device_entry_matches_host_entry(n_tables):
+    """hiddengem_viterbi_batch_device: packed tables, and tables at a fixed stride exactly as score_ld leaves them in
+    ibdgem_scores.w_loglik_device ([T][max_windows][3] natural logs, rows past n_windows NaN)."""
+    import torch
+    import ibdgem_b200 as ib
+    import oracle
+    rng = np.random.default_rng(31)
+    lens = rng.integers(300, 500, n_tables)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    nb = int(off[-1])
+    ll = rng.normal(-200, 30, (nb, 3))
+    seg = np.repeat(rng.integers(0, 3, nb // 25 + 1), 25)[:nb]
+    ll[np.arange(nb), seg] += 5.0
+    stride = 512
+    strided = np.full((n_tables, stride, 3), np.nan)
+    for t in range(n_tables):
+        strided[t, : lens[t]] = ll[off[t]: off[t + 1]]
+    with ib.Engine(ib.Params()) as e:
+        st_h, sc_h, cnt_h = e.viterbi_batch(ll, off, True)
+        d_ll = torch.from_numpy(ll).cuda()
+        d_state = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+        d_score = torch.zeros((nb, 3), dtype=torch.float64, device="cuda")
+        d_cnt = torch.zeros((n_tables, 3), dtype=torch.int64, device="cuda")
+        e.viterbi_batch_device(d_ll.data_ptr(), off, True, d_state.data_ptr(), d_score.data_ptr(), d_cnt.data_ptr())
+        np.testing.assert_array_equal(d_state.cpu().numpy(), st_h)
+        np.testing.assert_array_equal(d_cnt.cpu().numpy(), cnt_h)
+        np.testing.assert_allclose(d_score.cpu().numpy(), sc_h, rtol=0, atol=1e-9)
+        d_str = torch.from_numpy(strided).cuda()
+        d_state2 = torch.full((n_tables, stride), 9, dtype=torch.uint8, device="cuda")
+        d_score2 = torch.zeros((n_tables, stride, 3), dtype=torch.float64, device="cuda")
+        d_cnt.zero_()
+        e.viterbi_batch_device(d_str.data_ptr(), off, True, d_state2.data_ptr(), d_score2.data_ptr(), d_cnt.data_ptr(), table_stride=stride)
+        s2 = d_state2.cpu().numpy()
+        np.testing.assert_array_equal(d_cnt.cpu().numpy(), cnt_h)
+        for t in range(n_tables):
+            np.testing.assert_array_equal(s2[t, : lens[t]], st_h[off[t]: off[t + 1]])
+            assert (s2[t, lens[t]:] == 9).all()  # nothing is written past a table's bins
+    for t in (0, n_tables - 1):
+        st, sc, _ = oracle.hiddengem(np.exp(ll[off[t]: off[t + 1]]))
+        np.testing.assert_array_equal(st_h[off[t]: off[t + 1]], st)
+
+
+def test_hiddengem_near_tie_guard_flags_and_matches_long_double():
+    """Dyadic likelihoods and power-of-two penalties make exact ties in the reference's long double products; the
+    device flags those tables and the host long double recurrence decides them (oracle: long double restatement)."""
+    import ibdgem_b200 as ib
+    import oracle
+    rng = np.random.default_rng(41)
+    vals = np.array([2.0 ** -k for k in range(4, 12)])
+    tables, offs = [], [0]
+    for n in [50] * 70 + [700]:
+        tables.append(vals[rng.integers(0, len(vals), (n, 3))])
+        offs.append(offs[-1] + n)
+    lik = np.concatenate(tables)
+    pen = (0.5, 0.25, 0.5)
+    with ib.Engine(ib.Params()) as e:
+        state, score, counts = e.viterbi_batch(lik, offs, False, *pen)
+        assert e.viterbi_last_flagged() > 0
+    for i, l in enumerate(tables):
+        st, sc, _ = oracle.hiddengem(l, *pen)
+        a, b = offs[i], offs[i + 1]
+        np.testing.assert_array_equal(state[a:b], st)
+        np.testing.assert_array_equal(counts[i], np.bincount(st, minlength=3))
+        np.testing.assert_allclose(score[a:b], sc, rtol=0, atol=1e-7)
