@@ -8,6 +8,7 @@
 // src/hiddengem.c:91-99).  Zeros become -inf and NaN rows (0/0, src/hiddengem.c:74-76)
 // propagate exactly as they do through the products.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -292,6 +293,164 @@ viterbi_out_kernel(int n_tables, const int64_t *__restrict__ start, const int64_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused forward pass for large batches (C4: 10,000 tables x 10,000 bins): one read of the likelihoods, one write of
+// the scores.  A block takes 32 tables.  Four worker warps move 16-bin chunks between global memory and shared
+// memory with coalesced accesses (a table's chunk is 384 contiguous bytes) and turn the likelihoods into ln nrm
+// there — that is where the fp64 exp / log work is, and it is parallel over bins; ONE solver warp (lane = table)
+// walks the chunk sequentially, which the recursion demands, touching shared memory only.  Chunks are double
+// buffered, so loads, normalisation, recursion and stores of neighbouring chunks overlap.  The arithmetic is that
+// of viterbi_kernel, operation for operation.  Back-pointers leave bin-major (coalesced over tables) for
+// viterbi_back_kernel; scores leave in the caller's table-major layout.
+constexpr int VF_TABLES = 32, VF_BINS = 16, VF_ROW = VF_BINS * 3 + 1;  // padded row: lanes hit distinct banks
+constexpr int VF_WORKERS = 128, VF_THREADS = VF_WORKERS + 32;
+constexpr int VF_SMEM = 4 * VF_TABLES * VF_ROW * 8 + 2 * VF_TABLES * 8 + 2 * VF_BINS * VF_TABLES;
+__global__ void __launch_bounds__(VF_THREADS, 3)
+viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ start, const int64_t *__restrict__ len,
+                     const double *__restrict__ lik, int is_log, double lp01, double lp02, double lp12, double *__restrict__ score,
+                     uint8_t *__restrict__ fromT /*[maxbins][n_tables]*/, double *__restrict__ last /*[n_tables][3]*/,
+                     uint8_t *__restrict__ flag) {
+    extern __shared__ double vf_smem[];
+    double (*nrm)[VF_TABLES][VF_ROW] = reinterpret_cast<double (*)[VF_TABLES][VF_ROW]>(vf_smem);
+    double (*sco)[VF_TABLES][VF_ROW] = reinterpret_cast<double (*)[VF_TABLES][VF_ROW]>(vf_smem + 2 * VF_TABLES * VF_ROW);
+    int64_t *s_start = reinterpret_cast<int64_t *>(vf_smem + 4 * VF_TABLES * VF_ROW), *s_len = s_start + VF_TABLES;
+    uint8_t (*frm)[VF_BINS][VF_TABLES] = reinterpret_cast<uint8_t (*)[VF_BINS][VF_TABLES]>(s_len + VF_TABLES);
+    const int tb0 = blockIdx.x * VF_TABLES;
+    if (threadIdx.x < VF_TABLES) {
+        const int tb = tb0 + threadIdx.x;
+        s_start[threadIdx.x] = tb < n_tables ? start[tb] : 0;
+        s_len[threadIdx.x] = tb < n_tables ? len[tb] : 0;
+    }
+    __syncthreads();
+    int64_t blk_bins = 0;
+    for (int k = 0; k < VF_TABLES; k++) blk_bins = max(blk_bins, s_len[k]);
+    const int nchunk = (int)((blk_bins + VF_BINS - 1) / VF_BINS);
+    // named barriers: 1 + b = chunk in buffer b is normalised (workers arrive, solver syncs);
+    //                 3 + b = chunk in buffer b is solved (solver arrives, workers sync); 5 = workers only
+    if (threadIdx.x >= 32) {
+        // ===== workers =====
+        const int w = threadIdx.x - 32;
+        for (int c = 0; c <= nchunk; c++) {
+            const int b = c & 1;
+            if (c < nchunk) {
+                const int64_t i0 = (int64_t)c * VF_BINS;
+                // raw likelihoods, coalesced: 32 tables x 48 doubles
+#pragma unroll
+                for (int k = 0; k < VF_TABLES * VF_BINS * 3 / VF_WORKERS; k++) {
+                    const int idx = k * VF_WORKERS + w;
+                    const int t = idx / (VF_BINS * 3), d = idx % (VF_BINS * 3);
+                    double x = 0.0;
+                    if (i0 + d / 3 < s_len[t]) x = __ldcs(lik + (s_start[t] + i0) * 3 + d);
+                    nrm[b][t][d] = x;
+                }
+                asm volatile("bar.sync 5, %0;" ::"n"(VF_WORKERS) : "memory");
+                // ln nrm in place: 512 bins, 4 per worker
+#pragma unroll
+                for (int k = 0; k < VF_TABLES * VF_BINS / VF_WORKERS; k++) {
+                    const int idx = k * VF_WORKERS + w;
+                    const int t = idx / VF_BINS, i = idx % VF_BINS;
+                    if (i0 + i < s_len[t]) {
+                        const double v[3] = {nrm[b][t][i * 3], nrm[b][t][i * 3 + 1], nrm[b][t][i * 3 + 2]};
+                        double n0, n1, n2;
+                        ln_nrm(v, is_log, n0, n1, n2);
+                        nrm[b][t][i * 3] = n0;
+                        nrm[b][t][i * 3 + 1] = n1;
+                        nrm[b][t][i * 3 + 2] = n2;
+                    }
+                }
+                __threadfence_block();
+                if (b == 0) asm volatile("bar.arrive 1, %0;" ::"n"(VF_THREADS) : "memory");
+                else asm volatile("bar.arrive 2, %0;" ::"n"(VF_THREADS) : "memory");
+            }
+            if (c >= 1) {  // drain the chunk the solver has just finished
+                const int pb = (c - 1) & 1;
+                if (pb == 0) asm volatile("bar.sync 3, %0;" ::"n"(VF_THREADS) : "memory");
+                else asm volatile("bar.sync 4, %0;" ::"n"(VF_THREADS) : "memory");
+                const int64_t i0 = (int64_t)(c - 1) * VF_BINS;
+#pragma unroll
+                for (int k = 0; k < VF_TABLES * VF_BINS * 3 / VF_WORKERS; k++) {
+                    const int idx = k * VF_WORKERS + w;
+                    const int t = idx / (VF_BINS * 3), d = idx % (VF_BINS * 3);
+                    if (i0 + d / 3 < s_len[t]) __stcs(score + (s_start[t] + i0) * 3 + d, sco[pb][t][d]);
+                }
+#pragma unroll
+                for (int k = 0; k < VF_TABLES * VF_BINS / VF_WORKERS; k++) {
+                    const int idx = k * VF_WORKERS + w;
+                    const int i = idx / VF_TABLES, t = idx % VF_TABLES;
+                    if (tb0 + t < n_tables && i0 + i < s_len[t]) fromT[(size_t)(i0 + i) * n_tables + tb0 + t] = frm[pb][i][t];
+                }
+                asm volatile("bar.sync 5, %0;" ::"n"(VF_WORKERS) : "memory");  // buffer pb is free for chunk c + 1
+            }
+        }
+    } else {
+        // ===== solver: lane = table =====
+        const int lane = threadIdx.x;
+        const int64_t n = s_len[lane];
+        double s0 = 0, s1 = 0, s2 = 0;
+        bool tie = false;
+        for (int c = 0; c < nchunk; c++) {
+            const int b = c & 1;
+            if (b == 0) asm volatile("bar.sync 1, %0;" ::"n"(VF_THREADS) : "memory");
+            else asm volatile("bar.sync 2, %0;" ::"n"(VF_THREADS) : "memory");
+            const int64_t i0 = (int64_t)c * VF_BINS;
+#pragma unroll 4
+            for (int q = 0; q < VF_BINS; q++) {
+                const int64_t i = i0 + q;
+                if (i < n) {
+                    const double n0 = nrm[b][lane][q * 3], n1 = nrm[b][lane][q * 3 + 1], n2 = nrm[b][lane][q * 3 + 2];
+                    uint8_t from;
+                    if (i == 0) {
+                        s0 = n0; s1 = n1; s2 = n2;
+                        from = 0 | (1 << 2) | (2 << 4);
+                    } else {
+                        const double a0 = s0 + n0, a1 = (s1 + n0) + lp01, a2 = (s2 + n0) + lp02;
+                        const double b0 = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
+                        const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
+                        const int k0 = argmax3(a0, a1, a2), k1 = argmax3(b0, b1, b2), k2 = argmax3(c0, c1, c2);
+                        tie |= near_tie(a0, a1, a2, k0, i) | near_tie(b0, b1, b2, k1, i) | near_tie(c0, c1, c2, k2, i);
+                        s0 = k0 == 0 ? a0 : (k0 == 1 ? a1 : a2);
+                        s1 = k1 == 0 ? b0 : (k1 == 1 ? b1 : b2);
+                        s2 = k2 == 0 ? c0 : (k2 == 1 ? c1 : c2);
+                        from = (uint8_t)(k0 | (k1 << 2) | (k2 << 4));
+                    }
+                    if (!is_log) tie |= below_ldbl(s0, s1, s2);
+                    sco[b][lane][q * 3] = s0;
+                    sco[b][lane][q * 3 + 1] = s1;
+                    sco[b][lane][q * 3 + 2] = s2;
+                    frm[b][q][lane] = from;
+                }
+            }
+            __threadfence_block();
+            if (b == 0) asm volatile("bar.arrive 3, %0;" ::"n"(VF_THREADS) : "memory");
+            else asm volatile("bar.arrive 4, %0;" ::"n"(VF_THREADS) : "memory");
+        }
+        const int tb = tb0 + lane;
+        if (tb < n_tables) {
+            last[(size_t)tb * 3 + 0] = s0;
+            last[(size_t)tb * 3 + 1] = s1;
+            last[(size_t)tb * 3 + 2] = s2;
+            if (n > 0) tie |= near_tie(s0, s1, s2, argmax3(s0, s1, s2), n);
+            flag[tb] = tie ? 1 : 0;
+        }
+    }
+}
+
+// states of the back-trace (bin-major) -> the caller's table-major layout
+__global__ void __launch_bounds__(1024)
+viterbi_state_out_kernel(int n_tables, const int64_t *__restrict__ start, const int64_t *__restrict__ len, const uint8_t *__restrict__ stateT,
+                         uint8_t *__restrict__ state) {
+    __shared__ uint8_t st[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int t_in = blockIdx.x * 32 + tx;
+    const int64_t i_in = (int64_t)blockIdx.y * 32 + ty;
+    if (t_in < n_tables && i_in < len[t_in]) st[ty][tx] = stateT[(size_t)i_in * n_tables + t_in];
+    __syncthreads();
+    const int t_out = blockIdx.x * 32 + ty;
+    const int64_t i_out = (int64_t)blockIdx.y * 32 + tx;
+    if (t_out < n_tables && i_out < len[t_out]) state[start[t_out] + i_out] = st[tx][ty];
+}
+
 }  // namespace ibdgem
 
 using namespace ibdgem;
@@ -376,29 +535,47 @@ int viterbi_on_device(ibdgem_engine *e, int n_tables, int64_t maxbins, int64_t t
                       long long *d_counts, uint8_t *d_flag) {
     const bool batched = n_tables >= 64 && (double)maxbins * n_tables <= 2.0 * (double)total_bins;
     if (batched) {
-        double *d_nrmT, *d_scoreT, *d_last;
+        double *d_last;
         uint8_t *d_fromT;
         const size_t cells = (size_t)maxbins * n_tables;
-        if (scratch(e, SC_HG_NRMT, cells * 24, (void **)&d_nrmT) || scratch(e, SC_HG_SCORET, cells * 24, (void **)&d_scoreT) ||
-            scratch(e, SC_HG_FROMT, cells, (void **)&d_fromT) || scratch(e, SC_HG_LAST, (size_t)n_tables * 24, (void **)&d_last))
-            return 1;
+        static const int fused = [] { const char *s = getenv("IBDGEM_VITERBI_FUSED"); return s ? atoi(s) : 1; }();
+        if (scratch(e, SC_HG_FROMT, cells, (void **)&d_fromT) || scratch(e, SC_HG_LAST, (size_t)n_tables * 24, (void **)&d_last)) return 1;
         const dim3 tiles((unsigned)((n_tables + 31) / 32), (unsigned)((maxbins + 31) / 32));
-        {
-            LaunchScope ls(e, K_VITERBI_NORM);
-            viterbi_norm_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, maxbins, d_start, d_len, d_lik, is_log, d_nrmT);
-        }
-        {
-            LaunchScope ls(e, K_VITERBI);
-            viterbi_forward_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_len, is_log, d_nrmT, log(p01), log(p02), log(p12),
-                                                                             d_fromT, d_scoreT, d_last, d_flag);
-        }
-        {
-            LaunchScope ls(e, K_VITERBI_BACK);
-            viterbi_back_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_len, d_fromT, d_last, d_counts);
-        }
-        {
-            LaunchScope ls(e, K_VITERBI_OUT);
-            viterbi_out_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, d_start, d_len, d_fromT, d_scoreT, d_state, d_score);
+        if (fused) {
+            {
+                LaunchScope ls(e, K_VITERBI);
+                IBD_CUDA(cudaFuncSetAttribute(viterbi_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VF_SMEM));
+                viterbi_fused_kernel<<<(n_tables + VF_TABLES - 1) / VF_TABLES, VF_THREADS, VF_SMEM, e->stream>>>(
+                    n_tables, maxbins, d_start, d_len, d_lik, is_log, log(p01), log(p02), log(p12), d_score, d_fromT, d_last, d_flag);
+            }
+            {
+                LaunchScope ls(e, K_VITERBI_BACK);
+                viterbi_back_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_len, d_fromT, d_last, d_counts);
+            }
+            {
+                LaunchScope ls(e, K_VITERBI_OUT);
+                viterbi_state_out_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, d_start, d_len, d_fromT, d_state);
+            }
+        } else {  // the four-kernel pipeline with bin-major intermediates (kept for A/B measurement)
+            double *d_nrmT, *d_scoreT;
+            if (scratch(e, SC_HG_NRMT, cells * 24, (void **)&d_nrmT) || scratch(e, SC_HG_SCORET, cells * 24, (void **)&d_scoreT)) return 1;
+            {
+                LaunchScope ls(e, K_VITERBI_NORM);
+                viterbi_norm_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, maxbins, d_start, d_len, d_lik, is_log, d_nrmT);
+            }
+            {
+                LaunchScope ls(e, K_VITERBI);
+                viterbi_forward_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_len, is_log, d_nrmT, log(p01), log(p02), log(p12),
+                                                                                 d_fromT, d_scoreT, d_last, d_flag);
+            }
+            {
+                LaunchScope ls(e, K_VITERBI_BACK);
+                viterbi_back_kernel<<<(n_tables + 63) / 64, 64, 0, e->stream>>>(n_tables, d_len, d_fromT, d_last, d_counts);
+            }
+            {
+                LaunchScope ls(e, K_VITERBI_OUT);
+                viterbi_out_kernel<<<tiles, 1024, 0, e->stream>>>(n_tables, d_start, d_len, d_fromT, d_scoreT, d_state, d_score);
+            }
         }
     } else {
         LaunchScope ls(e, K_VITERBI);

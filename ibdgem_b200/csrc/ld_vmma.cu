@@ -58,6 +58,8 @@ struct VCache {
     size_t b_slot = 0, b_n = 0, b_l0 = 0, b_tbits = 0;
 };
 
+__device__ __forceinline__ uint32_t vspread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
 namespace vmma {
 using namespace tcx;
 constexpr int BM = 128, KBYTES = 128, UK = 32;
@@ -74,7 +76,9 @@ constexpr int NACC = 2;
 constexpr int ACC_STRIDE = 256;            // TMEM columns between the two accumulator slots
 constexpr int EPI_WARP0 = 4;
 constexpr int NSETS = 2;                   // epilogue warp sets (4 warps each); set = accumulator slot
-constexpr int THREADS = 128 + NSETS * 128;
+constexpr int BP_WARP0 = EPI_WARP0 + NSETS * 4;  // column-operand producers: warps 12 .. 16
+constexpr int BP_WARPS = 5;                // 160 threads = 40 individuals x 4 words of a k-block
+constexpr int THREADS = 128 + NSETS * 128 + BP_WARPS * 32;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + NSTAGE * A_SLAB;
 constexpr int OFF_MERGE = OFF_B + NSTAGE * B_SLAB;           // NSETS x 128 double2
@@ -107,6 +111,9 @@ struct Params {
     const double *lognb;         // [T] ln n_refpanel or NaN
     double *wll;                 // [T][outW][3]
     int *unit_counter;
+    const int32_t *bgU;          // [nU] unique background individuals (column order)
+    int nU, H;
+    const uint32_t *tbits;       // [nblk][H][32] haplotype-major bits over the K axis
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
@@ -137,7 +144,9 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NSTAGE; i++) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 1); }
+        // a stage is full when the row slabs have landed (TMA bytes, one expect_tx arrival) and the column-operand
+        // producer warps of BOTH CTAs have written their slabs
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(s_full + i, 1 + 2 * BP_WARPS); mbar_init(s_empty + i, 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * CG); }
         for (int i = 0; i < URING; i++) mbar_init(ufull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -175,13 +184,12 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 const int tile = p.unit0 + u;
                 const int kb0 = __ldg(p.tile_kb0 + tile), nkb = __ldg(p.tile_nkb + tile);
                 const int slabA = (int)(__ldg(p.tile_slab + tile) + (int64_t)rank * nkb);
+                (void)kb0;
                 for (int n = 0; n < p.NT; n++) {
-                    const int slabB = (n * 2 + (int)rank) * p.nKB + kb0;
                     for (int kr = 0; kr < nkb; kr++) {
                         mbar_wait(s_empty + st, ph ^ 1u);
-                        if (rank == 0) mbar_expect_tx(s_full + st, (uint32_t)(CG * (A_SLAB + B_SLAB)));
+                        if (rank == 0) mbar_expect_tx(s_full + st, (uint32_t)(CG * A_SLAB));
                         tma_load_3d_cg<CG>(smem + OFF_A + st * A_SLAB, &tmapA, s_full + st, 0, 0, slabA + kr);
-                        tma_load_3d_cg<CG>(smem + OFF_B + st * B_SLAB, &tmapB, s_full + st, 0, 0, slabB + kr);
                         if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                     }
                 }
@@ -209,7 +217,7 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
                     const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                     for (int kr = 0; kr < nkb; kr++) {
-                        mbar_wait(s_full + st, ph);
+                        mbar_wait_cluster(s_full + st, ph);  // the peer CTA's producer warps arrive from across the pair
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t ad = adesc0 + (uint64_t)((st * A_SLAB) >> 4);
@@ -264,6 +272,61 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 double *o = p.wll + ((size_t)t * p.outW + w) * 3;
                 o[0] = l0;
                 o[1] = l1;
+            }
+        }
+    } else if (warp >= BP_WARP0) {
+        // ===== column-operand producers: the 0/1 bytes of r0, r1 and r0 & r1 are expanded from the packed bits HERE,
+        // straight into the swizzled stage, so the background operand costs 1.25 KB of L2 traffic per stage instead of
+        // 15 KB (the kernel was bound by the L2 -> SM feed of its two streamed operands).  Thread = (individual i of
+        // this CTA's 40, 32-slot word of the k-block); its two haplotype words of a whole 1,024-slot block (8 k-blocks)
+        // are fetched at once. =====
+        const int bt = (int)threadIdx.x - BP_WARP0 * 32;
+        const int i = bt >> 2, part = bt & 3;
+        int st = 0;
+        uint32_t ph = 0;
+        for (int it = 0;; it++) {
+            const int u = unit_of(uring, ufull, it);
+            if (u < 0) break;
+            const int tile = p.unit0 + u;
+            const int kb0 = __ldg(p.tile_kb0 + tile), kb1 = kb0 + __ldg(p.tile_nkb + tile);
+            for (int n = 0; n < p.NT; n++) {
+                const int uidx = (n * 2 + (int)rank) * IND_HALF + i;
+                const int ind = uidx < p.nU ? __ldg(p.bgU + uidx) : -1;
+                for (int g = kb0 >> 3; g <= (kb1 - 1) >> 3; g++) {
+                    uint32_t x0[8], x1[8];
+                    const uint32_t *r0 = p.tbits + ((size_t)g * p.H + 2 * (ind < 0 ? 0 : ind)) * 32 + part;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int kb = g * 8 + q;
+                        const bool in = ind >= 0 && kb >= kb0 && kb < kb1;
+                        x0[q] = in ? __ldg(r0 + q * 4) : 0u;
+                        x1[q] = in ? __ldg(r0 + 32 + q * 4) : 0u;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int kb = g * 8 + q;
+                        if (kb < kb0 || kb >= kb1) continue;
+                        mbar_wait(s_empty + st, ph ^ 1u);
+                        unsigned char *slab = smem + OFF_B + st * B_SLAB;
+                        const uint32_t xs[3] = {x0[q], x1[q], x0[q] & x1[q]};
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const int row = c * IND_HALF + i;
+                            uint32_t e[8];
+#pragma unroll
+                            for (int k = 0; k < 8; k++) e[k] = vspread4((xs[c] >> (4 * k)) & 15u);
+                            // 128-byte swizzle: 16-byte chunk index XOR (row & 7) within each 1,024-byte group of 8 rows
+                            unsigned char *rb = slab + (row >> 3) * 1024 + (row & 7) * 128;
+                            *reinterpret_cast<uint4 *>(rb + (((part * 2) ^ (row & 7)) << 4)) = make_uint4(e[0], e[1], e[2], e[3]);
+                            *reinterpret_cast<uint4 *>(rb + (((part * 2 + 1) ^ (row & 7)) << 4)) = make_uint4(e[4], e[5], e[6], e[7]);
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0)
+                            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(s_full + st) & PEER_MASK) : "memory");
+                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
+                    }
+                }
             }
         }
     } else if (warp >= EPI_WARP0) {
@@ -380,7 +443,6 @@ v_slots_kernel(int64_t S, const uint8_t *__restrict__ status, const uint32_t *__
     l0[j] = lnP[(size_t)(a * C + b) * 3];
 }
 
-__device__ __forceinline__ uint32_t vspread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 __device__ __forceinline__ unsigned vwarp_sum(unsigned v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -973,18 +1035,9 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     IBD_CUDA(cudaMemcpyAsync(h_nkb.data(), d_tile_nkb, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
 
-    // ---- background operand over the whole K axis ------------------------------------------------
-    unsigned char *d_B;
-    const size_t b_bytes = (size_t)NT * 2 * nKB * B_SLAB;
-    if (scratch(e, SC_MMA_BG, b_bytes, (void **)&d_B)) return 1;
-    {
-        LaunchScope ls(e, K_V_EXPAND_B);
-        v_expand_b_kernel<<<dim3((unsigned)nKB, (unsigned)(NT * 2)), 160, 0, e->stream>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
-    }
-    IBD_CUDA(cudaGetLastError());
+    // (the background operand is expanded inside the GEMM kernel from c->d_tbits: no buffer, no pass)
     CUtensorMap mapB;
-    if (make_slab_map(&mapB, d_B, BROWS, (int64_t)NT * 2 * nKB)) return 1;
-
+    memset(&mapB, 0, sizeof mapB);
     // ---- row tiles in batches under the A budget ---------------------------------------------------
     static const size_t a_budget = [] {
         const char *sb = getenv("IBDGEM_V_BUDGET_MB");
@@ -1044,6 +1097,7 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         p.tile_kb0 = d_tile_kb0; p.tile_nkb = d_tile_nkb; p.tile_slab = d_tile_slab; p.order = d_order;
         p.tw_t = d_tw_t; p.tw_w = d_tw_w; p.tw_own = d_tw_own; p.tw_C0 = d_tw_C0; p.tw_R0 = d_tw_R0; p.tw_R1 = d_tw_R1;
         p.lnc = d_lnc; p.lognb = d_lognb; p.wll = d_wll;
+        p.bgU = d_bgU; p.nU = nU; p.H = c->H; p.tbits = c->d_tbits;
         IBD_CUDA(cudaMemsetAsync(d_unit, 0, 4, e->stream));
         p.unit_counter = d_unit;
         {
