@@ -3,7 +3,8 @@
 // (src/ibdgem.c:41-66, 779-1183); the arithmetic is done by libibdgem_b200.so through the C ABI
 // (include/ibdgem_b200.h) and there is no CPU fallback.  Additive options: --gpus N (shard the
 // targets over N devices), --batch N (targets per engine call), --no-tab (skip *.tab.txt),
-// --panel-cache FILE (binary cache of the parsed IMPUTE or VCF panel).
+// --panel-cache FILE (binary cache of the parsed IMPUTE or VCF panel), --hiddengem [--p01/--p02/--p12] (chain the
+// batched Viterbi pass over each target's window scores: <pileup>.<target>.hiddengem.txt).
 #include <getopt.h>
 #include <limits.h>
 #include <unistd.h>
@@ -37,6 +38,8 @@ struct Options {
     std::string cache_fn;  // --panel-cache
     const char *uchr = nullptr;
     int gpus = 1, batch = 0, no_tab = 0;
+    int hiddengem = 0;  // --hiddengem: also write <pileup>.<target>.hiddengem.txt from the window scores
+    double p01 = 0.001, p02 = 0.000001, p12 = 0.001;
 };
 
 void print_help(int code) {
@@ -92,6 +95,23 @@ void print_help(int code) {
 }
 
 // C's %e of a double, with the reference's "-nan" for 0/0 (src/ibdgem.c:751-752)
+// "%.5Le" of exp(L) from its logarithm (hiddengem's score columns; same routine as hiddengem_main.cpp)
+void put_score_log(char *dst, double L) {
+    if (std::isnan(L)) { strcpy(dst, "-nan"); return; }
+    if (std::isinf(L) && L < 0) { strcpy(dst, "0.00000e+00"); return; }
+    const long double l10 = (long double)L / logl(10.0L);
+    long double ex = floorl(l10);
+    long double mant = powl(10.0L, l10 - ex);
+    char m[32];
+    snprintf(m, sizeof(m), "%.5Lf", mant);
+    if (strncmp(m, "10.", 3) == 0) {
+        ex += 1;
+        snprintf(m, sizeof(m), "%.5Lf", 1.0L);
+    }
+    const long e = (long)ex;
+    sprintf(dst, "%se%c%02ld", m, e < 0 ? '-' : '+', e < 0 ? -e : e);
+}
+
 int put_e(char *dst, double v) {
     if (std::isnan(v)) return sprintf(dst, "-nan");
     return sprintf(dst, "%e", v);
@@ -268,6 +288,28 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
         for (size_t k = 0; k < T; k++)
             fprintf(stderr, "Running %s-vs-%s comparison...\n", o.sq_id, sh->targets[b0 + k].name.c_str());
 
+        // --hiddengem: the batch's window scores go straight into the batched Viterbi as natural logs (is_log = 1) —
+        // no round trip through the 7-digit text of summary.txt that the reference's hiddengem parses
+        // (src/hiddengem.c:66-76).  One table per target, in the same call order.
+        std::vector<uint8_t> hg_state;
+        std::vector<double> hg_score;
+        std::vector<int64_t> hg_counts, hg_off;
+        if (o.hiddengem) {
+            std::vector<double> packed;
+            hg_off.assign(1, 0);
+            for (size_t k = 0; k < T; k++) {
+                packed.insert(packed.end(), wll.begin() + (ptrdiff_t)(k * (size_t)maxW * 3), wll.begin() + (ptrdiff_t)((k * (size_t)maxW + (size_t)nw[k]) * 3));
+                hg_off.push_back(hg_off.back() + nw[k]);
+            }
+            const size_t nbins = (size_t)hg_off.back();
+            hg_state.resize(nbins);
+            hg_score.resize(nbins * 3);
+            hg_counts.resize(T * 3);
+            if (nbins && hiddengem_viterbi_batch(e, (int32_t)T, hg_off.data(), packed.data(), 1, o.p01, o.p02, o.p12, hg_state.data(),
+                                                 hg_score.data(), hg_counts.data()))
+                return fail_engine();
+        }
+
         // one target = two files: independent, so the batch is written by a few threads
         auto write_target = [&](size_t k, std::vector<char> &line) -> int {
             const Sample &smp = sh->targets[b0 + k];
@@ -346,6 +388,27 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
                 fprintf(sum, "%d\t%lu\t%lu\t%s\t%s\t%s\t%d\n", w + 1, (unsigned long)ws[i], (unsigned long)we[i], e0, e1, e2, wn[i]);
             }
             fclose(sum);
+            if (o.hiddengem && nw[k] > 0) {  // the table hiddengem prints to stdout (src/hiddengem.c:259-283)
+                const std::string hg_fn = o.out_dir + "/" + o.sq_id + "." + smp.name + ".hiddengem.txt";
+                FILE *hg = fopen(hg_fn.c_str(), "w");
+                if (!hg) {
+                    fprintf(stderr, "[::] ERROR: Cannot open '%s' for writing.\n", hg_fn.c_str());
+                    return 1;
+                }
+                fprintf(hg, "Segment\tIBD0_Score\tIBD1_Score\tIBD2_Score\tInferred_State\n");
+                const int64_t a = hg_off[k], b = hg_off[k + 1];
+                char s0[48], s1[48], s2[48];
+                for (int64_t i = a; i < b; i++) {
+                    put_score_log(s0, hg_score[(size_t)i * 3]);
+                    put_score_log(s1, hg_score[(size_t)i * 3 + 1]);
+                    put_score_log(s2, hg_score[(size_t)i * 3 + 2]);
+                    fprintf(hg, "%d\t%s\t%s\t%s\t%d\n", (int)(i - a + 1), s0, s1, s2, (int)hg_state[(size_t)i]);
+                }
+                const double n = (double)(b - a);
+                for (int c = 0; c < 3; c++)
+                    fprintf(hg, "#%% IBD%d (n = %.0f): %.2f\n", c, (double)hg_counts[k * 3 + (size_t)c], ((double)hg_counts[k * 3 + (size_t)c] / n) * 100);
+                fclose(hg);
+            }
             return 0;
         };
         const size_t n_writers = std::max<size_t>(1, std::min<size_t>({T, (size_t)WRITER_THREADS, (size_t)std::thread::hardware_concurrency()}));
@@ -374,7 +437,7 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
 int main(int argc, char *argv[]) {
     const clock_t start = clock();
     Options o;
-    static int ld_flag = 0, no_tab_flag = 0;
+    static int ld_flag = 0, no_tab_flag = 0, hg_flag = 0;
     static struct option longopts[] = {{"LD", no_argument, &ld_flag, 1},
                                        {"vcf", required_argument, 0, 'V'},
                                        {"hap", required_argument, 0, 'H'},
@@ -402,6 +465,10 @@ int main(int argc, char *argv[]) {
                                        {"batch", required_argument, 0, 1002},    // additive
                                        {"panel-cache", required_argument, 0, 1003},  // additive
                                        {"no-tab", no_argument, &no_tab_flag, 1},  // additive
+                                       {"hiddengem", no_argument, &hg_flag, 1},   // additive: chain the Viterbi pass
+                                       {"p01", required_argument, 0, 1004},
+                                       {"p02", required_argument, 0, 1005},
+                                       {"p12", required_argument, 0, 1006},
                                        {0, 0, 0, 0}};
     if (argc == 1) print_help(0);
     char cwd[PATH_MAX];
@@ -435,6 +502,9 @@ int main(int argc, char *argv[]) {
             case 1001: o.gpus = atoi(optarg); break;
             case 1002: o.batch = atoi(optarg); break;
             case 1003: o.cache_fn = optarg; break;
+            case 1004: o.p01 = atof(optarg); break;
+            case 1005: o.p02 = atof(optarg); break;
+            case 1006: o.p12 = atof(optarg); break;
             case ':':
                 fprintf(stderr, "Option -%c missing required argument.\n", optopt);
                 exit(0);
@@ -449,6 +519,7 @@ int main(int argc, char *argv[]) {
     }
     o.ld = ld_flag;
     o.no_tab = no_tab_flag;
+    o.hiddengem = hg_flag;
     for (int i = optind; i < argc; i++) fprintf(stderr, "Given extra argument %s.\n", argv[i]);
     // validation: the reference exits with status 0 on invalid values (src/ibdgem.c:966-989)
     if (o.opt_d && o.target_dp <= 0) {

@@ -238,3 +238,19 @@ def test_hiddengem_long_table_past_the_long_double_range(tmp_path):
     assert gs == ws and gc == wc
     exact = sum(a == b for a, b in zip(got.splitlines(), want.splitlines()))
     assert exact >= 0.9 * n
+
+
+def test_ibdgem_hiddengem_chaining_matches_the_two_step_run(golden_dir, tmp_path):
+    """--hiddengem (additive): the window scores go into the batched Viterbi as natural logs inside the same run.
+    The states must be those the reference's hiddengem infers from the summary files (golden stdout)."""
+    ca = os.path.join(golden_dir, "ref_runs", "caseA")
+    meta = json.load(open(os.path.join(ca, "nonld_w10", "ARGS.json")))
+    _run("ibdgem", ["-H", "panel.hap", "-L", "panel.legend", "-I", "panel.indv", "-P", "unk.pileup", "-O", str(tmp_path)] +
+         meta["args"] + ["--hiddengem", "--no-tab"], cwd=ca)
+    for ind in ("ind2", "ind3", "ind5"):
+        got = open(tmp_path / f"UNKWN.{ind}.hiddengem.txt").read()
+        want = open(os.path.join(ca, "hiddengem", f"{ind}.default.txt")).read()
+        gs, gc = _states(got)
+        ws, wc = _states(want)
+        assert gs == ws and gc == wc
+        assert got.splitlines()[0] == want.splitlines()[0]
