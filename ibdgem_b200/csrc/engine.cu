@@ -430,41 +430,73 @@ window_nonld_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ tar
     }
 }
 
-// K_WINDOW_NONLD, shared window map (no -v, no -D): one warp per (window, 32 targets), lane = target.
-// Every lane walks the same sites, so the per-site loads (status byte, the window's rows of the 56-byte log table,
-// the panel words that hold the 32 genotypes) are warp-wide broadcasts served by L1; there is no shared-memory
-// staging and no block barrier, and the loop iterations are independent, so several sites' loads are in flight
-// at once.  (A CTA-per-window version that staged the table rows in shared memory spent its time in three block
-// barriers and a chain of dependent L2 round trips per window: 12 % of HBM.)
-__global__ void __launch_bounds__(256)
+// K_WINDOW_NONLD, shared window map (no -v, no -D): one CTA per window, one thread per target.
+// The window's rows of the per-site log table (56 bytes per site, target-independent) are staged
+// in shared memory once per CTA; every thread then walks the sites with its target's genotype
+// bits, so the table is read from HBM once per window instead of once per target.
+constexpr int NONLD_TILE = 256;  // sites staged per pass
+__global__ void __launch_bounds__(128)
 window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ targets, int T,
                            const uint64_t *__restrict__ pos, const uint8_t *__restrict__ status,
                            const double *__restrict__ lnlik7, int outW, double *__restrict__ wll,
                            int32_t *__restrict__ wn, uint64_t *__restrict__ ws, uint64_t *__restrict__ we,
                            int32_t *__restrict__ nwin_out) {
-    const int lane = threadIdx.x & 31;
-    const int tgroups = (T + 31) / 32;
-    const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    __shared__ double sl[NONLD_TILE][7];
+    __shared__ int64_t ssite[NONLD_TILE];
+    __shared__ int segcnt[NONLD_TILE / 32];
+    constexpr int PASSES = NONLD_TILE / 128;
+    const int w = blockIdx.x;
     const int nw = m.nwin[0];
-    const int w = (int)(gw / tgroups), t = (int)(gw % tgroups) * 32 + lane;
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
     if (w == 0 && t < T) nwin_out[t] = nw;
     if (w >= nw || w >= m.maxW) return;
     const int64_t s0 = m.wfirst[w], s1 = m.wlast[w];
-    const int indiv = t < T ? targets[t] : targets[0];
-    const uint32_t *col = v.bits + (indiv >> 4);
-    const int sh = (indiv & 15) * 2;
+    const int indiv = t < T ? targets[t] : 0;
+    const int lane = threadIdx.x & 31;
     double a0 = 0, a1 = 0, a2 = 0;
     int n = 0;
-#pragma unroll 4
-    for (int64_t s = s0; s <= s1; s++) {
-        if (__ldg(status + s) != 1) continue;  // warp-uniform
-        const uint32_t pr = (__ldg(col + s * v.Wh) >> sh) & 3u;
-        const int g = (int)(pr & 1u) + (int)(pr >> 1);
-        const double *L = lnlik7 + s * 7;
-        a0 += __ldg(L);
-        a1 += __ldg(L + 1 + g);
-        a2 += __ldg(L + 4 + g);
-        n++;
+    for (int64_t sb = s0; sb <= s1; sb += NONLD_TILE) {
+        __syncthreads();
+        // compact the informative sites of this pass into shared memory, in site order
+        unsigned bal[PASSES];
+#pragma unroll
+        for (int q = 0; q < PASSES; q++) {
+            const int64_t s = sb + q * 128 + threadIdx.x;
+            bal[q] = __ballot_sync(0xffffffffu, s <= s1 && status[s] == 1);
+            if (lane == 0) segcnt[(q * 128 + threadIdx.x) >> 5] = __popc(bal[q]);
+        }
+        __syncthreads();
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < PASSES; q++) {
+            const int seg = (q * 128 + (int)threadIdx.x) >> 5;
+            int base = 0;
+            for (int k = 0; k < seg; k++) base += segcnt[k];
+            if ((bal[q] >> lane) & 1u) ssite[base + __popc(bal[q] & ((1u << lane) - 1u))] = sb + q * 128 + threadIdx.x;
+        }
+        for (int k = 0; k < NONLD_TILE / 32; k++) cnt += segcnt[k];
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 7; i += blockDim.x) sl[i / 7][i % 7] = lnlik7[ssite[i / 7] * 7 + i % 7];
+        __syncthreads();
+        if (t < T) {
+            // genotype loads are issued eight at a time: one dependent global load per site made this loop
+            // a chain of L2 round trips (the kernel sat at 12 % of HBM)
+            for (int j0 = 0; j0 < cnt; j0 += 8) {
+                uint32_t pr[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) pr[q] = (j0 + q < cnt) ? hap_pair(v.bits + ssite[j0 + q] * v.Wh, indiv) : 0u;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (j0 + q < cnt) {
+                        const int g = (int)(pr[q] & 1u) + (int)(pr[q] >> 1);
+                        a0 += sl[j0 + q][0];
+                        a1 += sl[j0 + q][1 + g];
+                        a2 += sl[j0 + q][4 + g];
+                    }
+                }
+            }
+            n += cnt;
+        }
     }
     if (t < T) {
         const int64_t o = (int64_t)t * outW + w;
@@ -1436,8 +1468,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         {
             LaunchScope ls(e, K_WINDOW_NONLD);
             if (shared) {
-                const int64_t warps = (int64_t)std::max(e->nW_shared, 1) * ((T + 31) / 32);
-                window_nonld_shared_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
+                window_nonld_shared_kernel<<<dim3((unsigned)std::max(e->nW_shared, 1), (unsigned)((T + 127) / 128)), 128, 0, e->stream>>>(
                     v, m, d_targets, T, e->d_pos, e->d_status, e->d_lnlik7, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
             } else {
                 const int64_t warps = (int64_t)nWT;

@@ -111,6 +111,7 @@ struct Params {
     const double *lognb;         // [T] ln n_refpanel or NaN
     double *wll;                 // [T][outW][3]
     int *unit_counter;
+    int debug;
     const int32_t *bgU;          // [nU] unique background individuals (column order)
     int nU, H;
     const uint32_t *tbits;       // [nblk][H][32] haplotype-major bits over the K axis
@@ -123,6 +124,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                  : "memory");
 }
 
+template <int BP>
 __global__ void __launch_bounds__(THREADS, 1)
 ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const Params p) {
     constexpr int CG = 2;
@@ -146,7 +148,7 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     if (warp == 1 && lane == 0) {
         // a stage is full when the row slabs have landed (TMA bytes, one expect_tx arrival) and the column-operand
         // producer warps of BOTH CTAs have written their slabs
-        for (int i = 0; i < NSTAGE; i++) { mbar_init(s_full + i, 1 + 2 * BP_WARPS); mbar_init(s_empty + i, 1); }
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(s_full + i, BP ? 1 + 2 * BP_WARPS : 1); mbar_init(s_empty + i, 1); }
         for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * CG); }
         for (int i = 0; i < URING; i++) mbar_init(ufull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -184,12 +186,16 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 const int tile = p.unit0 + u;
                 const int kb0 = __ldg(p.tile_kb0 + tile), nkb = __ldg(p.tile_nkb + tile);
                 const int slabA = (int)(__ldg(p.tile_slab + tile) + (int64_t)rank * nkb);
-                (void)kb0;
                 for (int n = 0; n < p.NT; n++) {
+                    const int slabB = (n * 2 + (int)rank) * p.nKB + kb0;
                     for (int kr = 0; kr < nkb; kr++) {
                         mbar_wait(s_empty + st, ph ^ 1u);
-                        if (rank == 0) mbar_expect_tx(s_full + st, (uint32_t)(CG * A_SLAB));
-                        tma_load_3d_cg<CG>(smem + OFF_A + st * A_SLAB, &tmapA, s_full + st, 0, 0, slabA + kr);
+                        // p.debug (IBDGEM_VMMA_DEBUG, timing experiments only — results are wrong): 1 = the row operand
+                        // is loaded for the first k-block of a column tile only, 2 = the same for the column operand
+                        const bool ldA = !(p.debug == 1 && kr > 0), ldB = !BP && !(p.debug == 2 && kr > 0);
+                        if (rank == 0) mbar_expect_tx(s_full + st, (uint32_t)(CG * ((ldA ? A_SLAB : 0) + (ldB ? B_SLAB : 0))));
+                        if (ldA) tma_load_3d_cg<CG>(smem + OFF_A + st * A_SLAB, &tmapA, s_full + st, 0, 0, slabA + kr);
+                        if (ldB) tma_load_3d_cg<CG>(smem + OFF_B + st * B_SLAB, &tmapB, s_full + st, 0, 0, slabB + kr);
                         if (++st == NSTAGE) { st = 0; ph ^= 1u; }
                     }
                 }
@@ -274,8 +280,8 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 o[1] = l1;
             }
         }
-    } else if (warp >= BP_WARP0) {
-        // ===== column-operand producers: the 0/1 bytes of r0, r1 and r0 & r1 are expanded from the packed bits HERE,
+    } else if (BP && warp >= BP_WARP0) {
+        // ===== column-operand producers (variant BP = 1): the 0/1 bytes of r0, r1 and r0 & r1 are expanded from the packed bits HERE,
         // straight into the swizzled stage, so the background operand costs 1.25 KB of L2 traffic per stage instead of
         // 15 KB (the kernel was bound by the L2 -> SM feed of its two streamed operands).  Thread = (individual i of
         // this CTA's 40, 32-slot word of the k-block); its two haplotype words of a whole 1,024-slot block (8 k-blocks)
@@ -306,7 +312,8 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     for (int q = 0; q < 8; q++) {
                         const int kb = g * 8 + q;
                         if (kb < kb0 || kb >= kb1) continue;
-                        mbar_wait(s_empty + st, ph ^ 1u);
+                        if (lane == 0) mbar_wait_relaxed(s_empty + st, ph ^ 1u);  // one lane polls, the warp follows
+                        __syncwarp();
                         unsigned char *slab = smem + OFF_B + st * B_SLAB;
                         const uint32_t xs[3] = {x0[q], x1[q], x0[q] & x1[q]};
 #pragma unroll
@@ -329,7 +336,7 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 }
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else if (warp >= EPI_WARP0 && warp < BP_WARP0) {
         // ===== epilogue: set s drains accumulator slot s.  Lane = one row; quad = one (target, window):
         // row 0/1 = n a_i (-> M), row 2 = v nref, row 3 = v nalt (-> Y, and the hom columns for the chain) =====
         const int ew = warp - EPI_WARP0, set = ew >> 2, quarter = warp & 3;
@@ -356,7 +363,7 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 const double *lncn = p.lnc + (size_t)n * TILE_IND;
                 // the screen is relative to the running row maximum, which starts at -inf: the set's first tile
                 // of a unit is read twice, once for its maximum alone
-                for (int pass = (seen == 0 ? 0 : 1); pass < 2; pass++) {
+                for (int pass = (seen == 0 ? 0 : 1); pass < 2 && p.debug != 3; pass++) {  // (debug 3: no epilogue arithmetic)
 #pragma unroll 1
                     for (int hf = 0; hf < 2; hf++) {
 #pragma unroll 1
@@ -1035,9 +1042,22 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     IBD_CUDA(cudaMemcpyAsync(h_nkb.data(), d_tile_nkb, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
 
-    // (the background operand is expanded inside the GEMM kernel from c->d_tbits: no buffer, no pass)
+    // ---- background operand over the whole K axis (variant IBDGEM_VMMA_BPROD=1 expands it inside the GEMM kernel) ----
+    static const int bprod = [] { const char *sb = getenv("IBDGEM_VMMA_BPROD"); return sb ? atoi(sb) : 0; }();
+    static const int vdebug = [] { const char *sb = getenv("IBDGEM_VMMA_DEBUG"); return sb ? atoi(sb) : 0; }();
     CUtensorMap mapB;
     memset(&mapB, 0, sizeof mapB);
+    if (!bprod) {
+        unsigned char *d_B;
+        const size_t b_bytes = (size_t)NT * 2 * nKB * B_SLAB;
+        if (scratch(e, SC_MMA_BG, b_bytes, (void **)&d_B)) return 1;
+        {
+            LaunchScope ls(e, K_V_EXPAND_B);
+            v_expand_b_kernel<<<dim3((unsigned)nKB, (unsigned)(NT * 2)), 160, 0, e->stream>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
+        }
+        IBD_CUDA(cudaGetLastError());
+        if (make_slab_map(&mapB, d_B, BROWS, (int64_t)NT * 2 * nKB)) return 1;
+    }
     // ---- row tiles in batches under the A budget ---------------------------------------------------
     static const size_t a_budget = [] {
         const char *sb = getenv("IBDGEM_V_BUDGET_MB");
@@ -1046,7 +1066,8 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     std::vector<int64_t> h_slab((size_t)n_tiles);
     int *d_unit;
     if (scratch(e, SC_MMA_UNIT, 64, (void **)&d_unit)) return 1;
-    IBD_CUDA(cudaFuncSetAttribute(ld_vmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IBD_CUDA(cudaFuncSetAttribute(ld_vmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IBD_CUDA(cudaFuncSetAttribute(ld_vmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int u0 = 0;
     bool slabs_uploaded = false;
     // slab offsets restart at every batch; all batches' offsets go up in one copy
@@ -1098,6 +1119,7 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         p.tw_t = d_tw_t; p.tw_w = d_tw_w; p.tw_own = d_tw_own; p.tw_C0 = d_tw_C0; p.tw_R0 = d_tw_R0; p.tw_R1 = d_tw_R1;
         p.lnc = d_lnc; p.lognb = d_lognb; p.wll = d_wll;
         p.bgU = d_bgU; p.nU = nU; p.H = c->H; p.tbits = c->d_tbits;
+        p.debug = vdebug;
         IBD_CUDA(cudaMemsetAsync(d_unit, 0, 4, e->stream));
         p.unit_counter = d_unit;
         {
@@ -1115,7 +1137,10 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            IBD_CUDA(cudaLaunchKernelEx(&cfg, ld_vmma_kernel, mapA, mapB, p));
+            if (bprod)
+                IBD_CUDA(cudaLaunchKernelEx(&cfg, ld_vmma_kernel<1>, mapA, mapB, p));
+            else
+                IBD_CUDA(cudaLaunchKernelEx(&cfg, ld_vmma_kernel<0>, mapA, mapB, p));
         }
         IBD_CUDA(cudaGetLastError());
     }
