@@ -304,7 +304,7 @@ viterbi_out_kernel(int n_tables, const int64_t *__restrict__ start, const int64_
 // of viterbi_kernel, operation for operation.  Back-pointers leave bin-major (coalesced over tables) for
 // viterbi_back_kernel; scores leave in the caller's table-major layout.
 constexpr int VF_TABLES = 32, VF_BINS = 16, VF_ROW = VF_BINS * 3 + 1;  // padded row: lanes hit distinct banks
-constexpr int VF_WORKERS = 128, VF_THREADS = VF_WORKERS + 32;
+constexpr int VF_WORKERS = 256, VF_THREADS = VF_WORKERS + 32;
 constexpr int VF_SMEM = 4 * VF_TABLES * VF_ROW * 8 + 2 * VF_TABLES * 8 + 2 * VF_BINS * VF_TABLES;
 __global__ void __launch_bounds__(VF_THREADS, 3)
 viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ start, const int64_t *__restrict__ len,
@@ -331,19 +331,30 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
     if (threadIdx.x >= 32) {
         // ===== workers =====
         const int w = threadIdx.x - 32;
+        constexpr int NLD = VF_TABLES * VF_BINS * 3 / VF_WORKERS;
+        // raw likelihoods of the NEXT chunk are fetched (coalesced: 32 tables x 48 doubles) before this chunk's
+        // exp / log work starts, so DRAM latency hides under it
+        double pre[NLD];
+        auto fetch = [&](int c) {
+            const int64_t i0 = (int64_t)c * VF_BINS;
+#pragma unroll
+            for (int k = 0; k < NLD; k++) {
+                const int idx = k * VF_WORKERS + w;
+                const int t = idx / (VF_BINS * 3), d = idx % (VF_BINS * 3);
+                pre[k] = (i0 + d / 3 < s_len[t]) ? __ldcs(lik + (s_start[t] + i0) * 3 + d) : 0.0;
+            }
+        };
+        if (nchunk > 0) fetch(0);
         for (int c = 0; c <= nchunk; c++) {
             const int b = c & 1;
             if (c < nchunk) {
                 const int64_t i0 = (int64_t)c * VF_BINS;
-                // raw likelihoods, coalesced: 32 tables x 48 doubles
 #pragma unroll
-                for (int k = 0; k < VF_TABLES * VF_BINS * 3 / VF_WORKERS; k++) {
+                for (int k = 0; k < NLD; k++) {
                     const int idx = k * VF_WORKERS + w;
-                    const int t = idx / (VF_BINS * 3), d = idx % (VF_BINS * 3);
-                    double x = 0.0;
-                    if (i0 + d / 3 < s_len[t]) x = __ldcs(lik + (s_start[t] + i0) * 3 + d);
-                    nrm[b][t][d] = x;
+                    nrm[b][idx / (VF_BINS * 3)][idx % (VF_BINS * 3)] = pre[k];
                 }
+                if (c + 1 < nchunk) fetch(c + 1);
                 asm volatile("bar.sync 5, %0;" ::"n"(VF_WORKERS) : "memory");
                 // ln nrm in place: 512 bins, 4 per worker
 #pragma unroll

@@ -82,7 +82,8 @@ constexpr int THREADS = 128 + NSETS * 128 + BP_WARPS * 32;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + NSTAGE * A_SLAB;
 constexpr int OFF_MERGE = OFF_B + NSTAGE * B_SLAB;           // NSETS x 128 double2
-constexpr int OFF_BAR = OFF_MERGE + NSETS * BM * 16;
+constexpr int OFF_SMAX = OFF_MERGE + NSETS * BM * 16;         // 2 x 128 int32: the rows' running maxima, shared by the sets
+constexpr int OFF_BAR = OFF_SMAX + 2 * BM * 4;
 constexpr int NBAR = 2 * NSTAGE + 2 * NACC + URING;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int OFF_URING = OFF_TMEM + 16;
@@ -116,6 +117,14 @@ struct Params {
     int nU, H;
     const uint32_t *tbits;       // [nblk][H][32] haplotype-major bits over the K axis
 };
+
+// order-preserving float <-> int map, so that atomicMax on ints is a max on floats
+__device__ __forceinline__ int f2ord(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+constexpr int ORD_NEG_INF = (int)0x807fffff;  // f2ord(-inf)
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -153,6 +162,8 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         for (int i = 0; i < URING; i++) mbar_init(ufull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 3)
+        for (int i = lane; i < 2 * BM; i += 32) reinterpret_cast<int *>(smem + OFF_SMAX)[i] = ORD_NEG_INF;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -352,6 +363,11 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const int own = tw >= 0 ? __ldg(p.tw_own + tw) : -1;
             double m = -INFINITY, s = 0.0;  // rows 0, 1: the row's sum over background haplotypes; row 2: the chain over individuals
             float fmx = -INFINITY;
+            // The two sets see disjoint column tiles.  They share the row's running maximum through shared memory
+            // (monotone, so a stale read only lets more elements through the screen): without it the set that never
+            // meets the row's dominant column screens against its own, far lower, maximum and sends ~6 % of its
+            // elements down the fp64 path — measured 32.9 ms per C3 -v pass against a 16.4 ms MMA floor.
+            int *smax = reinterpret_cast<int *>(smem + OFF_SMAX) + (it & 1) * BM + rloc;
             int seen = 0;  // tiles this set has processed in this unit
             for (int n = 0; n < p.NT; n++) {
                 const uint32_t g = g0 + (uint32_t)n;
@@ -361,9 +377,14 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + set * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
                 const double *lncn = p.lnc + (size_t)n * TILE_IND;
+                fmx = fmaxf(fmx, ord2f(*reinterpret_cast<volatile int *>(smax)));
                 // the screen is relative to the running row maximum, which starts at -inf: the set's first tile
                 // of a unit is read twice, once for its maximum alone
                 for (int pass = (seen == 0 ? 0 : 1); pass < 2 && p.debug != 3; pass++) {  // (debug 3: no epilogue arithmetic)
+                    if (pass == 1 && seen == 0) {  // the warm pass is over: publish this tile's maximum, take the other set's
+                        atomicMax(smax, f2ord(fmx));
+                        fmx = fmaxf(fmx, ord2f(*reinterpret_cast<volatile int *>(smax)));
+                    }
 #pragma unroll 1
                     for (int hf = 0; hf < 2; hf++) {
 #pragma unroll 1
@@ -413,11 +434,13 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                         }
                     }
                 }
+                atomicMax(smax, f2ord(fmx));
                 seen++;
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader<CG>(acc_empty + set);
             }
+            if (set == 0) reinterpret_cast<int *>(smem + OFF_SMAX)[((it + 1) & 1) * BM + rloc] = ORD_NEG_INF;  // next unit's slot (idle since unit it - 1)
             asm volatile("bar.sync 2, %0;" ::"n"(NSETS * 128 + 32) : "memory");  // previous unit's partials consumed
             merge[set * BM + rloc] = make_double2(m, s);
             asm volatile("bar.arrive 1, %0;" ::"n"(NSETS * 128 + 32) : "memory");
