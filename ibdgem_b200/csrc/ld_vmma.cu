@@ -75,10 +75,10 @@ constexpr int NSTAGE = 6;
 constexpr int NACC = 2;
 constexpr int ACC_STRIDE = 256;            // TMEM columns between the two accumulator slots
 constexpr int EPI_WARP0 = 4;
-constexpr int NSETS = 2;                   // epilogue warp sets (4 warps each); set = accumulator slot
-constexpr int BP_WARP0 = EPI_WARP0 + NSETS * 4;  // column-operand producers: warps 12 .. 16
-constexpr int BP_WARPS = 5;                // 160 threads = 40 individuals x 4 words of a k-block
-constexpr int THREADS = 128 + NSETS * 128 + BP_WARPS * 32;
+constexpr int NSETS = 4;                   // epilogue warp sets of 4 warps (one per TMEM lane quarter); every set works on every
+                                           // tile and owns a quarter of its individuals
+constexpr int SET_IND = TILE_IND / NSETS;  // 20 individuals per set and tile, in chunks of 4
+constexpr int THREADS = 128 + NSETS * 128;
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + NSTAGE * A_SLAB;
 constexpr int OFF_MERGE = OFF_B + NSTAGE * B_SLAB;           // NSETS x 128 double2
@@ -113,9 +113,6 @@ struct Params {
     double *wll;                 // [T][outW][3]
     int *unit_counter;
     int debug;
-    const int32_t *bgU;          // [nU] unique background individuals (column order)
-    int nU, H;
-    const uint32_t *tbits;       // [nblk][H][32] haplotype-major bits over the K axis
 };
 
 // order-preserving float <-> int map, so that atomicMax on ints is a max on floats
@@ -133,7 +130,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                  : "memory");
 }
 
-template <int BP>
 __global__ void __launch_bounds__(THREADS, 1)
 ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const Params p) {
     constexpr int CG = 2;
@@ -155,10 +151,8 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        // a stage is full when the row slabs have landed (TMA bytes, one expect_tx arrival) and the column-operand
-        // producer warps of BOTH CTAs have written their slabs
-        for (int i = 0; i < NSTAGE; i++) { mbar_init(s_full + i, BP ? 1 + 2 * BP_WARPS : 1); mbar_init(s_empty + i, 1); }
-        for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * CG); }
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, 1); }
+        for (int i = 0; i < NACC; i++) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * NSETS * CG); }
         for (int i = 0; i < URING; i++) mbar_init(ufull + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -203,7 +197,7 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                         mbar_wait(s_empty + st, ph ^ 1u);
                         // p.debug (IBDGEM_VMMA_DEBUG, timing experiments only — results are wrong): 1 = the row operand
                         // is loaded for the first k-block of a column tile only, 2 = the same for the column operand
-                        const bool ldA = !(p.debug == 1 && kr > 0), ldB = !BP && !(p.debug == 2 && kr > 0);
+                        const bool ldA = !(p.debug == 1 && kr > 0), ldB = !(p.debug == 2 && kr > 0);
                         if (rank == 0) mbar_expect_tx(s_full + st, (uint32_t)(CG * ((ldA ? A_SLAB : 0) + (ldB ? B_SLAB : 0))));
                         if (ldA) tma_load_3d_cg<CG>(smem + OFF_A + st * A_SLAB, &tmapA, s_full + st, 0, 0, slabA + kr);
                         if (ldB) tma_load_3d_cg<CG>(smem + OFF_B + st * B_SLAB, &tmapB, s_full + st, 0, 0, slabB + kr);
@@ -234,7 +228,7 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     mbar_wait(acc_empty + acc, (use & 1u) ^ 1u);
                     const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                     for (int kr = 0; kr < nkb; kr++) {
-                        mbar_wait_cluster(s_full + st, ph);  // the peer CTA's producer warps arrive from across the pair
+                        mbar_wait(s_full + st, ph);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint64_t ad = adesc0 + (uint64_t)((st * A_SLAB) >> 4);
@@ -273,9 +267,15 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             double L[3];
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                const double2 a = mb[0 * BM + lane * 4 + c], b = mb[1 * BM + lane * 4 + c];
-                const double M = fmax(a.x, b.x);
-                const double S = a.y * exp_nonpos(a.x - M) + b.y * exp_nonpos(b.x - M);
+                double2 o[NSETS];
+#pragma unroll
+                for (int q = 0; q < NSETS; q++) o[q] = mb[q * BM + lane * 4 + c];
+                double M = o[0].x;
+#pragma unroll
+                for (int q = 1; q < NSETS; q++) M = fmax(M, o[q].x);
+                double S = 0.0;
+#pragma unroll
+                for (int q = 0; q < NSETS; q++) S = fma(o[q].y, exp_nonpos(o[q].x - M), S);
                 L[c] = (S > 0.0) ? M + log(S) : -INFINITY;
             }
             asm volatile("bar.arrive 2, %0;" ::"n"(NSETS * 128 + 32) : "memory");
@@ -291,65 +291,12 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 o[1] = l1;
             }
         }
-    } else if (BP && warp >= BP_WARP0) {
-        // ===== column-operand producers (variant BP = 1): the 0/1 bytes of r0, r1 and r0 & r1 are expanded from the packed bits HERE,
-        // straight into the swizzled stage, so the background operand costs 1.25 KB of L2 traffic per stage instead of
-        // 15 KB (the kernel was bound by the L2 -> SM feed of its two streamed operands).  Thread = (individual i of
-        // this CTA's 40, 32-slot word of the k-block); its two haplotype words of a whole 1,024-slot block (8 k-blocks)
-        // are fetched at once. =====
-        const int bt = (int)threadIdx.x - BP_WARP0 * 32;
-        const int i = bt >> 2, part = bt & 3;
-        int st = 0;
-        uint32_t ph = 0;
-        for (int it = 0;; it++) {
-            const int u = unit_of(uring, ufull, it);
-            if (u < 0) break;
-            const int tile = p.unit0 + u;
-            const int kb0 = __ldg(p.tile_kb0 + tile), kb1 = kb0 + __ldg(p.tile_nkb + tile);
-            for (int n = 0; n < p.NT; n++) {
-                const int uidx = (n * 2 + (int)rank) * IND_HALF + i;
-                const int ind = uidx < p.nU ? __ldg(p.bgU + uidx) : -1;
-                for (int g = kb0 >> 3; g <= (kb1 - 1) >> 3; g++) {
-                    uint32_t x0[8], x1[8];
-                    const uint32_t *r0 = p.tbits + ((size_t)g * p.H + 2 * (ind < 0 ? 0 : ind)) * 32 + part;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int kb = g * 8 + q;
-                        const bool in = ind >= 0 && kb >= kb0 && kb < kb1;
-                        x0[q] = in ? __ldg(r0 + q * 4) : 0u;
-                        x1[q] = in ? __ldg(r0 + 32 + q * 4) : 0u;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int kb = g * 8 + q;
-                        if (kb < kb0 || kb >= kb1) continue;
-                        if (lane == 0) mbar_wait_relaxed(s_empty + st, ph ^ 1u);  // one lane polls, the warp follows
-                        __syncwarp();
-                        unsigned char *slab = smem + OFF_B + st * B_SLAB;
-                        const uint32_t xs[3] = {x0[q], x1[q], x0[q] & x1[q]};
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const int row = c * IND_HALF + i;
-                            uint32_t e[8];
-#pragma unroll
-                            for (int k = 0; k < 8; k++) e[k] = vspread4((xs[c] >> (4 * k)) & 15u);
-                            // 128-byte swizzle: 16-byte chunk index XOR (row & 7) within each 1,024-byte group of 8 rows
-                            unsigned char *rb = slab + (row >> 3) * 1024 + (row & 7) * 128;
-                            *reinterpret_cast<uint4 *>(rb + (((part * 2) ^ (row & 7)) << 4)) = make_uint4(e[0], e[1], e[2], e[3]);
-                            *reinterpret_cast<uint4 *>(rb + (((part * 2 + 1) ^ (row & 7)) << 4)) = make_uint4(e[4], e[5], e[6], e[7]);
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0)
-                            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(s_full + st) & PEER_MASK) : "memory");
-                        if (++st == NSTAGE) { st = 0; ph ^= 1u; }
-                    }
-                }
-            }
-        }
-    } else if (warp >= EPI_WARP0 && warp < BP_WARP0) {
-        // ===== epilogue: set s drains accumulator slot s.  Lane = one row; quad = one (target, window):
-        // row 0/1 = n a_i (-> M), row 2 = v nref, row 3 = v nalt (-> Y, and the hom columns for the chain) =====
+    } else if (warp >= EPI_WARP0) {
+        // ===== epilogue.  Every set works on every tile: set q owns individuals [20 q, 20 q + 20) of the tile, in
+        // chunks of 4.  Lane = one accumulator row; quad = one (target, window): row 0/1 = n a_i (-> M), row 2 = v nref,
+        // row 3 = v nalt (-> Y, and the hom columns of the chain).  A chunk is handled in two steps so that the hot
+        // path is straight-line code the compiler can interleave: first all shuffles and the fp32 screen values of the
+        // chunk's 8 elements, then — rarely — the fp64 terms of the elements that passed. =====
         const int ew = warp - EPI_WARP0, set = ew >> 2, quarter = warp & 3;
         const int rloc = quarter * 32 + lane;
         const int c = lane & 3, qb = lane & ~3;
@@ -363,71 +310,85 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             const int own = tw >= 0 ? __ldg(p.tw_own + tw) : -1;
             double m = -INFINITY, s = 0.0;  // rows 0, 1: the row's sum over background haplotypes; row 2: the chain over individuals
             float fmx = -INFINITY;
-            // The two sets see disjoint column tiles.  They share the row's running maximum through shared memory
-            // (monotone, so a stale read only lets more elements through the screen): without it the set that never
-            // meets the row's dominant column screens against its own, far lower, maximum and sends ~6 % of its
-            // elements down the fp64 path — measured 32.9 ms per C3 -v pass against a 16.4 ms MMA floor.
+            // The sets see disjoint columns.  They share the row's running maximum through shared memory (monotone,
+            // so a stale read only lets more elements through the screen).
             int *smax = reinterpret_cast<int *>(smem + OFF_SMAX) + (it & 1) * BM + rloc;
-            int seen = 0;  // tiles this set has processed in this unit
             for (int n = 0; n < p.NT; n++) {
                 const uint32_t g = g0 + (uint32_t)n;
-                if ((int)(g & 1u) != set) continue;
-                const uint32_t use = g >> 1;
-                mbar_wait_relaxed(acc_full + set, use & 1u);
+                const int slot = (int)(g & 1u);
+                mbar_wait_relaxed(acc_full + slot, (g >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + set * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+                const uint32_t taddr = tmem_base + slot * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
                 const double *lncn = p.lnc + (size_t)n * TILE_IND;
                 fmx = fmaxf(fmx, ord2f(*reinterpret_cast<volatile int *>(smax)));
-                // the screen is relative to the running row maximum, which starts at -inf: the set's first tile
-                // of a unit is read twice, once for its maximum alone
-                for (int pass = (seen == 0 ? 0 : 1); pass < 2 && p.debug != 3; pass++) {  // (debug 3: no epilogue arithmetic)
-                    if (pass == 1 && seen == 0) {  // the warm pass is over: publish this tile's maximum, take the other set's
+                // the screen is relative to the running row maximum, which starts at -inf: the first tile of a unit is
+                // read twice, once for its maximum alone (shared by the sets)
+                for (int pass = (n == 0 ? 0 : 1); pass < 2 && p.debug != 3; pass++) {
+                    if (pass == 1 && n == 0) {
                         atomicMax(smax, f2ord(fmx));
+                        asm volatile("bar.sync 3, %0;" ::"n"(NSETS * 128) : "memory");
                         fmx = fmaxf(fmx, ord2f(*reinterpret_cast<volatile int *>(smax)));
                     }
 #pragma unroll 1
-                    for (int hf = 0; hf < 2; hf++) {
-#pragma unroll 1
-                        for (int i0 = 0; i0 < IND_HALF; i0 += 8) {
-                            int v0[8], v1[8], vh[8];
-                            __syncwarp();
-                            tmem_ld8(taddr + hf * BROWS + i0, v0);
-                            tmem_ld8(taddr + hf * BROWS + IND_HALF + i0, v1);
-                            tmem_ld8(taddr + hf * BROWS + 2 * IND_HALF + i0, vh);
-                            tmem_ld_wait();
+                    for (int ch = 0; ch < SET_IND / 4; ch++) {
+                        const int ci = set * SET_IND + ch * 4;          // first individual of the chunk within the tile
+                        const int hf = ci / IND_HALF, i0 = ci % IND_HALF;
+                        int v0[4], v1[4], vh[4];
+                        __syncwarp();
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(v0[0]), "=r"(v0[1]), "=r"(v0[2]), "=r"(v0[3]) : "r"(taddr + hf * BROWS + i0) : "memory");
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(v1[0]), "=r"(v1[1]), "=r"(v1[2]), "=r"(v1[3]) : "r"(taddr + hf * BROWS + IND_HALF + i0) : "memory");
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(vh[0]), "=r"(vh[1]), "=r"(vh[2]), "=r"(vh[3]) : "r"(taddr + hf * BROWS + 2 * IND_HALF + i0) : "memory");
+                        double lc[4];
 #pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const int ind = hf * IND_HALF + i0 + i;
-                                const int vr0 = __shfl_sync(0xffffffffu, v0[i], qb | 2), va0 = __shfl_sync(0xffffffffu, v0[i], qb | 3);
-                                const int vr1 = __shfl_sync(0xffffffffu, v1[i], qb | 2), va1 = __shfl_sync(0xffffffffu, v1[i], qb | 3);
-                                const int vah = __shfl_sync(0xffffffffu, vh[i], qb | 3);
-                                const double lc = __ldg(lncn + ind);
-                                const float lcf = (n * TILE_IND + ind == own) ? -INFINITY : (float)lc;
-                                const float y0 = fmaf(p.alpha_f, (float)vr0, p.beta_f * (float)va0) + lcf;
-                                const float y1 = fmaf(p.alpha_f, (float)vr1, p.beta_f * (float)va1) + lcf;
-                                float t0, t1;
-                                if (c < 2) {
-                                    t0 = fmaf(p.kappa_f, (float)v0[i], y0);
-                                    t1 = fmaf(p.kappa_f, (float)v1[i], y1);
-                                } else {  // row 2 carries the chain P[r0 + r1] of the individual; row 3 only supplies its counts
-                                    t0 = (c == 2) ? fmaf(p.kappa_f, (float)(vh[i] + vah), y0 + (y1 - lcf)) : -INFINITY;
-                                    if (!(lcf > -INFINITY)) t0 = -INFINITY;
-                                    t1 = -INFINITY;
-                                }
-                                fmx = fmaxf(fmx, fmaxf(t0, t1));
-                                if (pass == 0) continue;
-                                const float thr = fmx - p.screen_f;
-                                if (t0 > thr) {
+                        for (int i = 0; i < 4; i++) lc[i] = __ldg(lncn + ci + i);
+                        tmem_ld_wait();
+                        int vr0[4], va0[4], vr1[4], va1[4], vah[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            vr0[i] = __shfl_sync(0xffffffffu, v0[i], qb | 2);
+                            va0[i] = __shfl_sync(0xffffffffu, v0[i], qb | 3);
+                            vr1[i] = __shfl_sync(0xffffffffu, v1[i], qb | 2);
+                            va1[i] = __shfl_sync(0xffffffffu, v1[i], qb | 3);
+                            vah[i] = __shfl_sync(0xffffffffu, vh[i], qb | 3);
+                        }
+                        float t0[4], t1[4];
+                        float cmx = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const float lcf = (n * TILE_IND + ci + i == own) ? -INFINITY : (float)lc[i];
+                            const float y0 = fmaf(p.alpha_f, (float)vr0[i], p.beta_f * (float)va0[i]);
+                            const float y1 = fmaf(p.alpha_f, (float)vr1[i], p.beta_f * (float)va1[i]);
+                            // rows 0, 1: the two pairings of the row's haplotype with the individual's; row 2: the chain
+                            // P[r0 + r1] of the individual; row 3 only supplies counts
+                            const float a = c < 2 ? fmaf(p.kappa_f, (float)v0[i], y0) : fmaf(p.kappa_f, (float)(vh[i] + vah[i]), y0 + y1);
+                            const float b = fmaf(p.kappa_f, (float)v1[i], y1);
+                            t0[i] = c < 3 ? a + lcf : -INFINITY;
+                            t1[i] = c < 2 ? b + lcf : -INFINITY;
+                            cmx = fmaxf(cmx, fmaxf(t0[i], t1[i]));
+                        }
+                        fmx = fmaxf(fmx, cmx);
+                        if (pass == 0) continue;
+                        const float thr = p.debug == 4 ? INFINITY : fmx - p.screen_f;  // (debug 4: nothing passes)
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) mask |= (t0[i] > thr ? 1u << (2 * i) : 0u) | (t1[i] > thr ? 2u << (2 * i) : 0u);
+                        if (mask) {  // rare: the fp64 terms of the survivors
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                if (mask & (1u << (2 * i))) {
                                     double x;
                                     if (c < 2)
-                                        x = fma(p.kappa, (double)v0[i], fma(p.alpha, (double)vr0, p.beta * (double)va0)) + lc;
+                                        x = fma(p.kappa, (double)v0[i], fma(p.alpha, (double)vr0[i], p.beta * (double)va0[i])) + lc[i];
                                     else
-                                        x = fma(p.kappa, (double)(vh[i] + vah),
-                                                fma(p.alpha, (double)(vr0 + vr1), p.beta * (double)(va0 + va1))) + lc;
+                                        x = fma(p.kappa, (double)(vh[i] + vah[i]),
+                                                fma(p.alpha, (double)(vr0[i] + vr1[i]), p.beta * (double)(va0[i] + va1[i]))) + lc[i];
                                     lse_add_fast(m, s, x);
                                 }
-                                if (t1 > thr) {
-                                    const double x = fma(p.kappa, (double)v1[i], fma(p.alpha, (double)vr1, p.beta * (double)va1)) + lc;
+                                if (mask & (2u << (2 * i))) {
+                                    const double x = fma(p.kappa, (double)v1[i], fma(p.alpha, (double)vr1[i], p.beta * (double)va1[i])) + lc[i];
                                     lse_add_fast(m, s, x);
                                 }
                             }
@@ -435,10 +396,9 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                     }
                 }
                 atomicMax(smax, f2ord(fmx));
-                seen++;
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_leader<CG>(acc_empty + set);
+                if (lane == 0) mbar_arrive_leader<CG>(acc_empty + slot);
             }
             if (set == 0) reinterpret_cast<int *>(smem + OFF_SMAX)[((it + 1) & 1) * BM + rloc] = ORD_NEG_INF;  // next unit's slot (idle since unit it - 1)
             asm volatile("bar.sync 2, %0;" ::"n"(NSETS * 128 + 32) : "memory");  // previous unit's partials consumed
@@ -1065,22 +1025,19 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     IBD_CUDA(cudaMemcpyAsync(h_nkb.data(), d_tile_nkb, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
 
-    // ---- background operand over the whole K axis (variant IBDGEM_VMMA_BPROD=1 expands it inside the GEMM kernel) ----
-    static const int bprod = [] { const char *sb = getenv("IBDGEM_VMMA_BPROD"); return sb ? atoi(sb) : 0; }();
+    // ---- background operand over the whole K axis ------------------------------------------------
     static const int vdebug = [] { const char *sb = getenv("IBDGEM_VMMA_DEBUG"); return sb ? atoi(sb) : 0; }();
-    CUtensorMap mapB;
-    memset(&mapB, 0, sizeof mapB);
-    if (!bprod) {
-        unsigned char *d_B;
-        const size_t b_bytes = (size_t)NT * 2 * nKB * B_SLAB;
-        if (scratch(e, SC_MMA_BG, b_bytes, (void **)&d_B)) return 1;
-        {
-            LaunchScope ls(e, K_V_EXPAND_B);
-            v_expand_b_kernel<<<dim3((unsigned)nKB, (unsigned)(NT * 2)), 160, 0, e->stream>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
-        }
-        IBD_CUDA(cudaGetLastError());
-        if (make_slab_map(&mapB, d_B, BROWS, (int64_t)NT * 2 * nKB)) return 1;
+    unsigned char *d_B;
+    const size_t b_bytes = (size_t)NT * 2 * nKB * B_SLAB;
+    if (scratch(e, SC_MMA_BG, b_bytes, (void **)&d_B)) return 1;
+    {
+        LaunchScope ls(e, K_V_EXPAND_B);
+        v_expand_b_kernel<<<dim3((unsigned)nKB, (unsigned)(NT * 2)), 160, 0, e->stream>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
     }
+    IBD_CUDA(cudaGetLastError());
+    CUtensorMap mapB;
+    if (make_slab_map(&mapB, d_B, BROWS, (int64_t)NT * 2 * nKB)) return 1;
+
     // ---- row tiles in batches under the A budget ---------------------------------------------------
     static const size_t a_budget = [] {
         const char *sb = getenv("IBDGEM_V_BUDGET_MB");
@@ -1089,8 +1046,7 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     std::vector<int64_t> h_slab((size_t)n_tiles);
     int *d_unit;
     if (scratch(e, SC_MMA_UNIT, 64, (void **)&d_unit)) return 1;
-    IBD_CUDA(cudaFuncSetAttribute(ld_vmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    IBD_CUDA(cudaFuncSetAttribute(ld_vmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    IBD_CUDA(cudaFuncSetAttribute(ld_vmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int u0 = 0;
     bool slabs_uploaded = false;
     // slab offsets restart at every batch; all batches' offsets go up in one copy
@@ -1141,9 +1097,8 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         p.tile_kb0 = d_tile_kb0; p.tile_nkb = d_tile_nkb; p.tile_slab = d_tile_slab; p.order = d_order;
         p.tw_t = d_tw_t; p.tw_w = d_tw_w; p.tw_own = d_tw_own; p.tw_C0 = d_tw_C0; p.tw_R0 = d_tw_R0; p.tw_R1 = d_tw_R1;
         p.lnc = d_lnc; p.lognb = d_lognb; p.wll = d_wll;
-        p.bgU = d_bgU; p.nU = nU; p.H = c->H; p.tbits = c->d_tbits;
         p.debug = vdebug;
-        IBD_CUDA(cudaMemsetAsync(d_unit, 0, 4, e->stream));
+        IBD_CUDA(cudaMemsetAsync(d_unit, 0, 8, e->stream));
         p.unit_counter = d_unit;
         {
             LaunchScope ls(e, K_LD_VMMA);
@@ -1160,10 +1115,7 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            if (bprod)
-                IBD_CUDA(cudaLaunchKernelEx(&cfg, ld_vmma_kernel<1>, mapA, mapB, p));
-            else
-                IBD_CUDA(cudaLaunchKernelEx(&cfg, ld_vmma_kernel<0>, mapA, mapB, p));
+            IBD_CUDA(cudaLaunchKernelEx(&cfg, ld_vmma_kernel, mapA, mapB, p));
         }
         IBD_CUDA(cudaGetLastError());
     }
