@@ -33,9 +33,10 @@ __device__ __forceinline__ int argmax3(double c0, double c1, double c2) {
 // on the host in long double.  NaN / -inf candidates never flag: their comparisons are exact in both worlds.
 constexpr double LN_LDBL_MIN = -11355.137111933024;  // ln(3.3621e-4932)
 __device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int best, int64_t i) {
-    const double w = best == 0 ? c0 : (best == 1 ? c1 : c2);
-    const double r = best == 0 ? fmax(c1, c2) : (best == 1 ? fmax(c0, c2) : fmax(c0, c1));
-    const double tol = 4.0 * (double)(i + 1) * 1.1102230246251565e-16 * fabs(w) + 1e-12;
+    (void)best;
+    const double m01 = fmax(c0, c1), w = fmax(m01, c2);          // winner
+    const double r = fmax(fmin(c0, c1), fmin(m01, c2));          // runner-up
+    const double tol = fma((double)(int)(i + 1) * 4.440892098500626e-16, fabs(w), 1e-12);  // 4 (i + 1) 2^-53 |w| + 1e-12
     return (w - r) < tol;  // false for NaN and for inf - inf
 }
 // a finite score below the smallest normal long double: the reference's product is a denormal (or zero) there

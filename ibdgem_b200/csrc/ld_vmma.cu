@@ -447,16 +447,31 @@ __device__ __forceinline__ double vwarp_sum_d(double v) {
 // -v window map in rank space: one warp per target walks the words v = x0 | x1 of the target's two haplotype
 // rows (32 slots per word, 32 words per pass) and records the slot of the first and last member of every
 // window (W2, src/ibdgem.c:559-578, 723-730).
-__global__ void __launch_bounds__(128)
+constexpr int WMAP_WARPS = 8;
+__global__ void __launch_bounds__(WMAP_WARPS * 32)
 v_wmap_kernel(int T, const int32_t *__restrict__ targets, const uint32_t *__restrict__ tbits, int H, int nblk, int W, int mapW,
               int32_t *__restrict__ ks, int32_t *__restrict__ ke, int32_t *__restrict__ nwin, int64_t *__restrict__ ktot) {
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    // one CTA per target; warp k takes the k-th contiguous share of the 1,024-slot blocks: a first pass counts its
+    // members, a prefix over the warps gives its starting rank, a second pass records the window boundaries
+    __shared__ int64_t wcnt[WMAP_WARPS];
+    __shared__ int wlast[WMAP_WARPS];
+    const int t = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (t >= T) return;
     const int ind = __ldg(targets + t);
+    const int per = (nblk + WMAP_WARPS - 1) / WMAP_WARPS;
+    const int b_lo = min(nblk, wid * per), b_hi = min(nblk, b_lo + per);
+    const uint32_t *r0 = tbits + (size_t)(2 * ind) * 32 + lane, *r1 = r0 + 32;
+    int64_t cnt = 0;
+    for (int b = b_lo; b < b_hi; b++) cnt += __popc(__ldg(r0 + (size_t)b * H * 32) | __ldg(r1 + (size_t)b * H * 32));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) wcnt[wid] = cnt;
+    __syncthreads();
     int64_t running = 0;
+    for (int k = 0; k < wid; k++) running += wcnt[k];
     int last = -1;
-    for (int b = 0; b < nblk; b++) {
-        const uint32_t m = __ldg(tbits + ((size_t)b * H + 2 * ind) * 32 + lane) | __ldg(tbits + ((size_t)b * H + 2 * ind + 1) * 32 + lane);
+    for (int b = b_lo; b < b_hi; b++) {
+        const uint32_t m = __ldg(r0 + (size_t)b * H * 32) | __ldg(r1 + (size_t)b * H * 32);
         const int pc = __popc(m);
         int incl = pc;
 #pragma unroll
@@ -480,11 +495,19 @@ v_wmap_kernel(int T, const int32_t *__restrict__ targets, const uint32_t *__rest
         running += __shfl_sync(0xffffffffu, incl, 31);
     }
     last = __reduce_max_sync(0xffffffffu, last);
-    if (lane == 0) {
-        const int64_t nw = (running + W - 1) / W;
-        if (running % W != 0 && nw - 1 < mapW) ke[(size_t)t * mapW + nw - 1] = last;  // the partial last window (src/ibdgem.c:575-578)
+    if (lane == 0) wlast[wid] = last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t total = 0;
+        int lastall = -1;
+        for (int k = 0; k < WMAP_WARPS; k++) {
+            total += wcnt[k];
+            lastall = max(lastall, wlast[k]);
+        }
+        const int64_t nw = (total + W - 1) / W;
+        if (total % W != 0 && nw - 1 < mapW) ke[(size_t)t * mapW + nw - 1] = lastall;  // the partial last window (src/ibdgem.c:575-578)
         nwin[t] = (int32_t)nw;
-        ktot[t] = running;
+        ktot[t] = total;
     }
 }
 
@@ -560,13 +583,12 @@ v_tw_kernel(int T, int mapW, int outW, const int32_t *__restrict__ targets, cons
             N1 = __dp4a(e1, nn[k], N1);
             M = __dp4a(e0 & e1, nn[k], M);
         }
-        uint32_t v = x0 | x1;
+        const uint32_t v = x0 | x1;
         cnt += __popc(v);
-        while (v) {
-            const int b = __ffs((int)v) - 1;
-            v &= v - 1u;
-            c0 += __ldg(l0 + (size_t)j * 32 + b);
-        }
+        const double *lp = l0 + (size_t)j * 32;
+#pragma unroll
+        for (int b = 0; b < 32; b++)  // independent predicated loads (a serial walk over the set bits was a chain of L2 round trips)
+            if ((v >> b) & 1u) c0 += __ldg(lp + b);
     }
     A0 = vwarp_sum(A0); N0 = vwarp_sum(N0); A1 = vwarp_sum(A1); N1 = vwarp_sum(N1); M = vwarp_sum(M); cnt = vwarp_sum(cnt);
     c0 = vwarp_sum_d(c0);
@@ -949,8 +971,7 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         if (build_window_map(e, v, d_targets, T, mapW, d_wf, d_wl, d_nwin, d_ktot, nullptr)) return 1;
     } else {
         LaunchScope ls(e, K_V_WMAP);
-        v_wmap_kernel<<<(unsigned)(((int64_t)T * 32 + 127) / 128), 128, 0, e->stream>>>(T, d_targets, c->d_tbits, c->H, c->nblk, W, mapW, d_ks,
-                                                                                        d_ke, d_nwin, d_ktot);
+        v_wmap_kernel<<<(unsigned)T, WMAP_WARPS * 32, 0, e->stream>>>(T, d_targets, c->d_tbits, c->H, c->nblk, W, mapW, d_ks, d_ke, d_nwin, d_ktot);
     }
     {
         LaunchScope ls(e, K_V_SORT);
