@@ -178,10 +178,18 @@ __device__ __forceinline__ void lse_add(double &m, double &s, double x) {
     m = up ? x : m;
 }
 
-// the same with the short-chain exp, for the screened candidates of the GEMM epilogue
+// the same with the short-chain exp, for the screened candidates of the GEMM epilogue.  Two tiers: a term more than
+// 12 nats below the running maximum is at most 6e-6 of the sum, so its exponential is taken in fp32 (ex2.approx,
+// relative error ~2e-7: 1e-12 of the sum per term, 1e-8 for ten thousand of them — the window tolerance is 1e-6);
+// rows without a dominant column send most of their survivors through this tier.
 __device__ __forceinline__ void lse_add_fast(double &m, double &s, double x) {
-    const bool up = x > m;
-    const double e = exp_nonpos_fast(up ? m - x : x - m);
+    const double d = x - m;
+    if (d < -12.0) {
+        s += (double)__expf((float)d);
+        return;
+    }
+    const bool up = d > 0.0;
+    const double e = exp_nonpos_fast(up ? -d : d);
     s = up ? fma(s, e, 1.0) : s + e;
     m = up ? x : m;
 }
