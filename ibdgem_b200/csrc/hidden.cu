@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "tc_common.cuh"
 
 namespace ibdgem {
 
@@ -32,12 +33,14 @@ __device__ __forceinline__ int argmax3(double c0, double c1, double c2) {
 // of a normal long double, where the reference's products lose bits and then vanish) are flagged and re-evaluated
 // on the host in long double.  NaN / -inf candidates never flag: their comparisons are exact in both worlds.
 constexpr double LN_LDBL_MIN = -11355.137111933024;  // ln(3.3621e-4932)
+__device__ __forceinline__ double tie_scale(int64_t i) { return (double)(int)(i + 1) * 4.440892098500626e-16; }  // 4 (i + 1) 2^-53
+__device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int best, double scale) {
+    const double w = best == 0 ? c0 : (best == 1 ? c1 : c2);
+    const double r = best == 0 ? fmax(c1, c2) : (best == 1 ? fmax(c0, c2) : fmax(c0, c1));
+    return (w - r) < fma(scale, fabs(w), 1e-12);  // false for NaN and for inf - inf
+}
 __device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int best, int64_t i) {
-    (void)best;
-    const double m01 = fmax(c0, c1), w = fmax(m01, c2);          // winner
-    const double r = fmax(fmin(c0, c1), fmin(m01, c2));          // runner-up
-    const double tol = fma((double)(int)(i + 1) * 4.440892098500626e-16, fabs(w), 1e-12);  // 4 (i + 1) 2^-53 |w| + 1e-12
-    return (w - r) < tol;  // false for NaN and for inf - inf
+    return near_tie(c0, c1, c2, best, tie_scale(i));
 }
 // a finite score below the smallest normal long double: the reference's product is a denormal (or zero) there
 __device__ __forceinline__ bool below_ldbl(double s0, double s1, double s2) {
@@ -86,7 +89,8 @@ viterbi_kernel(int n_tables, const int64_t *__restrict__ start, const int64_t *_
             const double b0_ = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
             const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
             const int k0 = argmax3(a0, a1, a2), k1 = argmax3(b0_, b1, b2), k2 = argmax3(c0, c1, c2);
-            tie |= near_tie(a0, a1, a2, k0, i) | near_tie(b0_, b1, b2, k1, i) | near_tie(c0, c1, c2, k2, i);
+            const double ts = tie_scale(i);
+            tie |= near_tie(a0, a1, a2, k0, ts) | near_tie(b0_, b1, b2, k1, ts) | near_tie(c0, c1, c2, k2, ts);
             s0 = k0 == 0 ? a0 : (k0 == 1 ? a1 : a2);
             s1 = k1 == 0 ? b0_ : (k1 == 1 ? b1 : b2);
             s2 = k2 == 0 ? c0 : (k2 == 1 ? c1 : c2);
@@ -125,8 +129,8 @@ __device__ __forceinline__ void ln_nrm(const double *L, int is_log, double &n0, 
         const double m = fmax(L[0], fmax(L[1], L[2]));
         if (m == -INFINITY) {
             n0 = n1 = n2 = __longlong_as_double(0x7ff8000000000000LL);
-        } else {
-            const double z = m + log(exp(L[0] - m) + exp(L[1] - m) + exp(L[2] - m));
+        } else {  // exp_nonpos: arguments are <= 0, degree-12 polynomial, error ~1 ulp (half the instructions of exp())
+            const double z = m + log(exp_nonpos(L[0] - m) + exp_nonpos(L[1] - m) + exp_nonpos(L[2] - m));
             n0 = L[0] - z; n1 = L[1] - z; n2 = L[2] - z;
         }
     } else {
@@ -212,7 +216,8 @@ viterbi_forward_kernel(int n_tables, const int64_t *__restrict__ len, int is_log
                 const double b0 = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
                 const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
                 const int k0 = argmax3(a0, a1, a2), k1 = argmax3(b0, b1, b2), k2 = argmax3(c0, c1, c2);
-                tie |= near_tie(a0, a1, a2, k0, i) | near_tie(b0, b1, b2, k1, i) | near_tie(c0, c1, c2, k2, i);
+                const double ts = tie_scale(i);
+                tie |= near_tie(a0, a1, a2, k0, ts) | near_tie(b0, b1, b2, k1, ts) | near_tie(c0, c1, c2, k2, ts);
                 s0 = k0 == 0 ? a0 : (k0 == 1 ? a1 : a2);
                 s1 = k1 == 0 ? b0 : (k1 == 1 ? b1 : b2);
                 s2 = k2 == 0 ? c0 : (k2 == 1 ? c1 : c2);
@@ -420,7 +425,8 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
                         const double b0 = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
                         const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
                         const int k0 = argmax3(a0, a1, a2), k1 = argmax3(b0, b1, b2), k2 = argmax3(c0, c1, c2);
-                        tie |= near_tie(a0, a1, a2, k0, i) | near_tie(b0, b1, b2, k1, i) | near_tie(c0, c1, c2, k2, i);
+                        const double ts = tie_scale(i);
+                tie |= near_tie(a0, a1, a2, k0, ts) | near_tie(b0, b1, b2, k1, ts) | near_tie(c0, c1, c2, k2, ts);
                         s0 = k0 == 0 ? a0 : (k0 == 1 ? a1 : a2);
                         s1 = k1 == 0 ? b0 : (k1 == 1 ? b1 : b2);
                         s2 = k2 == 0 ? c0 : (k2 == 1 ? c1 : c2);
