@@ -1147,6 +1147,67 @@ int ibdgem_engine_set_panel_device(ibdgem_engine *e, int64_t n_sites, int32_t n_
     return 0;
 }
 
+// The packed panel of `src` (another engine of this process, usually on another GPU) copied device to device over
+// NVLink, chunk by chunk as src's own upload lands: one PCIe upload per node instead of one per engine.
+int ibdgem_engine_clone_panel(ibdgem_engine *e, ibdgem_engine *src) {
+    if (!e || !src || e == src || !src->have_panel) {
+        set_error("[::] ERROR in ibdgem_engine_clone_panel(): the source engine has no panel.");
+        return 1;
+    }
+    if (e->have_sites && e->S != src->S) {
+        set_error("[::] ERROR: panel has %lld rows but %lld sites were uploaded.", (long long)src->S, (long long)e->S);
+        return 1;
+    }
+    IBD_CUDA(cudaSetDevice(e->device));
+    if (e->have_panel && (e->S != src->S || e->Wh != src->Wh || !e->owns_bits)) {
+        free_prepared(e, e->S);
+        free_panel(e, e->S);
+    }
+    if (!e->have_panel) {
+        e->S = src->S;
+        e->Wh = src->Wh;
+        if (dev_alloc(e, (void **)&e->d_bits, (size_t)e->S * e->Wh * 4)) return 1;
+    }
+    e->N = src->N;
+    if (!e->copy_stream) {
+        IBD_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        IBD_CUDA(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
+    }
+    if (e->device != src->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, e->device, src->device);
+        if (can && cudaDeviceEnablePeerAccess(src->device, 0) == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    }
+    IBD_CUDA(cudaEventRecord(e->ev_order, e->stream));
+    IBD_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_order, 0));
+    // src's chunk layout: a caller-owned source panel (no chunks of its own) is taken as one piece, already complete
+    const size_t nchunk = std::max<size_t>(1, src->chunk_end.size());
+    while (e->chunk_ev.size() < nchunk) {
+        cudaEvent_t ev;
+        IBD_CUDA(cudaEventCreateWithFlags(&ev, e->t0_set ? cudaEventDefault : cudaEventDisableTiming));
+        e->chunk_ev.push_back(ev);
+    }
+    e->chunk_end.assign(nchunk, 0);
+    int64_t s0 = 0;
+    for (size_t k = 0; k < nchunk; k++) {
+        const int64_t s1 = src->chunk_end.empty() ? src->S : src->chunk_end[k];
+        if (!src->chunk_end.empty()) IBD_CUDA(cudaStreamWaitEvent(e->copy_stream, src->chunk_ev[k], 0));
+        IBD_CUDA(cudaMemcpyPeerAsync(e->d_bits + (size_t)s0 * e->Wh, e->device, src->d_bits + (size_t)s0 * e->Wh, src->device,
+                                     (size_t)(s1 - s0) * e->Wh * 4, e->copy_stream));
+        IBD_CUDA(cudaEventRecord(e->chunk_ev[k], e->copy_stream));
+        e->chunk_end[k] = s1;
+        s0 = s1;
+    }
+    e->chunks_waited = 0;
+    e->have_panel = true;
+    e->owns_bits = true;
+    e->prepared = false;
+    e->table_from = e->table_upto = 0;
+    ld_tensor_invalidate(e);
+    ld_vtensor_invalidate(e);
+    return 0;
+}
+
 int ibdgem_engine_panel_rows_ready(ibdgem_engine *e, int64_t row_end, void *stream) {
     if (!e || !e->have_panel || e->owns_bits) {
         set_error("[::] ERROR in ibdgem_engine_panel_rows_ready(): no caller-owned device panel is set.");

@@ -17,6 +17,8 @@
 #include <ctime>
 #include <string>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -220,7 +222,17 @@ int fail_engine() {
 }
 
 // Scores targets [t0, t1) on one device and writes their two tables.
-int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
+// --gpus N: device 0's engine is the one that uploads the panel over PCIe; the others clone it over NVLink
+// (ibdgem_engine_clone_panel) as its chunks land.  The engine pointer is published once its upload has been issued.
+struct PanelSource {
+    std::mutex mu;
+    std::condition_variable cv;
+    ibdgem_engine *engine = nullptr;
+    bool failed = false;
+    std::atomic<int> users{0};  // clones still reading from it
+};
+
+int run_shard(Shared *sh, int device, size_t t0, size_t t1, PanelSource *psrc = nullptr) {
     const Options &o = *sh->opt;
     const PackedPanel &P = *sh->panel;
     const size_t S = (size_t)P.S;
@@ -233,11 +245,31 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
     prm.variable_sites_only = o.opt_v;
     prm.device = device;
     ibdgem_engine *e = nullptr;
+    struct Release {  // a clone stops reading the source engine's panel at the latest when its shard is done (any exit path)
+        PanelSource *p;
+        ~Release() { if (p) p->users.fetch_sub(1); }
+    } release{psrc && device != 0 ? psrc : nullptr};
     if (ibdgem_engine_create(&prm, &e)) return fail_engine();
     if (ibdgem_engine_upload_sites(e, P.S, P.pos.data(), P.n_ref.data(), P.n_alt.data(), P.host_keep.data(),
-                                   P.af_user.empty() ? nullptr : P.af_user.data()) ||
-        ibdgem_engine_upload_panel(e, P.S, P.N, P.bits.data(), P.Wh) || ibdgem_engine_prepare(e))
+                                   P.af_user.empty() ? nullptr : P.af_user.data()))
         return fail_engine();
+    if (psrc && device != 0) {
+        std::unique_lock<std::mutex> lk(psrc->mu);
+        psrc->cv.wait(lk, [&] { return psrc->engine || psrc->failed; });
+        if (psrc->failed) return 1;
+        if (ibdgem_engine_clone_panel(e, psrc->engine)) return fail_engine();
+    } else {
+        const int urc = ibdgem_engine_upload_panel(e, P.S, P.N, P.bits.data(), P.Wh);
+        if (psrc) {
+            std::lock_guard<std::mutex> lk(psrc->mu);
+            psrc->engine = urc ? nullptr : e;
+            psrc->failed = urc != 0;
+            psrc->cv.notify_all();
+        }
+        if (urc) return fail_engine();
+    }
+    if (ibdgem_engine_prepare(e)) return fail_engine();
+
     std::vector<double> f(S), lik7(S * 7);
     std::vector<uint8_t> st_shared(S);
     if (ibdgem_engine_get_site_table(e, f.data(), st_shared.data(), lik7.data())) return fail_engine();
@@ -428,6 +460,8 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1) {
         }
         if (write_rc) return 1;
     }
+    if (psrc && device == 0)
+        while (psrc->users.load() > 0) std::this_thread::yield();  // clones may still be copying from this engine's panel
     ibdgem_engine_destroy(e);
     return 0;
 }
@@ -683,10 +717,12 @@ int main(int argc, char *argv[]) {
         std::vector<std::thread> th;
         std::vector<int> rcs((size_t)gpus, 0);
         const size_t n = sh.targets.size();
+        PanelSource psrc;
+        psrc.users = gpus - 1;
         for (int d = 0; d < gpus; d++) {
             const size_t base = n / (size_t)gpus, extra = n % (size_t)gpus;
             const size_t lo = (size_t)d * base + std::min<size_t>((size_t)d, extra), hi = lo + base + ((size_t)d < extra ? 1 : 0);
-            th.emplace_back([&, d, lo, hi] { rcs[(size_t)d] = run_shard(&sh, d, lo, hi); });
+            th.emplace_back([&, d, lo, hi] { rcs[(size_t)d] = run_shard(&sh, d, lo, hi, &psrc); });
         }
         for (auto &t : th) t.join();
         for (int r : rcs) rc |= r;

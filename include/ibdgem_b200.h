@@ -122,6 +122,11 @@ int ibdgem_engine_set_panel_device(ibdgem_engine *e, int64_t n_sites, int32_t n_
                                    const uint32_t *d_bits, int64_t words_per_site);
 int ibdgem_engine_panel_rows_ready(ibdgem_engine *e, int64_t row_end, void *stream);
 
+/* Panel copied from another engine of the same process (usually on another GPU), device to device over NVLink, chunk
+ * by chunk as the source's own upload lands: `ibdgem --gpus N` uploads the panel over PCIe once and clones it N-1
+ * times.  `src` must stay alive, with its panel unchanged, until this engine's next call that returns results. */
+int ibdgem_engine_clone_panel(ibdgem_engine *e, ibdgem_engine *src);
+
 /* Target-independent stage: allele frequency by popcount over the packed row (find_f_impute /
  * find_f_vcf, src/ibd-parse.c:91-110), the AF-range and max-cov filters (src/ibdgem.c:616-626),
  * per-site IBD0 / IBD1[g] / IBD2[g] (find_pDgf, find_pDgIBD1, src/ibd-math.c:84-142) and the
