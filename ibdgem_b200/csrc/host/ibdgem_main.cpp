@@ -249,6 +249,17 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1, PanelSource *psrc = 
         PanelSource *p;
         ~Release() { if (p) p->users.fetch_sub(1); }
     } release{psrc && device != 0 ? psrc : nullptr};
+    struct Publish {  // device 0 leaving before it has published its engine must not leave the clones waiting
+        PanelSource *p;
+        bool done = false;
+        ~Publish() {
+            if (p && !done) {
+                std::lock_guard<std::mutex> lk(p->mu);
+                p->failed = true;
+                p->cv.notify_all();
+            }
+        }
+    } publish{psrc && device == 0 ? psrc : nullptr};
     if (ibdgem_engine_create(&prm, &e)) return fail_engine();
     if (ibdgem_engine_upload_sites(e, P.S, P.pos.data(), P.n_ref.data(), P.n_alt.data(), P.host_keep.data(),
                                    P.af_user.empty() ? nullptr : P.af_user.data()))
@@ -265,6 +276,7 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1, PanelSource *psrc = 
             psrc->engine = urc ? nullptr : e;
             psrc->failed = urc != 0;
             psrc->cv.notify_all();
+            publish.done = true;
         }
         if (urc) return fail_engine();
     }
