@@ -353,7 +353,7 @@ def main():
         d_ll = torch.empty((T, maxW, 3), dtype=torch.float64, device=dev)
         dst = d_ll.data_ptr()
     cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr(), o_we.data_ptr(), o_wn.data_ptr(), o_ll.data_ptr(),
-                  None, None, None, None, None, None, dst)
+                  None, None, None, None, None, None, None, dst)
 
     # N > 1: the packed panel is the same on every rank, so each rank copies 1/N of it over PCIe and the
     # ranks all_gather the pieces over NVLink (shard.replicate_panel) instead of N full uploads

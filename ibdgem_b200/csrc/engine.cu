@@ -30,6 +30,7 @@ static const char *const kKernelNameList[] = {
     "ld_stage",       "ld_expand_bg",  "ld_expand_tgt", "ld_windows",   "ld_ibd0",
     "ld_mma",         "viterbi",       "viterbi_norm",  "viterbi_back", "viterbi_out", "fill",
     "v_slots",        "v_wmap",        "v_tw",          "v_sort",       "v_expand_a",  "v_expand_b",   "ld_vmma",
+    "window_linear",
 };
 static_assert(sizeof(kKernelNameList) / sizeof(kKernelNameList[0]) == K_COUNT, "one name per KernelId, in enum order");
 const char *const *const kKernelNames = kKernelNameList;
@@ -507,6 +508,45 @@ window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restric
         ws[o] = pos[s0];
         we[o] = pos[s1];
     }
+}
+
+// K_WINDOW_LINEAR: the reference's own window aggregates, bit for bit — one thread per (target, window) multiplies
+// the per-site likelihoods in file order with round-to-nearest fp64 products starting from 1.0, exactly the sequence
+// of src/ibdgem.c:562, 665-667 (no fused operations, no reassociation), so denormals and the underflow to 0 come out
+// as they do there.  The per-site values themselves are the reference's doubles (tab.txt columns, tested).
+__global__ void __launch_bounds__(128)
+window_linear_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ targets, int T, const double *__restrict__ f,
+                     const double *__restrict__ lik7, const double *__restrict__ Ptab, int C, int outW, double *__restrict__ wlin) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T * outW) return;
+    const int t = (int)(i / outW), w = (int)(i % outW);
+    const int row = (m.rows == 1) ? 0 : t;
+    if (w >= m.nwin[row] || w >= m.maxW) return;
+    const int indiv = targets[t];
+    const int64_t s0 = m.wfirst[(int64_t)row * m.maxW + w], s1 = m.wlast[(int64_t)row * m.maxW + w];
+    double p0 = 1.0, p1 = 1.0, p2 = 1.0;
+    for (int64_t s = s0; s <= s1; s++) {
+        int r, a, g;
+        if (site_eval(v, t, indiv, s, r, a, g) != 1) continue;
+        double l0, l1, l2;
+        if (v.tgt_counts) {
+            const double *P = Ptab + (size_t)(r * C + a) * 3;
+            l0 = lik_ibd0(f[s], P[0], P[1], P[2]);
+            l1 = lik_ibd1(g, f[s], P[0], P[1], P[2]);
+            l2 = P[g];
+        } else {
+            const double *L = lik7 + s * 7;
+            l0 = L[0];
+            l1 = L[1 + g];
+            l2 = L[4 + g];
+        }
+        p0 = __dmul_rn(p0, l0);
+        p1 = __dmul_rn(p1, l1);
+        p2 = __dmul_rn(p2, l2);
+    }
+    wlin[i * 3 + 0] = p0;
+    wlin[i * 3 + 1] = p1;
+    wlin[i * 3 + 2] = p2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1404,7 +1444,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     const bool shared = !vflag && !tgt_counts;
     const int mapW = shared ? std::max(e->nW_shared, 1) : (int)(S / e->prm.window_size + 2);
     const bool want_windows = out->n_windows || out->w_start || out->w_end || out->w_nsites || out->w_loglik ||
-                              out->w_loglik_device;
+                              out->w_loglik_device || out->w_lik_linear;
     const int outW = want_windows ? out->max_windows : mapW;
     if (want_windows && outW <= 0) {
         set_error("[::] ERROR: ibdgem_scores.max_windows must be positive.");
@@ -1583,6 +1623,21 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     }
 
     if (e->shard_count == 1 && ensure_table(e, S)) return 1;  // no-op unless the tensor path left a tail
+    // the reference's own linear window products, on request (not for --LD with per-target windows: that path keeps its
+    // window map in rank space)
+    double *d_wlin = nullptr;
+    if (out->w_lik_linear && e->shard_count == 1) {
+        if (scratch(e, SC_WLIN, nWT * 24, (void **)&d_wlin)) return 1;
+        {
+            LaunchScope ls(e, K_FILL);
+            fill_nan_kernel<<<(unsigned)std::min<int64_t>((int64_t)(nWT * 3 + 255) / 256, 4096), 256, 0, e->stream>>>(d_wlin, (int64_t)nWT * 3);
+        }
+        if (!vtensor) {
+            LaunchScope ls(e, K_WINDOW_LINEAR);
+            window_linear_kernel<<<(unsigned)((nWT + 127) / 128), 128, 0, e->stream>>>(v, m, d_targets, T, e->d_f, e->d_lik7, e->d_P, C, outW, d_wlin);
+        }
+        IBD_CUDA(cudaGetLastError());
+    }
     // counters
     const bool want_counters = out->processed || out->skipped || out->final_total_cov || out->final_dist;
     unsigned long long *d_cnt = nullptr;
@@ -1619,6 +1674,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         IBD_CUDA(cudaMemcpyAsync(out->w_loglik_device, d_wll, nWT * 24, cudaMemcpyDefault, e->stream));
     if (out->w_loglik && !e->wll_streamed)
         IBD_CUDA(cudaMemcpyAsync(out->w_loglik, d_wll, nWT * 24, cudaMemcpyDeviceToHost, e->stream));
+    if (d_wlin) IBD_CUDA(cudaMemcpyAsync(out->w_lik_linear, d_wlin, nWT * 24, cudaMemcpyDeviceToHost, e->stream));
     if (e->t0_set) IBD_CUDA(cudaEventRecord(e->ev_wll, e->wll_streamed ? e->d2h_stream : e->stream));
     // the bookkeeping arrays of the tensor path are final before the GEMM starts: copy them on the
     // copy stream so the transfer overlaps it

@@ -309,6 +309,10 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1, PanelSource *psrc = 
         std::vector<int32_t> nw(T), wn(T * (size_t)maxW);
         std::vector<uint64_t> ws(T * (size_t)maxW), we(T * (size_t)maxW), processed(T), skipped(T), totcov(T), fdist(T * (size_t)C);
         std::vector<double> wll(T * (size_t)maxW * 3);
+        // the reference's own linear window products (bit for bit, underflow included): the three columns of a non-LD
+        // summary row and LIBD2 of an --LD row are printed from them, so those columns are the reference's bytes
+        const bool want_linear = !(o.ld && per_target);
+        std::vector<double> wlin(want_linear ? T * (size_t)maxW * 3 : 0);
         std::vector<uint8_t> sst;
         std::vector<double> slik;
         ibdgem_scores sc{};
@@ -316,6 +320,7 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1, PanelSource *psrc = 
         sc.n_windows = nw.data(); sc.w_start = ws.data(); sc.w_end = we.data(); sc.w_nsites = wn.data();
         sc.w_loglik = wll.data(); sc.processed = processed.data(); sc.skipped = skipped.data();
         sc.final_total_cov = totcov.data(); sc.final_dist = fdist.data();
+        if (want_linear) sc.w_lik_linear = wlin.data();
         if (per_target) {
             sst.resize(T * S);
             sc.site_status = sst.data();
@@ -426,9 +431,10 @@ int run_shard(Shared *sh, int device, size_t t0, size_t t1, PanelSource *psrc = 
             for (int w = 0; w < nw[k]; w++) {
                 const size_t i = k * (size_t)maxW + (size_t)w;
                 char e0[40], e1[40], e2[40];
-                put_e(e0, exp(wll[i * 3]));
-                put_e(e1, exp(wll[i * 3 + 1]));
-                put_e(e2, exp(wll[i * 3 + 2]));
+                const bool lin = want_linear && wlin[i * 3 + 2] == wlin[i * 3 + 2];
+                put_e(e0, lin && !o.ld ? wlin[i * 3] : exp(wll[i * 3]));
+                put_e(e1, lin && !o.ld ? wlin[i * 3 + 1] : exp(wll[i * 3 + 1]));
+                put_e(e2, lin ? wlin[i * 3 + 2] : exp(wll[i * 3 + 2]));
                 fprintf(sum, "%d\t%lu\t%lu\t%s\t%s\t%s\t%d\n", w + 1, (unsigned long)ws[i], (unsigned long)we[i], e0, e1, e2, wn[i]);
             }
             fclose(sum);

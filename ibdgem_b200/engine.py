@@ -25,7 +25,7 @@ class _CScores(C.Structure):
                 ("w_end", C.c_void_p), ("w_nsites", C.c_void_p), ("w_loglik", C.c_void_p),
                 ("processed", C.c_void_p), ("skipped", C.c_void_p), ("final_total_cov", C.c_void_p),
                 ("final_dist", C.c_void_p), ("site_status", C.c_void_p), ("site_lik", C.c_void_p),
-                ("w_loglik_device", C.c_void_p)]
+                ("w_lik_linear", C.c_void_p), ("w_loglik_device", C.c_void_p)]
 
 
 @dataclass
@@ -54,6 +54,7 @@ class Scores:
     final_dist: np.ndarray
     site_status: np.ndarray | None = None
     site_lik: np.ndarray | None = None
+    w_lik_linear: np.ndarray | None = None
     extra: dict = field(default_factory=dict)
 
 
@@ -152,7 +153,7 @@ class Engine:
         return f, st, lik7
 
     # -- scoring ----------------------------------------------------------------------------
-    def _alloc_scores(self, T, max_windows, expanded, device_out):
+    def _alloc_scores(self, T, max_windows, expanded, device_out, linear=False):
         C_ = self.params.max_cov + 1
         s = Scores(np.zeros(T, np.int32), np.zeros((T, max_windows), np.uint64),
                    np.zeros((T, max_windows), np.uint64), np.zeros((T, max_windows), np.int32),
@@ -161,29 +162,31 @@ class Engine:
         if expanded:
             s.site_status = np.zeros((T, self.S), np.uint8)
             s.site_lik = np.zeros((T, self.S, 3))
+        if linear:
+            s.w_lik_linear = np.full((T, max_windows, 3), np.nan)
         cs = _CScores(max_windows, _ptr(s.n_windows), _ptr(s.w_start), _ptr(s.w_end), _ptr(s.w_nsites),
                       _ptr(s.w_loglik), _ptr(s.processed), _ptr(s.skipped), _ptr(s.final_total_cov),
-                      _ptr(s.final_dist), _ptr(s.site_status), _ptr(s.site_lik),
+                      _ptr(s.final_dist), _ptr(s.site_status), _ptr(s.site_lik), _ptr(s.w_lik_linear),
                       C.c_void_p(device_out) if device_out else None)
         return s, cs
 
     def default_max_windows(self):
         return self.S // max(self.params.window_size, 1) + 2
 
-    def score_nonld(self, targets, tgt_counts=None, max_windows=None, expanded=False, device_out=0) -> Scores:
+    def score_nonld(self, targets, tgt_counts=None, max_windows=None, expanded=False, device_out=0, linear=False) -> Scores:
         targets = np.ascontiguousarray(targets, np.int32)
         T = len(targets)
-        s, cs = self._alloc_scores(T, max_windows or self.default_max_windows(), expanded, device_out)
+        s, cs = self._alloc_scores(T, max_windows or self.default_max_windows(), expanded, device_out, linear)
         tc = None if tgt_counts is None else np.ascontiguousarray(tgt_counts, np.uint8)
         self._check(self._lib.ibdgem_engine_score_nonld(self._h, C.c_int32(T), _ptr(targets), _ptr(tc), C.byref(cs)))
         return s
 
     def score_ld(self, targets, bg, pu_idx=-1, tgt_counts=None, max_windows=None, expanded=False,
-                 device_out=0) -> Scores:
+                 device_out=0, linear=False) -> Scores:
         targets = np.ascontiguousarray(targets, np.int32)
         bg = np.ascontiguousarray(bg, np.int32)
         T = len(targets)
-        s, cs = self._alloc_scores(T, max_windows or self.default_max_windows(), expanded, device_out)
+        s, cs = self._alloc_scores(T, max_windows or self.default_max_windows(), expanded, device_out, linear)
         tc = None if tgt_counts is None else np.ascontiguousarray(tgt_counts, np.uint8)
         self._check(self._lib.ibdgem_engine_score_ld(self._h, C.c_int32(T), _ptr(targets), C.c_int32(len(bg)),
                                                      _ptr(bg), C.c_int32(pu_idx), _ptr(tc), C.byref(cs)))

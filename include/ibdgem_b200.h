@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define IBDGEM_B200_ABI_VERSION 1
+#define IBDGEM_B200_ABI_VERSION 2
 #define IBDGEM_MAX_COV_LIMIT 127 /* src/pileup.h:12 MAX_COV 128: lines with cov >= 128 are dropped */
 
 typedef struct ibdgem_engine ibdgem_engine;
@@ -62,6 +62,13 @@ typedef struct ibdgem_scores {
     uint64_t *final_dist;      /* [T][C] "# FINAL COVERAGE DISTRIBUTION" */
     uint8_t *site_status;      /* [T][S]    optional expanded per-target site status */
     double *site_lik;          /* [T][S][3] optional expanded LIBD0, LIBD1, LIBD2 of each tab row (linear) */
+    double *w_lik_linear;      /* [T][maxW][3] optional: the reference's OWN window aggregates — running fp64 products of
+                                  the per-site likelihoods in file order, starting from 1.0 (sum_ibd0 *= ibd0 ...,
+                                  src/ibdgem.c:562, 665-667) — bit for bit, underflow to denormals and 0 included, so
+                                  that a formatter can print summary.txt columns identical to the reference's.  These are
+                                  the three columns of a non-LD row and the LIBD2 column of an --LD row (the --LD means
+                                  over the background have no linear-space twin; take those from w_loglik).  Not
+                                  available for --LD runs with -v / -D (rows stay NaN). */
     void *w_loglik_device;     /* optional DEVICE pointer: [T][maxW][3] doubles are also written here, for the
                                   device-resident hiddengem front-end or as this rank's block of a gathered
                                   table in another GPU's memory (ibdgem_peer_open).  The tensor --LD path

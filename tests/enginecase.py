@@ -49,10 +49,11 @@ def run_engine(case, device=0, force_general=False, expanded=True, align_words=4
             tc = draw_downsampled_counts(case, f, st_shared != 0)
         if force_general:
             e.force_general_ld(True)
+        linear = not (prm.ld_mode and (prm.opt_v or tc is not None))  # not offered for --LD with per-target windows
         if prm.ld_mode:
-            sc = e.score_ld(case.targets, case.bg, prm.pu_idx, tgt_counts=tc, expanded=expanded)
+            sc = e.score_ld(case.targets, case.bg, prm.pu_idx, tgt_counts=tc, expanded=expanded, linear=linear)
         else:
-            sc = e.score_nonld(case.targets, tgt_counts=tc, expanded=expanded)
+            sc = e.score_nonld(case.targets, tgt_counts=tc, expanded=expanded, linear=linear)
         stats = e.kernel_stats()
     results = []
     for k, t in enumerate(case.targets):
@@ -72,6 +73,7 @@ def run_engine(case, device=0, force_general=False, expanded=True, align_words=4
                    w_nsites=sc.w_nsites[k, :nw], w_log=ll, w_lin=lin, processed=int(sc.processed[k]),
                    skipped=int(sc.skipped[k]), final_total_cov=int(sc.final_total_cov[k]),
                    final_dist=sc.final_dist[k], ld_path=sc.extra.get("ld_path"), lik7=lik7,
+                   w_lin_exact=(sc.w_lik_linear[k, :nw] if linear else None), ld_mode=bool(prm.ld_mode),
                    st_shared=st_shared, kernel_stats=stats)
         results.append(res)
     return results
@@ -100,6 +102,11 @@ def assert_matches_oracle(res, ora, ll_atol=1e-6, site_rtol=1e-9):
             np.testing.assert_allclose(a, b, rtol=site_rtol, atol=0)
             la, lb = np.log(a), np.log(b)
             assert np.all(np.abs(la - lb) <= site_rtol * np.abs(lb) + 1e-300)
+    if res.get("w_lin_exact") is not None:
+        # the reference's own linear window products, bit for bit (denormals and zeros included): all three columns
+        # of a non-LD row, the LIBD2 column of an --LD row
+        cols = [2] if res["ld_mode"] else [0, 1, 2]
+        np.testing.assert_array_equal(res["w_lin_exact"][:, cols], ora["w_lin"][:, cols])
     a, b = res["w_log"], ora["w_log"]
     assert a.shape == b.shape
     nan_a, nan_b = np.isnan(a), np.isnan(b)

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = ib.load_library()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.ibdgem_abi_version() == 1
+    assert lib.ibdgem_abi_version() == 2
 
 
 def test_no_cpu_fallback():

@@ -88,7 +88,7 @@ def leg_c2(torch, ib, bits, pos, N, steps=5, ref_dir=None, cpu_sites=10_000):
     o_ll = _pinned(torch, (T, maxW, 3), torch.float64)
     cnt = [np.zeros(T, np.uint64) for _ in range(3)] + [np.zeros((T, 21), np.uint64)]
     cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr(), o_we.data_ptr(), o_wn.data_ptr(), o_ll.data_ptr(),
-                  cnt[0].ctypes.data, cnt[1].ctypes.data, cnt[2].ctypes.data, cnt[3].ctypes.data, None, None, None)
+                  cnt[0].ctypes.data, cnt[1].ctypes.data, cnt[2].ctypes.data, cnt[3].ctypes.data, None, None, None, None)
     with ib.Engine(ib.Params(window_size=W, device=torch.cuda.current_device())) as e:
         e.set_stream(stream.cuda_stream)
 
@@ -253,7 +253,7 @@ def leg_ld(torch, ib, bits, pos, n_ref, n_alt, N, T, W, steps, variable_sites_on
     o_wn = _pinned(torch, (T, maxW), torch.int32)
     o_ll = _pinned(torch, (T, maxW, 3), torch.float64)
     cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr(), o_we.data_ptr(), o_wn.data_ptr(), o_ll.data_ptr(),
-                  None, None, None, None, None, None, None)
+                  None, None, None, None, None, None, None, None)
     with ib.Engine(ib.Params(window_size=W, variable_sites_only=variable_sites_only, device=torch.cuda.current_device())) as e:
         e.set_stream(stream.cuda_stream)
         e.upload_sites(pos, n_ref, n_alt, keep)
@@ -307,7 +307,7 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
     if table.is_root and table.ok:
         table.tensor().fill_(float("nan"))
     cs = _CScores(maxW, o_nw.data_ptr(), o_ws.data_ptr() if book else None, o_we.data_ptr() if book else None,
-                  o_wn.data_ptr() if book else None, o_ll.data_ptr(), None, None, None, None, None, None,
+                  o_wn.data_ptr() if book else None, o_ll.data_ptr(), None, None, None, None, None, None, None,
                   table.ptr if table.ok else None)
     d_panel = torch.empty((S, bits.shape[1]), dtype=torch.int32, device=dev)
     up_stream = torch.cuda.Stream(device=dev)
