@@ -42,6 +42,27 @@ __device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int be
 __device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int best, int64_t i) {
     return near_tie(c0, c1, c2, best, tie_scale(i));
 }
+// One target state of one bin, branch-free: the three candidates, the reference's arg-max (strict '>', lowest index
+// wins, NaN never wins — src/hiddengem.c:91-99) and the near-tie test.  The tie test here is the cheaper superset
+// "ANY two candidates closer than the tolerance" (three subtractions and compares instead of fp64 min / max
+// networks): it can only flag more tables, never fewer.
+struct Step3 {
+    double v;
+    int k;
+    bool tie;
+};
+__device__ __forceinline__ Step3 step3(double c0, double c1, double c2, double scale) {
+    Step3 o;
+    const bool g1 = c1 > c0;
+    const double m01 = g1 ? c1 : c0;
+    const bool g2 = c2 > m01;
+    o.v = g2 ? c2 : m01;
+    o.k = g2 ? 2 : (g1 ? 1 : 0);
+    const double tol = fma(scale, fabs(o.v), 1e-12);  // |winner|: finite whenever any candidate is
+    o.tie = (fabs(c0 - c1) < tol) | (fabs(c0 - c2) < tol) | (fabs(c1 - c2) < tol);  // false for NaN and inf - inf
+    return o;
+}
+
 // a finite score below the smallest normal long double: the reference's product is a denormal (or zero) there
 __device__ __forceinline__ bool below_ldbl(double s0, double s1, double s2) {
     return (s0 < LN_LDBL_MIN && s0 > -INFINITY) || (s1 < LN_LDBL_MIN && s1 > -INFINITY) || (s2 < LN_LDBL_MIN && s2 > -INFINITY);
@@ -401,7 +422,9 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
             }
         }
     } else {
-        // ===== solver: lane = table =====
+        // ===== solver: lane = table.  A single warp walks the bins, so its time is (instructions per bin) x (issue
+        // latency): the step is branch-free and starts from s = 0, which makes bin 0 an ordinary step (the diagonal
+        // candidate wins there, s_k = ln nrm_k exactly; its back-pointers are never followed). =====
         const int lane = threadIdx.x;
         const int64_t n = s_len[lane];
         double s0 = 0, s1 = 0, s2 = 0;
@@ -411,33 +434,26 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
             if (b == 0) asm volatile("bar.sync 1, %0;" ::"n"(VF_THREADS) : "memory");
             else asm volatile("bar.sync 2, %0;" ::"n"(VF_THREADS) : "memory");
             const int64_t i0 = (int64_t)c * VF_BINS;
+            const double *nr = &nrm[b][lane][0];
+            double *so = &sco[b][lane][0];
+            const int nq = (int)min((int64_t)VF_BINS, n - i0);  // bins of this table in the chunk (<= 0: none)
 #pragma unroll 4
             for (int q = 0; q < VF_BINS; q++) {
-                const int64_t i = i0 + q;
-                if (i < n) {
-                    const double n0 = nrm[b][lane][q * 3], n1 = nrm[b][lane][q * 3 + 1], n2 = nrm[b][lane][q * 3 + 2];
-                    uint8_t from;
-                    if (i == 0) {
-                        s0 = n0; s1 = n1; s2 = n2;
-                        from = 0 | (1 << 2) | (2 << 4);
-                    } else {
-                        const double a0 = s0 + n0, a1 = (s1 + n0) + lp01, a2 = (s2 + n0) + lp02;
-                        const double b0 = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
-                        const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
-                        const int k0 = argmax3(a0, a1, a2), k1 = argmax3(b0, b1, b2), k2 = argmax3(c0, c1, c2);
-                        const double ts = tie_scale(i);
-                tie |= near_tie(a0, a1, a2, k0, ts) | near_tie(b0, b1, b2, k1, ts) | near_tie(c0, c1, c2, k2, ts);
-                        s0 = k0 == 0 ? a0 : (k0 == 1 ? a1 : a2);
-                        s1 = k1 == 0 ? b0 : (k1 == 1 ? b1 : b2);
-                        s2 = k2 == 0 ? c0 : (k2 == 1 ? c1 : c2);
-                        from = (uint8_t)(k0 | (k1 << 2) | (k2 << 4));
-                    }
-                    if (!is_log) tie |= below_ldbl(s0, s1, s2);
-                    sco[b][lane][q * 3] = s0;
-                    sco[b][lane][q * 3 + 1] = s1;
-                    sco[b][lane][q * 3 + 2] = s2;
-                    frm[b][q][lane] = from;
-                }
+                const double n0 = nr[q * 3], n1 = nr[q * 3 + 1], n2 = nr[q * 3 + 2];
+                const double ts = (double)(int)(i0 + q + 1) * 4.440892098500626e-16;
+                const Step3 A = step3(s0 + n0, (s1 + n0) + lp01, (s2 + n0) + lp02, ts);
+                const Step3 B = step3((s0 + n1) + lp01, s1 + n1, (s2 + n1) + lp12, ts);
+                const Step3 Cc = step3((s0 + n2) + lp02, (s1 + n2) + lp12, s2 + n2, ts);
+                const bool live = q < nq;
+                s0 = live ? A.v : s0;
+                s1 = live ? B.v : s1;
+                s2 = live ? Cc.v : s2;
+                tie |= live & (i0 + q > 0) & (A.tie | B.tie | Cc.tie);
+                if (!is_log) tie |= live & below_ldbl(s0, s1, s2);
+                so[q * 3] = s0;
+                so[q * 3 + 1] = s1;
+                so[q * 3 + 2] = s2;
+                frm[b][q][lane] = (uint8_t)(A.k | (B.k << 2) | (Cc.k << 4));
             }
             __threadfence_block();
             if (b == 0) asm volatile("bar.arrive 3, %0;" ::"n"(VF_THREADS) : "memory");
@@ -556,7 +572,10 @@ int viterbi_on_device(ibdgem_engine *e, int n_tables, int64_t maxbins, int64_t t
         double *d_last;
         uint8_t *d_fromT;
         const size_t cells = (size_t)maxbins * n_tables;
-        static const int fused = [] { const char *s = getenv("IBDGEM_VITERBI_FUSED"); return s ? atoi(s) : 1; }();
+        static const int fused_env = [] { const char *s = getenv("IBDGEM_VITERBI_FUSED"); return s ? atoi(s) : 1; }();
+        // the fused kernel starts from s = 0 and treats bin 0 as an ordinary step, which is the reference's bin 0 only
+        // while no switch is rewarded (penalties <= 1)
+        const bool fused = fused_env && p01 <= 1.0 && p02 <= 1.0 && p12 <= 1.0;
         if (scratch(e, SC_HG_FROMT, cells, (void **)&d_fromT) || scratch(e, SC_HG_LAST, (size_t)n_tables * 24, (void **)&d_last)) return 1;
         const dim3 tiles((unsigned)((n_tables + 31) / 32), (unsigned)((maxbins + 31) / 32));
         if (fused) {
