@@ -1071,7 +1071,6 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     if (scratch(e, SC_MMA_UNIT, 64, (void **)&d_unit)) return 1;
     IBD_CUDA(cudaFuncSetAttribute(ld_vmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int u0 = 0;
-    bool slabs_uploaded = false;
     // slab offsets restart at every batch; all batches' offsets go up in one copy
     std::vector<std::pair<int, int>> batches;
     std::vector<int64_t> batch_slabs;
@@ -1088,8 +1087,6 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         u0 = u1;
     }
     IBD_CUDA(cudaMemcpyAsync(d_tile_slab, h_slab.data(), (size_t)n_tiles * 8, cudaMemcpyHostToDevice, e->stream));
-    slabs_uploaded = true;
-    (void)slabs_uploaded;
     int64_t max_slabs = 0;
     for (auto s : batch_slabs) max_slabs = std::max(max_slabs, s);
     unsigned char *d_A;

@@ -115,6 +115,12 @@ class Engine:
         self._check(self._lib.ibdgem_engine_upload_panel(self._h, C.c_int64(bits.shape[0]), C.c_int32(n_indiv),
                                                          _ptr(bits), C.c_int64(bits.shape[1])))
 
+    def clone_panel(self, src: "Engine"):
+        """Panel copied device to device from another engine of this process (ibdgem_engine_clone_panel)."""
+        self._bits = None
+        self.N = src.N
+        self._check(self._lib.ibdgem_engine_clone_panel(self._h, src._h))
+
     def set_panel_device(self, d_bits_ptr: int, n_sites: int, n_indiv: int, words_per_site: int):
         """Panel rows live in caller-owned device memory (see shard.replicate_panel); declare them
         readable piece by piece with panel_rows_ready()."""

@@ -663,3 +663,29 @@ def test_hiddengem_near_tie_guard_flags_and_matches_long_double():
         np.testing.assert_array_equal(state[a:b], st)
         np.testing.assert_array_equal(counts[i], np.bincount(st, minlength=3))
         np.testing.assert_allclose(score[a:b], sc, rtol=0, atol=1e-7)
+
+
+def test_panel_cloned_from_another_engine():
+    """ibdgem_engine_clone_panel (what `ibdgem --gpus N` does for devices 1 .. N-1, here between two engines on one
+    GPU): the clone follows the source's upload chunk by chunk and scores exactly like an engine that uploaded."""
+    import torch
+    import ibdgem_b200 as ib
+    ec = _engine()
+    case = _synth_case(91, 50_000, 300, 100, True, range(5), pu_idx=2)
+    pk = case.pk
+    want = ec.run_engine(case, expanded=False)
+    bits = torch.from_numpy(ib.pack_bits(pk.hap).view(np.int32)).pin_memory()  # page-locked: the source's upload is asynchronous
+    with ib.Engine(ib.Params(window_size=100)) as src, ib.Engine(ib.Params(window_size=100)) as dst:
+        src.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, None)
+        src.upload_panel(bits.numpy().view(np.uint32), len(pk.names))
+        dst.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, None)
+        dst.clone_panel(src)
+        sc = dst.score_ld(case.targets, case.bg, 2)
+        for k, w in enumerate(want):
+            nw = w["n_windows"]
+            assert int(sc.n_windows[k]) == nw
+            np.testing.assert_allclose(sc.w_loglik[k, :nw], w["w_log"], rtol=0, atol=1e-9)
+            np.testing.assert_array_equal(sc.w_nsites[k, :nw], w["w_nsites"])
+    with ib.Engine(ib.Params(window_size=100)) as a, ib.Engine(ib.Params(window_size=100)) as b:
+        with pytest.raises(RuntimeError, match="no panel"):
+            b.clone_panel(a)
