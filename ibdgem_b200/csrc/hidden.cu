@@ -332,7 +332,7 @@ viterbi_out_kernel(int n_tables, const int64_t *__restrict__ start, const int64_
 // viterbi_back_kernel; scores leave in the caller's table-major layout.
 constexpr int VF_TABLES = 32, VF_BINS = 16, VF_ROW = VF_BINS * 3 + 1;  // padded row: lanes hit distinct banks
 constexpr int VF_WORKERS = 256, VF_THREADS = VF_WORKERS + 32;
-constexpr int VF_SMEM = 4 * VF_TABLES * VF_ROW * 8 + 2 * VF_TABLES * 8 + 2 * VF_BINS * VF_TABLES;
+constexpr int VF_SMEM = 4 * VF_TABLES * VF_ROW * 8 + 2 * VF_TABLES * 8 + 2 * VF_TABLES * 3 * 8 + VF_TABLES * 4 + 2 * VF_BINS * VF_TABLES;
 __global__ void __launch_bounds__(VF_THREADS, 3)
 viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ start, const int64_t *__restrict__ len,
                      const double *__restrict__ lik, int is_log, double lp01, double lp02, double lp12, double *__restrict__ score,
@@ -342,12 +342,15 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
     double (*nrm)[VF_TABLES][VF_ROW] = reinterpret_cast<double (*)[VF_TABLES][VF_ROW]>(vf_smem);
     double (*sco)[VF_TABLES][VF_ROW] = reinterpret_cast<double (*)[VF_TABLES][VF_ROW]>(vf_smem + 2 * VF_TABLES * VF_ROW);
     int64_t *s_start = reinterpret_cast<int64_t *>(vf_smem + 4 * VF_TABLES * VF_ROW), *s_len = s_start + VF_TABLES;
-    uint8_t (*frm)[VF_BINS][VF_TABLES] = reinterpret_cast<uint8_t (*)[VF_BINS][VF_TABLES]>(s_len + VF_TABLES);
+    double (*prevlast)[VF_TABLES][3] = reinterpret_cast<double (*)[VF_TABLES][3]>(s_len + VF_TABLES);  // last bin's scores of a chunk
+    int *tieflag = reinterpret_cast<int *>(&prevlast[2][0][0]);
+    uint8_t (*frm)[VF_BINS][VF_TABLES] = reinterpret_cast<uint8_t (*)[VF_BINS][VF_TABLES]>(tieflag + VF_TABLES);
     const int tb0 = blockIdx.x * VF_TABLES;
     if (threadIdx.x < VF_TABLES) {
         const int tb = tb0 + threadIdx.x;
         s_start[threadIdx.x] = tb < n_tables ? start[tb] : 0;
         s_len[threadIdx.x] = tb < n_tables ? len[tb] : 0;
+        tieflag[threadIdx.x] = 0;
     }
     __syncthreads();
     int64_t blk_bins = 0;
@@ -406,6 +409,32 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
                 if (pb == 0) asm volatile("bar.sync 3, %0;" ::"n"(VF_THREADS) : "memory");
                 else asm volatile("bar.sync 4, %0;" ::"n"(VF_THREADS) : "memory");
                 const int64_t i0 = (int64_t)(c - 1) * VF_BINS;
+                // Near-tie and long-double-range tests, moved off the solver's critical path: with the scores of bin
+                // i - 1 and ln nrm of bin i both still in shared memory, every bin's nine candidates can be rebuilt
+                // independently (the same expressions, hence the same doubles) — 512 bins over 256 workers.
+#pragma unroll
+                for (int k = 0; k < VF_TABLES * VF_BINS / VF_WORKERS; k++) {
+                    const int idx = k * VF_WORKERS + w;
+                    const int t = idx / VF_BINS, i = idx % VF_BINS;
+                    const int64_t gi = i0 + i;
+                    if (gi < s_len[t]) {
+                        const double *cur = &sco[pb][t][i * 3];
+                        bool tie = !is_log && below_ldbl(cur[0], cur[1], cur[2]);
+                        if (gi > 0) {
+                            const double *pv = i > 0 ? &sco[pb][t][(i - 1) * 3] : &prevlast[pb ^ 1][t][0];
+                            const double p0 = pv[0], p1 = pv[1], p2 = pv[2];
+                            const double n0 = nrm[pb][t][i * 3], n1 = nrm[pb][t][i * 3 + 1], n2 = nrm[pb][t][i * 3 + 2];
+                            const double ts = tie_scale(gi);
+                            const double a0 = p0 + n0, a1 = (p1 + n0) + lp01, a2 = (p2 + n0) + lp02;
+                            const double b0 = (p0 + n1) + lp01, b1 = p1 + n1, b2 = (p2 + n1) + lp12;
+                            const double c0 = (p0 + n2) + lp02, c1 = (p1 + n2) + lp12, c2 = p2 + n2;
+                            tie |= near_tie(a0, a1, a2, argmax3(a0, a1, a2), ts) | near_tie(b0, b1, b2, argmax3(b0, b1, b2), ts) |
+                                   near_tie(c0, c1, c2, argmax3(c0, c1, c2), ts);
+                        }
+                        if (tie) tieflag[t] = 1;
+                        if (i == VF_BINS - 1) { prevlast[pb][t][0] = cur[0]; prevlast[pb][t][1] = cur[1]; prevlast[pb][t][2] = cur[2]; }
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < VF_TABLES * VF_BINS * 3 / VF_WORKERS; k++) {
                     const int idx = k * VF_WORKERS + w;
@@ -428,7 +457,6 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
         const int lane = threadIdx.x;
         const int64_t n = s_len[lane];
         double s0 = 0, s1 = 0, s2 = 0;
-        bool tie = false;
         for (int c = 0; c < nchunk; c++) {
             const int b = c & 1;
             if (b == 0) asm volatile("bar.sync 1, %0;" ::"n"(VF_THREADS) : "memory");
@@ -440,20 +468,21 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
 #pragma unroll 4
             for (int q = 0; q < VF_BINS; q++) {
                 const double n0 = nr[q * 3], n1 = nr[q * 3 + 1], n2 = nr[q * 3 + 2];
-                const double ts = (double)(int)(i0 + q + 1) * 4.440892098500626e-16;
-                const Step3 A = step3(s0 + n0, (s1 + n0) + lp01, (s2 + n0) + lp02, ts);
-                const Step3 B = step3((s0 + n1) + lp01, s1 + n1, (s2 + n1) + lp12, ts);
-                const Step3 Cc = step3((s0 + n2) + lp02, (s1 + n2) + lp12, s2 + n2, ts);
+                // candidates (prev_k + ln nrm_s) + ln pen(k, s); strict '>' arg-max: lowest index wins, NaN never wins
+                const double a0 = s0 + n0, a1 = (s1 + n0) + lp01, a2 = (s2 + n0) + lp02;
+                const double b0 = (s0 + n1) + lp01, b1 = s1 + n1, b2 = (s2 + n1) + lp12;
+                const double c0 = (s0 + n2) + lp02, c1 = (s1 + n2) + lp12, c2 = s2 + n2;
+                const bool ga = a1 > a0, gb = b1 > b0, gc = c1 > c0;
+                const double ma = ga ? a1 : a0, mb = gb ? b1 : b0, mc = gc ? c1 : c0;
+                const bool ha = a2 > ma, hb = b2 > mb, hc = c2 > mc;
                 const bool live = q < nq;
-                s0 = live ? A.v : s0;
-                s1 = live ? B.v : s1;
-                s2 = live ? Cc.v : s2;
-                tie |= live & (i0 + q > 0) & (A.tie | B.tie | Cc.tie);
-                if (!is_log) tie |= live & below_ldbl(s0, s1, s2);
+                s0 = live ? (ha ? a2 : ma) : s0;
+                s1 = live ? (hb ? b2 : mb) : s1;
+                s2 = live ? (hc ? c2 : mc) : s2;
                 so[q * 3] = s0;
                 so[q * 3 + 1] = s1;
                 so[q * 3 + 2] = s2;
-                frm[b][q][lane] = (uint8_t)(A.k | (B.k << 2) | (Cc.k << 4));
+                frm[b][q][lane] = (uint8_t)((ha ? 2 : (int)ga) | ((hb ? 2 : (int)gb) << 2) | ((hc ? 2 : (int)gc) << 4));
             }
             __threadfence_block();
             if (b == 0) asm volatile("bar.arrive 3, %0;" ::"n"(VF_THREADS) : "memory");
@@ -464,7 +493,18 @@ viterbi_fused_kernel(int n_tables, int64_t maxbins, const int64_t *__restrict__ 
             last[(size_t)tb * 3 + 0] = s0;
             last[(size_t)tb * 3 + 1] = s1;
             last[(size_t)tb * 3 + 2] = s2;
-            if (n > 0) tie |= near_tie(s0, s1, s2, argmax3(s0, s1, s2), n);
+        }
+    }
+    __syncthreads();  // the workers' last drain has set the tie flags
+    if (threadIdx.x < VF_TABLES) {
+        const int tb = tb0 + threadIdx.x;
+        if (tb < n_tables) {
+            const int64_t n = s_len[threadIdx.x];
+            bool tie = tieflag[threadIdx.x] != 0;
+            if (n > 0) {
+                const double l0 = last[(size_t)tb * 3], l1 = last[(size_t)tb * 3 + 1], l2 = last[(size_t)tb * 3 + 2];
+                tie |= near_tie(l0, l1, l2, argmax3(l0, l1, l2), n);
+            }
             flag[tb] = tie ? 1 : 0;
         }
     }
