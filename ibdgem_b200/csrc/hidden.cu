@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
@@ -760,26 +761,43 @@ extern "C" int hiddengem_viterbi_batch(ibdgem_engine *e, int32_t n_tables, const
     if (rc) return 1;
     IBD_CUDA(cudaGetLastError());
     resolve_timers(e);
-    // flagged tables: the reference's long double recurrence decides
-    e->hg_flagged = 0;
-    std::vector<uint8_t> st_tmp;
-    std::vector<double> sc_tmp;
+    // flagged tables: the reference's long double recurrence decides (tables are independent: a few host threads)
+    std::vector<int> flagged;
     for (int t = 0; t < n_tables; t++) {
-        int64_t c[3] = {h_counts[(size_t)t * 3], h_counts[(size_t)t * 3 + 1], h_counts[(size_t)t * 3 + 2]};
-        if (h_flag[(size_t)t]) {
+        if (state_counts) {
+            state_counts[(size_t)t * 3] = h_counts[(size_t)t * 3];
+            state_counts[(size_t)t * 3 + 1] = h_counts[(size_t)t * 3 + 1];
+            state_counts[(size_t)t * 3 + 2] = h_counts[(size_t)t * 3 + 2];
+        }
+        if (h_flag[(size_t)t]) flagged.push_back(t);
+    }
+    e->hg_flagged = (int64_t)flagged.size();
+    auto redo = [&](size_t k0, size_t step) {
+        std::vector<uint8_t> st_tmp;
+        std::vector<double> sc_tmp;
+        for (size_t k = k0; k < flagged.size(); k += step) {
+            const int t = flagged[k];
             const int64_t b0 = bin_offsets[t], n = bin_offsets[t + 1] - b0;
+            int64_t c[3];
             st_tmp.resize((size_t)n);
             sc_tmp.resize((size_t)n * 3);
             viterbi_long_double(lik + b0 * 3, n, is_log, p01, p02, p12, st_tmp.data(), sc_tmp.data(), c);
             if (state) memcpy(state + b0, st_tmp.data(), (size_t)n);
             if (score_log) memcpy(score_log + b0 * 3, sc_tmp.data(), (size_t)n * 24);
-            e->hg_flagged++;
+            if (state_counts) {
+                state_counts[(size_t)t * 3] = c[0];
+                state_counts[(size_t)t * 3 + 1] = c[1];
+                state_counts[(size_t)t * 3 + 2] = c[2];
+            }
         }
-        if (state_counts) {
-            state_counts[(size_t)t * 3] = c[0];
-            state_counts[(size_t)t * 3 + 1] = c[1];
-            state_counts[(size_t)t * 3 + 2] = c[2];
-        }
+    };
+    const size_t nthr = std::max<size_t>(1, std::min<size_t>({flagged.size(), (size_t)16, (size_t)std::thread::hardware_concurrency()}));
+    if (nthr <= 1) {
+        redo(0, 1);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t k = 0; k < nthr; k++) pool.emplace_back(redo, k, nthr);
+        for (auto &th : pool) th.join();
     }
     return 0;
 }

@@ -185,6 +185,7 @@ def leg_c4(torch, ib, steps=3, n_tables=10_000, n_bins=10_000, ref_dir=None):
             e.viterbi_batch_raw(h_ll.data_ptr(), off, True, h_state.data_ptr(), h_score.data_ptr(), counts.ctypes.data)
 
         run()
+        flagged = e.viterbi_last_flagged()
         e.reset_stats()
         ms_e2e = _timed(torch, stream, run, steps)
         st = {k: v[0] / steps for k, v in e.kernel_stats().items() if v[1]}
@@ -213,6 +214,7 @@ def leg_c4(torch, ib, steps=3, n_tables=10_000, n_bins=10_000, ref_dir=None):
                        "(BASELINE.json configs[3])" % (n_tables, n_bins),
            "metric": "bins/s", "value": nb / ((ms_dev or ms_k) * 1e-3), "ms_per_step": ms_dev or ms_k, "ms_kernels": ms_k,
            "kernels_ms": st, "gpu_launches_per_step": launches, "planted_state_recovery": rec,
+           "near_tie_tables_reevaluated_in_long_double": int(flagged),
            "e2e": {"value": nb / (ms_e2e * 1e-3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(nb * 24 + off.nbytes),
                    "d2h_bytes_per_step": int(nb * 25 + counts.nbytes), "pcie_floor_ms_at_55GBs": nb * 25 / 55e9 * 1e3,
                    "note": "host pointers through hiddengem_viterbi_batch, pinned; H2D and D2H overlap at best, so the floor is "
