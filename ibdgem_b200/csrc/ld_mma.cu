@@ -463,6 +463,7 @@ struct Params {
     const double *C0;        // [nW]
     const double *lognb4;    // [T] ln(4 n_refpanel) or NaN
     double *wll;             // [T][outW][3]
+    double *wll_host;        // the same table in the caller's page-locked host memory (device alias), or nullptr
     int debug;               // IBDGEM_MMA_DEBUG experiments (0 = product behaviour)
     int warm_tiles;          // leading tiles of a unit whose maximum is taken before they are screened
     int *unit_counter;       // next unit to hand out (zeroed before the launch)
@@ -703,7 +704,20 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             if (mm == -INFINITY) r = -INFINITY;
             r = (c0w + r) - lnb;
             if (!(lnb == lnb)) r = __longlong_as_double(0x7ff8000000000000LL);  // n_refpanel = 0: 0/0 in the reference
-            if (ok) p.wll[((size_t)(row >> 1) * p.outW + w) * 3 + 1] = r;
+            if (ok) {
+                double *o = p.wll + ((size_t)(row >> 1) * p.outW + w) * 3;
+                o[1] = r;
+                if (p.wll_host) {
+                    // LIBD0 (ld_ibd0) and LIBD2 (ld_expand_tgt) of this cell were written before the launch: the finished
+                    // triple goes straight to the caller's page-locked buffer over PCIe, so no result copy is left
+                    // when the GEMM ends (24 MB at C3: 0.44 ms of tail)
+                    double *h = p.wll_host + ((size_t)(row >> 1) * p.outW + w) * 3;
+                    const double l0 = o[0], l2 = o[2];
+                    h[0] = l0;
+                    h[1] = r;
+                    h[2] = l2;
+                }
+            }
         }
     }
     } else {
@@ -1224,18 +1238,30 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     const bool stream_dev = e->d_wll_out_device != nullptr;
     // page-locked host destination: its device alias, for stores from a kernel
     double *h_wll_mapped = nullptr;
-    if (stream_out) {
+    if (e->h_wll_out) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, e->h_wll_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
             h_wll_mapped = static_cast<double *>(attr.devicePointer);
         else
             cudaGetLastError();
     }
-    if (stream_out || stream_dev) {
+    // direct mode: the GEMM's merge warps store finished score triples into the page-locked host table themselves
+    static const int direct_env = [] { const char *sd = getenv("IBDGEM_LD_DIRECT_STORE"); return sd ? atoi(sd) : 1; }();
+    const bool direct = direct_env && h_wll_mapped != nullptr;
+    if (stream_out || stream_dev || direct) {
         if (!e->d2h_stream) IBD_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
-        e->wll_streamed = stream_out;
+        e->wll_streamed = stream_out || direct;
         e->wll_dev_streamed = stream_dev;
     }
+    auto launch_ibd0 = [&](int wa, int wb_) -> int {
+        LaunchScope ls(e, K_LD_IBD0);
+        // the window's Q' row is staged in shared memory when it fits (one bulk, coalesced load instead
+        // of latency-bound passes over global memory)
+        const size_t q_smem = (size_t)nU * 8 <= 160 * 1024 ? (size_t)nU * 8 : 0;
+        IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        ld_ibd0_kernel<<<wb_ - wa, 256, q_smem, e->stream>>>(wa, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
+        return 0;
+    };
     int w_lo = shard_wb;
     for (size_t rk = 0; rk < range_end.size(); rk++) {
     const int w_hi = range_end[rk];
@@ -1286,6 +1312,8 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.akey = d_akey; p.Rp = d_Rp; p.Rt = d_Rt;
         p.row_own = d_rowown;
         p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
+        p.wll_host = direct ? h_wll_mapped : nullptr;
+        if (direct && launch_ibd0(w0, w0 + nw)) return 1;  // LIBD0 must be in the table before the GEMM's merge warps read it
         {
             static const int dbg = [] { const char *sdbg = getenv("IBDGEM_MMA_DEBUG"); return sdbg ? atoi(sdbg) : 0; }();
             p.debug = dbg;
@@ -1326,14 +1354,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             cudaFree(d_trace);
         }
     }
-    {
-        LaunchScope ls(e, K_LD_IBD0);
-        // the window's Q' row is staged in shared memory when it fits (one bulk, coalesced load instead
-        // of latency-bound passes over global memory)
-        const size_t q_smem = (size_t)nU * 8 <= 160 * 1024 ? (size_t)nU * 8 : 0;
-        IBD_CUDA(cudaFuncSetAttribute(ld_ibd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        ld_ibd0_kernel<<<w_hi - w_lo, 256, q_smem, e->stream>>>(w_lo, T, nU, outW, d_Qp, d_ownU, d_lognb, d_wll, q_smem ? 1 : 0);
-    }
+    if (!direct && launch_ibd0(w_lo, w_hi)) return 1;
     if (stream_out || stream_dev) {
         // the range's columns of d_wll [T][outW][3] are final: strided copies on their own stream
         while (e->range_ev.size() <= rk) {
@@ -1346,7 +1367,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         if (stream_dev)
             IBD_CUDA(cudaMemcpy2DAsync(e->d_wll_out_device + (size_t)w_lo * 3, (size_t)outW * 24, d_wll + (size_t)w_lo * 3,
                                        (size_t)outW * 24, (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDefault, e->d2h_stream));
-        if (stream_out) {
+        if (stream_out && !direct) {
             if (h_wll_mapped && T >= 256) {  // many short rows: store them from a kernel (see ld_store_cols_kernel)
                 const int64_t n = (int64_t)T * (w_hi - w_lo) * 3;
                 ld_store_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->d2h_stream>>>(d_wll, h_wll_mapped, T, outW, w_lo, w_hi - w_lo);
@@ -1359,7 +1380,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     }
     w_lo = w_hi;
     }  // window ranges
-    if (stream_out && outW > nW && !sharded) {  // the unused columns nW .. outW-1 (NaN since the fill at the start of the call)
+    if ((stream_out || direct) && outW > nW && !sharded) {  // the unused columns nW .. outW-1 (NaN since the fill at the start of the call)
         const size_t rk = range_end.size();
         while (e->range_ev.size() <= rk) {
             cudaEvent_t ev;

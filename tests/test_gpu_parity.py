@@ -689,3 +689,33 @@ def test_panel_cloned_from_another_engine():
     with ib.Engine(ib.Params(window_size=100)) as a, ib.Engine(ib.Params(window_size=100)) as b:
         with pytest.raises(RuntimeError, match="no panel"):
             b.clone_panel(a)
+
+
+def test_ld_results_stored_straight_into_page_locked_host_memory():
+    """With a page-locked w_loglik buffer the GEMM's merge warps store finished (LIBD0, LIBD1, LIBD2) triples into the
+    caller's table themselves (no result copy after the kernel); the table must equal the one a pageable buffer
+    receives by cudaMemcpy, NaN padding columns included."""
+    import torch
+    import ibdgem_b200 as ib
+    from ibdgem_b200.engine import _CScores
+    ec = _engine()
+    case = _synth_case(95, 40_000, 120, 100, True, range(300), pu_idx=7)
+    pk = case.pk
+    T = len(case.targets)
+    targets = np.asarray(case.targets, np.int32)
+    with ib.Engine(ib.Params(window_size=100)) as e:
+        e.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, None)
+        e.upload_panel(ib.pack_bits(pk.hap), len(pk.names))
+        want = e.score_ld(targets, case.bg, 7)  # pageable numpy outputs
+        assert e.last_ld_path() == 1
+        maxW = want.w_loglik.shape[1]
+        o_nw = torch.zeros(T, dtype=torch.int32).pin_memory()
+        o_ll = torch.full((T, maxW, 3), -7.0, dtype=torch.float64).pin_memory()
+        cs = _CScores(maxW, o_nw.data_ptr(), None, None, None, o_ll.data_ptr(), None, None, None, None, None, None, None, None)
+        for _ in range(2):
+            e.invalidate()
+            e.score_ld_raw(targets, np.asarray(case.bg, np.int32), 7, cs)
+    np.testing.assert_array_equal(o_nw.numpy(), want.n_windows)
+    got = o_ll.numpy()
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want.w_loglik))
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want.w_loglik), rtol=0, atol=1e-9)
