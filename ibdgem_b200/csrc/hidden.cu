@@ -708,8 +708,11 @@ extern "C" int hiddengem_viterbi_batch(ibdgem_engine *e, int32_t n_tables, const
     IBD_CUDA(cudaEventRecord(e->ev_order, e->stream));
     IBD_CUDA(cudaStreamWaitEvent(e->copy_stream, e->ev_order, 0));
     IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->ev_order, 0));
-    // batches of whole tables, ~192 MB of likelihoods each (3.5 ms of PCIe), at least 64 tables so the batched kernels apply
-    const int64_t target_bins = (int64_t)8 << 20;
+    // Batches of whole tables, at least 64 so the batched kernels apply.  A batch's kernels take the time of one block
+    // (the recursion is sequential in bins) however few tables it holds, so batches are few: about six per call —
+    // copy-bound with ~1/6 of the upload exposed at the front and ~1/6 of the download at the back — and never below
+    // ~192 MB of likelihoods.
+    const int64_t target_bins = std::max<int64_t>((int64_t)8 << 20, nb / 6);
     std::vector<int> cuts{0};
     for (int t = 0; t < n_tables;) {
         int t1 = t;

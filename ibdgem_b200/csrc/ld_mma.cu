@@ -1247,7 +1247,9 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     }
     // direct mode: the GEMM's merge warps store finished score triples into the page-locked host table themselves
     static const int direct_env = [] { const char *sd = getenv("IBDGEM_LD_DIRECT_STORE"); return sd ? atoi(sd) : 1; }();
-    const bool direct = direct_env && h_wll_mapped != nullptr;
+    // (not while panel chunks are still arriving: measured at C3 end to end, the 24-byte posted writes of every range
+    // compete with the upload on the link — 13.3 ms against 12.6 with the per-range store kernel)
+    const bool direct = direct_env && h_wll_mapped != nullptr && !by_chunk;
     if (stream_out || stream_dev || direct) {
         if (!e->d2h_stream) IBD_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
         e->wll_streamed = stream_out || direct;

@@ -699,7 +699,7 @@ def test_ld_results_stored_straight_into_page_locked_host_memory():
     import ibdgem_b200 as ib
     from ibdgem_b200.engine import _CScores
     ec = _engine()
-    case = _synth_case(95, 40_000, 120, 100, True, range(300), pu_idx=7)
+    case = _synth_case(95, 20_000, 320, 100, True, range(300), pu_idx=7)
     pk = case.pk
     T = len(case.targets)
     targets = np.asarray(case.targets, np.int32)
