@@ -216,9 +216,12 @@ def leg_c4(torch, ib, steps=3, n_tables=10_000, n_bins=10_000, ref_dir=None):
            "kernels_ms": st, "gpu_launches_per_step": launches, "planted_state_recovery": rec,
            "near_tie_tables_reevaluated_in_long_double": int(flagged),
            "e2e": {"value": nb / (ms_e2e * 1e-3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(nb * 24 + off.nbytes),
-                   "d2h_bytes_per_step": int(nb * 25 + counts.nbytes), "pcie_floor_ms_at_55GBs": nb * 25 / 55e9 * 1e3,
-                   "note": "host pointers through hiddengem_viterbi_batch, pinned; H2D and D2H overlap at best, so the floor is "
-                           "the larger direction"},
+                   "d2h_bytes_per_step": int(nb * 25 + counts.nbytes),
+                   "pcie_floor_ms_at_55GBs_full_duplex": nb * 25 / 55e9 * 1e3, "pcie_floor_ms_at_55GBs_combined": nb * 49 / 55e9 * 1e3,
+                   "note": "host pointers through hiddengem_viterbi_batch, page-locked; batches are pipelined over three streams "
+                           "(upload, kernels, download).  On these boxes upload and download do not add up: ~55 GB/s is what "
+                           "both directions get TOGETHER (92-97 ms measured for 4.9 GB whatever the batching), so the combined "
+                           "figure is the floor that applies"},
            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": hbm, "peak_source": src, "bytes": "49 B per bin (SURVEY.md 8d)",
                         "achieved": byt / 1e9 / (ms_k * 1e-3), "frac": byt / 1e9 / (ms_k * 1e-3) / hbm, "over": "sum of the pass's kernels"}}
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "hiddengem")
