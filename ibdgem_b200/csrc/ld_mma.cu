@@ -1249,7 +1249,9 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     static const int direct_env = [] { const char *sd = getenv("IBDGEM_LD_DIRECT_STORE"); return sd ? atoi(sd) : 1; }();
     // (not while panel chunks are still arriving: measured at C3 end to end, the 24-byte posted writes of every range
     // compete with the upload on the link — 13.3 ms against 12.6 with the per-range store kernel)
-    const bool direct = direct_env && h_wll_mapped != nullptr && !by_chunk;
+    // (nor for window shards: eight ranks scattering 24-byte writes over a 10,000-row host table — one 4 KB page per
+    // write — slowed the GEMM by 15 % at C5 over 8 GPUs; there the shard's columns leave by one store kernel at the end)
+    const bool direct = direct_env && h_wll_mapped != nullptr && !by_chunk && !sharded;
     if (stream_out || stream_dev || direct) {
         if (!e->d2h_stream) IBD_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
         e->wll_streamed = stream_out || direct;
