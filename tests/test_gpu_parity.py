@@ -719,3 +719,27 @@ def test_ld_results_stored_straight_into_page_locked_host_memory():
     got = o_ll.numpy()
     np.testing.assert_array_equal(np.isnan(got), np.isnan(want.w_loglik))
     np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want.w_loglik), rtol=0, atol=1e-9)
+
+
+def test_ld_variable_sites_degenerate_targets():
+    """-v edge cases on the tensor path: a target with no variable site at all (zero windows), one with fewer than a
+    window's worth (a single partial window), a single-target call, and a call in which NO target has a variable site."""
+    ec = _engine()
+    case = _synth_case(181, 3000, 40, 50, True, [3, 5, 9, 11], pu_idx=1, opt_v=1)
+    case.pk.hap[:, 6:8] = 0            # individual 3: hom-ref everywhere
+    case.pk.hap[:, 10:12] = 0          # individual 5: variable at 7 sites only
+    case.pk.hap[100:2000:300, 10] = 1
+    results = ec.run_engine(case, expanded=False)
+    assert results[0]["ld_path"] == 2
+    assert results[0]["n_windows"] == 0 and results[1]["n_windows"] == 1
+    for res, ora in zip(results, refcases.oracle_run(case)):
+        ec.assert_matches_oracle(res, ora)
+    one = _synth_case(182, 3000, 40, 50, True, [7], pu_idx=-1, opt_v=1)
+    for res, ora in zip(ec.run_engine(one, expanded=False), refcases.oracle_run(one)):
+        ec.assert_matches_oracle(res, ora)
+    none = _synth_case(183, 800, 12, 20, True, [2, 4], pu_idx=-1, opt_v=1)
+    none.pk.hap[:, 4:6] = 0
+    none.pk.hap[:, 8:10] = 0
+    for res, ora in zip(ec.run_engine(none, expanded=False), refcases.oracle_run(none)):
+        assert res["n_windows"] == 0
+        ec.assert_matches_oracle(res, ora)
