@@ -1368,9 +1368,16 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         }
         IBD_CUDA(cudaEventRecord(e->range_ev[rk], e->stream));
         IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->range_ev[rk], 0));
-        if (stream_dev)
-            IBD_CUDA(cudaMemcpy2DAsync(e->d_wll_out_device + (size_t)w_lo * 3, (size_t)outW * 24, d_wll + (size_t)w_lo * 3,
-                                       (size_t)outW * 24, (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDefault, e->d2h_stream));
+        if (stream_dev) {
+            if (T >= 256) {  // many short rows: coalesced stores from a kernel (to local or peer memory alike), not T DMA descriptors
+                const int64_t n = (int64_t)T * (w_hi - w_lo) * 3;
+                ld_store_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->d2h_stream>>>(d_wll, e->d_wll_out_device, T, outW, w_lo, w_hi - w_lo);
+                e->k_launches[K_LD_WINDOWS]++;
+            } else {
+                IBD_CUDA(cudaMemcpy2DAsync(e->d_wll_out_device + (size_t)w_lo * 3, (size_t)outW * 24, d_wll + (size_t)w_lo * 3,
+                                           (size_t)outW * 24, (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDefault, e->d2h_stream));
+            }
+        }
         if (stream_out && !direct) {
             if (h_wll_mapped && T >= 256) {  // many short rows: store them from a kernel (see ld_store_cols_kernel)
                 const int64_t n = (int64_t)T * (w_hi - w_lo) * 3;
