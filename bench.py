@@ -6,8 +6,12 @@ site x target x background-individual x 1-of-4 haplotype pairing (the multiply a
 src/ibdgem.c:716-719 of the reference).  Workload at N=1: BASELINE.json configs[2] — `--LD`
 scoring of a synthetic chr20-scale panel, 1,000,000 sites x 2,504 phased samples, 1,000 targets,
 window 1,000 sites (SURVEY.md §8d "C3", depth >= 1 variant).  At N>1 every rank scores its own
-1,000 targets against the replicated panel (weak scaling) and the per-window scores are
-all-gathered over NCCL.
+1,000 targets against the replicated panel (weak scaling) and stores its window scores into the
+gathered table in rank 0's HBM over NVLink (CUDA IPC peer stores; fallback: one NCCL all_gather).
+
+The other configurations of BASELINE.json ride on the same JSON line under "aux" (tools/bench_aux.py):
+c2 (non-LD), c4 (hiddengem), c5 (10k targets x 5k background; windows partitioned across the ranks at every N),
+strong_c3 (N>1: C3 in full, windows partitioned), ld_v (C3 with -v), flat_rows, cli_e2e, int8_peak.
 
     python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
     python bench.py --impl reference ...                     (the reference's CPU binary)
