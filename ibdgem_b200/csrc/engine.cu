@@ -1759,6 +1759,12 @@ int ibdgem_engine_set_window_shard(ibdgem_engine *e, int32_t index, int32_t coun
     return 0;
 }
 
+int ibdgem_engine_set_shard_compact_output(ibdgem_engine *e, int32_t on) {
+    if (!e) return 1;
+    e->shard_compact = on != 0;
+    return 0;
+}
+
 int ibdgem_engine_window_shard(ibdgem_engine *e, int32_t *w_begin, int32_t *w_end, int64_t *site_begin, int64_t *site_end) {
     if (!e) return 1;
     if (ibdgem_engine_prepare(e)) return 1;

@@ -122,6 +122,7 @@ struct ibdgem_engine {
     // Window shard (multi-GPU, shared windows): this engine scores windows [nW*index/count, nW*(index+1)/count)
     // of every target and touches only the panel rows of those windows (ibdgem_engine_set_window_shard)
     int32_t shard_index = 0, shard_count = 1;
+    bool shard_compact = false;              // window shards: the host score table is [T][shard windows][3], not [T][maxW][3]
     double *d_wll_out_device = nullptr;      // the call's optional device destination (may be peer memory)
     bool wll_dev_streamed = false;           // ld_tensor_score has already issued the copies to it
     bool lazy_table = false;                 // status does not need the panel (no -A, AF range [0, 1])
@@ -191,7 +192,7 @@ enum ScratchSlot {
     SC_WN, SC_WS, SC_WE, SC_COUNTERS, SC_SITE_STATUS, SC_SITE_LIK, SC_LD_PART, SC_NREFPANEL,
     SC_HG_LIK, SC_HG_OFF, SC_HG_STATE, SC_HG_SCORE, SC_HG_COUNTS, SC_HG_NRMT, SC_HG_SCORET, SC_HG_FROMT, SC_HG_LAST,
     SC_MMA_TGT, SC_MMA_BG, SC_MMA_ROWLSE, SC_MMA_BGIDX, SC_MMA_MISC, SC_MMA_UNIT,
-    SC_WLIN, SC_V_KS, SC_V_KE, SC_V_TWBASE, SC_V_TWI, SC_V_TWD, SC_V_ORDER, SC_V_HIST, SC_V_TILES, SC_V_MISC, SC_SLOTS
+    SC_WLIN, SC_WLL_PACK, SC_V_KS, SC_V_KE, SC_V_TWBASE, SC_V_TWI, SC_V_TWD, SC_V_ORDER, SC_V_HIST, SC_V_TILES, SC_V_MISC, SC_SLOTS
 };
 int scratch(ibdgem_engine *e, int slot, size_t bytes, void **out);
 

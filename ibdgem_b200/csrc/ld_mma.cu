@@ -308,6 +308,16 @@ ld_store_cols_kernel(const double *__restrict__ src, double *__restrict__ dst, i
     dst[o] = src[o];
 }
 
+// the same columns packed into a compact table [T][ncols][3] (window shards with a compact host table)
+__global__ void __launch_bounds__(256)
+ld_pack_cols_kernel(const double *__restrict__ src, double *__restrict__ dst, int T, int outW, int w_lo, int ncols) {
+    const int64_t per = (int64_t)ncols * 3;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T * per) return;
+    const int64_t t = i / per, c = i % per;
+    dst[i] = src[(t * outW + w_lo) * 3 + c];
+}
+
 // window bookkeeping (W2) for every (target, window)
 __global__ void __launch_bounds__(256)
 ld_windows_kernel(int w_lo, int w_hi, int T, int nW, int outW, int W, int64_t K, const int64_t *__restrict__ wfirst,
@@ -1378,7 +1388,15 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
                                            (size_t)outW * 24, (size_t)(w_hi - w_lo) * 24, (size_t)T, cudaMemcpyDefault, e->d2h_stream));
             }
         }
-        if (stream_out && !direct) {
+        if (stream_out && sharded && e->shard_compact) {
+            // compact host table of a window shard: pack on the device, one contiguous copy
+            double *d_pack;
+            const int64_t n = (int64_t)T * (w_hi - w_lo) * 3;
+            if (scratch(e, SC_WLL_PACK, (size_t)n * 8, (void **)&d_pack)) return 1;
+            ld_pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->d2h_stream>>>(d_wll, d_pack, T, outW, w_lo, w_hi - w_lo);
+            e->k_launches[K_LD_WINDOWS]++;
+            IBD_CUDA(cudaMemcpyAsync(e->h_wll_out, d_pack, (size_t)n * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
+        } else if (stream_out && !direct) {
             if (h_wll_mapped && T >= 256) {  // many short rows: store them from a kernel (see ld_store_cols_kernel)
                 const int64_t n = (int64_t)T * (w_hi - w_lo) * 3;
                 ld_store_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->d2h_stream>>>(d_wll, h_wll_mapped, T, outW, w_lo, w_hi - w_lo);

@@ -136,6 +136,10 @@ class Engine:
         """Multi-GPU partition by windows (shared window maps): see include/ibdgem_b200.h."""
         self._check(self._lib.ibdgem_engine_set_window_shard(self._h, C.c_int32(index), C.c_int32(count)))
 
+    def set_shard_compact_output(self, on: bool = True):
+        """Window shards: the host score table is written as [T][shard windows][3] (one contiguous copy)."""
+        self._check(self._lib.ibdgem_engine_set_shard_compact_output(self._h, C.c_int32(1 if on else 0)))
+
     def window_shard(self):
         """(w_begin, w_end, site_begin, site_end) of this engine's shard; prepares the window map."""
         wb, we, sb, se = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int64()

@@ -483,6 +483,13 @@ def test_window_shards_reassemble_the_unsharded_table():
                 assert int(sc.n_windows[k]) == w["n_windows"]
                 np.testing.assert_array_equal(sc.w_nsites[k, :w["n_windows"]], w["w_nsites"])
                 np.testing.assert_array_equal(sc.w_start[k, :w["n_windows"]], w["w_start"])
+        # compact host table of a shard: [T][we - wb][3], the same numbers
+        e.set_shard_compact_output(True)
+        wb, we, _, _ = e.window_shard()
+        scc = e.score_ld(case.targets, case.bg, 3, max_windows=maxW)
+        compact = scc.w_loglik.reshape(-1)[: T * (we - wb) * 3].reshape(T, we - wb, 3)
+        np.testing.assert_array_equal(compact, merged[:, wb:we])
+        e.set_shard_compact_output(False)
         # non-tensor paths refuse a window shard instead of silently scoring everything
         with pytest.raises(RuntimeError, match="window shard"):
             e.score_nonld(case.targets)

@@ -303,7 +303,8 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
     maxW = S // W + 2
     stream = torch.cuda.current_stream()
     o_nw = _pinned(torch, (T,), torch.int32)
-    o_ll = _pinned(torch, (T, maxW, 3), torch.float64)
+    # the host score table of a window shard is compact: [T][this rank's windows][3] (ibdgem_engine_set_shard_compact_output)
+    o_ll = _pinned(torch, (T, (S // W + world) // world + 1, 3), torch.float64)
     book = rank == 0  # the bookkeeping arrays are the same on every rank: only the root fetches them
     o_ws = _pinned(torch, (T, maxW), torch.int64) if book else None
     o_we = _pinned(torch, (T, maxW), torch.int64) if book else None
@@ -338,6 +339,7 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
     with ib.Engine(ib.Params(window_size=W, device=dev_i)) as e:
         e.set_stream(stream.cuda_stream)
         e.set_window_shard(rank, world)
+        e.set_shard_compact_output(True)
         e.upload_sites(pos, n_ref, n_alt, keep)
         e.upload_panel(bits, N)
         e.sync_uploads()
@@ -368,13 +370,14 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
         n2 = max(2, min(steps, 3))
         ms_e2e = timed(e2e, n2)
     nW = int(o_nw[0])
-    ok_cols = bool(np.isfinite(o_ll.numpy()[:, wb:we]).all())
+    mine = o_ll.numpy().reshape(-1)[: T * (we - wb) * 3].reshape(T, we - wb, 3)  # compact: [T][we - wb][3]
+    ok_cols = bool(np.isfinite(mine).all())
     gathered_ok = None
     if table.ok:
         barrier()
         if table.is_root:
             g = table.tensor()[:, :nW].cpu().numpy()
-            gathered_ok = bool(np.isfinite(g).all()) and bool(np.array_equal(g[:, wb:we], o_ll.numpy()[:, wb:we]))
+            gathered_ok = bool(np.isfinite(g).all()) and bool(np.array_equal(g[:, wb:we], mine))
         barrier()
     table.close()
     inf = int(((n_ref.astype(np.int64) + n_alt) >= 1).sum())
@@ -391,7 +394,8 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
             "gather_bytes_per_rank": int(T) * (we - wb) * 24,
             "e2e": {"ms_per_step": ms_e2e, "comparisons_per_s": comps / (ms_e2e * 1e-3),
                     "h2d_bytes_per_step_rank0": int(h2d[0] + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes),
-                    "d2h_bytes_per_step_rank0": int(T * (we - wb) * 24 + T * maxW * 20 + T * 4)}}
+                    "d2h_bytes_per_step_rank0": int(T * (we - wb) * 24 + T * maxW * 20 + T * 4)},
+            "host_table": "compact [T][this rank's windows][3] per rank (one contiguous copy)"}
 
 
 def c5_inputs(torch, S, N, seed=5, src=None):
