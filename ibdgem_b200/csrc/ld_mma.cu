@@ -308,14 +308,14 @@ ld_store_cols_kernel(const double *__restrict__ src, double *__restrict__ dst, i
     dst[o] = src[o];
 }
 
-// the same columns packed into a compact table [T][ncols][3] (window shards with a compact host table)
+// the same columns packed WINDOW-major into a compact table [ncols][T][3] (window shards with a compact host table:
+// any sub-range of the shard's windows is then one contiguous block)
 __global__ void __launch_bounds__(256)
 ld_pack_cols_kernel(const double *__restrict__ src, double *__restrict__ dst, int T, int outW, int w_lo, int ncols) {
-    const int64_t per = (int64_t)ncols * 3;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= (int64_t)T * per) return;
-    const int64_t t = i / per, c = i % per;
-    dst[i] = src[(t * outW + w_lo) * 3 + c];
+    if (i >= (int64_t)T * ncols * 3) return;
+    const int64_t c = i % 3, t = (i / 3) % T, w = i / ((int64_t)3 * T);
+    dst[i] = src[(t * outW + w_lo + w) * 3 + c];
 }
 
 // window bookkeeping (W2) for every (target, window)
@@ -1165,7 +1165,18 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     const bool sharded = e->shard_count > 1;
     if (sharded) {
         window_shard_bounds(e, &shard_wb, &shard_we, nullptr, &shard_se);
-        range_end.assign(1, shard_we);
+        range_end.clear();
+        // three sub-ranges when results go to the host and the shard is large: the copy of a sub-range's columns runs
+        // under the next sub-range's GEMM, so a third of it is left at the end
+        const int span = shard_we - shard_wb;
+        static const int parts_env = [] { const char *sp = getenv("IBDGEM_SHARD_PARTS"); return sp ? atoi(sp) : 3; }();
+        // ... as long as every sub-range still keeps the persistent GEMM busy for >= 8 rounds of units (IBDGEM_SHARD_PARTS < 0
+        // forces |value| parts, for tests)
+        const int64_t units = (int64_t)span * ((2 * T + 255) / 256);
+        int parts = 1;
+        if (parts_env < 0) parts = std::min(span, -parts_env);
+        else if (e->h_wll_out && parts_env > 1) parts = (int)std::max<int64_t>(1, std::min<int64_t>(parts_env, units / (8 * std::max(1, e->sm_count / 2))));
+        for (int k = 1; k <= parts; k++) range_end.push_back(shard_wb + (int)((int64_t)span * k / parts));
         by_chunk = false;
     }
     auto range_sites = [&](size_t k) { return by_chunk ? e->chunk_end[k] : shard_se; };
@@ -1391,11 +1402,11 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         if (stream_out && sharded && e->shard_compact) {
             // compact host table of a window shard: pack on the device, one contiguous copy
             double *d_pack;
-            const int64_t n = (int64_t)T * (w_hi - w_lo) * 3;
-            if (scratch(e, SC_WLL_PACK, (size_t)n * 8, (void **)&d_pack)) return 1;
-            ld_pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->d2h_stream>>>(d_wll, d_pack, T, outW, w_lo, w_hi - w_lo);
+            const int64_t n = (int64_t)T * (w_hi - w_lo) * 3, off = (int64_t)T * (w_lo - shard_wb) * 3;
+            if (scratch(e, SC_WLL_PACK, (size_t)T * (shard_we - shard_wb) * 24, (void **)&d_pack)) return 1;
+            ld_pack_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->d2h_stream>>>(d_wll, d_pack + off, T, outW, w_lo, w_hi - w_lo);
             e->k_launches[K_LD_WINDOWS]++;
-            IBD_CUDA(cudaMemcpyAsync(e->h_wll_out, d_pack, (size_t)n * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
+            IBD_CUDA(cudaMemcpyAsync(e->h_wll_out + off, d_pack + off, (size_t)n * 8, cudaMemcpyDeviceToHost, e->d2h_stream));
         } else if (stream_out && !direct) {
             if (h_wll_mapped && T >= 256) {  // many short rows: store them from a kernel (see ld_store_cols_kernel)
                 const int64_t n = (int64_t)T * (w_hi - w_lo) * 3;

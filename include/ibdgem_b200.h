@@ -166,10 +166,10 @@ int ibdgem_engine_get_site_table(ibdgem_engine *e, double *f, uint8_t *status, d
 int ibdgem_engine_set_window_shard(ibdgem_engine *e, int32_t index, int32_t count);
 int ibdgem_engine_window_shard(ibdgem_engine *e, int32_t *w_begin, int32_t *w_end, int64_t *site_begin,
                                int64_t *site_end); /* prepares the window map if necessary */
-/* With a window shard set, have score_ld write the HOST table ibdgem_scores.w_loglik compactly, as
- * [T][w_end - w_begin][3] (only the shard's columns exist): one contiguous device-to-host copy instead of T short
- * strided rows (10,000 rows of 3 KB at C5 over 8 GPUs cost more than the rank's share of the upload).  The device
- * table w_loglik_device keeps the full [T][max_windows][3] layout. */
+/* With a window shard set, have score_ld write the HOST table ibdgem_scores.w_loglik compactly and WINDOW-major, as
+ * [w_end - w_begin][T][3] (only the shard's windows exist): contiguous device-to-host copies, issued sub-range by
+ * sub-range under the scoring of the next one, instead of T short strided rows (10,000 rows of 3 KB at C5 over
+ * 8 GPUs).  The device table w_loglik_device keeps the full [T][max_windows][3] layout. */
 int ibdgem_engine_set_shard_compact_output(ibdgem_engine *e, int32_t on);
 
 /* Gather of per-window scores over NVLink without a rendezvous inside the scoring loop: the root

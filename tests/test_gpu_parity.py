@@ -483,11 +483,11 @@ def test_window_shards_reassemble_the_unsharded_table():
                 assert int(sc.n_windows[k]) == w["n_windows"]
                 np.testing.assert_array_equal(sc.w_nsites[k, :w["n_windows"]], w["w_nsites"])
                 np.testing.assert_array_equal(sc.w_start[k, :w["n_windows"]], w["w_start"])
-        # compact host table of a shard: [T][we - wb][3], the same numbers
+        # compact, window-major host table of a shard: [we - wb][T][3], the same numbers
         e.set_shard_compact_output(True)
         wb, we, _, _ = e.window_shard()
         scc = e.score_ld(case.targets, case.bg, 3, max_windows=maxW)
-        compact = scc.w_loglik.reshape(-1)[: T * (we - wb) * 3].reshape(T, we - wb, 3)
+        compact = scc.w_loglik.reshape(-1)[: T * (we - wb) * 3].reshape(we - wb, T, 3).transpose(1, 0, 2)
         np.testing.assert_array_equal(compact, merged[:, wb:we])
         e.set_shard_compact_output(False)
         # non-tensor paths refuse a window shard instead of silently scoring everything
@@ -750,3 +750,32 @@ def test_ld_variable_sites_degenerate_targets():
     for res, ora in zip(ec.run_engine(none, expanded=False), refcases.oracle_run(none)):
         assert res["n_windows"] == 0
         ec.assert_matches_oracle(res, ora)
+
+
+def test_window_shard_in_sub_ranges_with_compact_output():
+    """A window shard scored in three sub-ranges (as large shards are: the copy of one sub-range's columns runs under the
+    next one's GEMM), compact window-major host table: same numbers as the unsharded run."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')\n"
+        "import numpy as np, ibdgem_b200 as ib, enginecase as ec\n"
+        "from test_gpu_parity import _synth_case\n"
+        "case = _synth_case(83, 9000, 40, 100, True, range(7), pu_idx=3)\n"
+        "want = ec.run_engine(case, expanded=False)\n"
+        "pk = case.pk; T = 7; maxW = 9000 // 100 + 2\n"
+        "with ib.Engine(ib.Params(window_size=100)) as e:\n"
+        "    e.set_window_shard(1, 2); e.set_shard_compact_output(True)\n"
+        "    e.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, None)\n"
+        "    e.upload_panel(ib.pack_bits(pk.hap), len(pk.names))\n"
+        "    wb, we, _, _ = e.window_shard()\n"
+        "    sc = e.score_ld(case.targets, case.bg, 3, max_windows=maxW)\n"
+        "    assert e.kernel_stats()['ld_mma'][1] == 3, e.kernel_stats()['ld_mma']\n"
+        "got = sc.w_loglik.reshape(-1)[: T * (we - wb) * 3].reshape(we - wb, T, 3).transpose(1, 0, 2)\n"
+        "for k, w in enumerate(want):\n"
+        "    np.testing.assert_allclose(got[k, : w['n_windows'] - wb], w['w_log'][wb:we], rtol=0, atol=1e-9)\n"
+        "print('ok')\n")
+    env = dict(os.environ, IBDGEM_SHARD_PARTS="-3")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -303,8 +303,9 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
     maxW = S // W + 2
     stream = torch.cuda.current_stream()
     o_nw = _pinned(torch, (T,), torch.int32)
-    # the host score table of a window shard is compact: [T][this rank's windows][3] (ibdgem_engine_set_shard_compact_output)
-    o_ll = _pinned(torch, (T, (S // W + world) // world + 1, 3), torch.float64)
+    # the host score table of a window shard is compact and window-major: [this rank's windows][T][3]
+    # (ibdgem_engine_set_shard_compact_output)
+    o_ll = _pinned(torch, ((S // W + world) // world + 1, T, 3), torch.float64)
     book = rank == 0  # the bookkeeping arrays are the same on every rank: only the root fetches them
     o_ws = _pinned(torch, (T, maxW), torch.int64) if book else None
     o_we = _pinned(torch, (T, maxW), torch.int64) if book else None
@@ -370,7 +371,7 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
         n2 = max(2, min(steps, 3))
         ms_e2e = timed(e2e, n2)
     nW = int(o_nw[0])
-    mine = o_ll.numpy().reshape(-1)[: T * (we - wb) * 3].reshape(T, we - wb, 3)  # compact: [T][we - wb][3]
+    mine = o_ll.numpy()[: we - wb].transpose(1, 0, 2)  # compact, window-major: [we - wb][T][3] -> [T][we - wb][3]
     ok_cols = bool(np.isfinite(mine).all())
     gathered_ok = None
     if table.ok:
@@ -395,7 +396,7 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
             "e2e": {"ms_per_step": ms_e2e, "comparisons_per_s": comps / (ms_e2e * 1e-3),
                     "h2d_bytes_per_step_rank0": int(h2d[0] + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes),
                     "d2h_bytes_per_step_rank0": int(T * (we - wb) * 24 + T * maxW * 20 + T * 4)},
-            "host_table": "compact [T][this rank's windows][3] per rank (one contiguous copy)"}
+            "host_table": "compact, window-major [this rank's windows][T][3] per rank; contiguous copies, three sub-ranges"}
 
 
 def c5_inputs(torch, S, N, seed=5, src=None):
