@@ -37,7 +37,7 @@ const char *const *const kKernelNames = kKernelNameList;
 
 // ---------------------------------------------------------------------------------------------
 // instrumentation
-LaunchScope::LaunchScope(ibdgem_engine *e_, int id_) : e(e_), id(id_) {
+LaunchScope::LaunchScope(ibdgem_engine *e_, int id_, cudaStream_t s_) : e(e_), id(id_), s(s_ ? s_ : e_->stream) {
     e->k_launches[id]++;
     if (!e->timing) return;
     auto get = [&]() {
@@ -52,11 +52,11 @@ LaunchScope::LaunchScope(ibdgem_engine *e_, int id_) : e(e_), id(id_) {
     };
     a = get();
     b = get();
-    cudaEventRecord(a, e->stream);
+    cudaEventRecord(a, s);
 }
 LaunchScope::~LaunchScope() {
     if (!a) return;
-    cudaEventRecord(b, e->stream);
+    cudaEventRecord(b, s);
     e->pending.push_back({id, a, b});
 }
 int resolve_timers(ibdgem_engine *e) {

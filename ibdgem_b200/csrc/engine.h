@@ -178,7 +178,8 @@ struct LaunchScope {
     ibdgem_engine *e;
     int id;
     cudaEvent_t a = nullptr, b = nullptr;
-    LaunchScope(ibdgem_engine *e_, int id_);
+    cudaStream_t s = nullptr;  // the stream the timed work is launched on (default: the engine stream)
+    LaunchScope(ibdgem_engine *e_, int id_, cudaStream_t s_ = nullptr);
     ~LaunchScope();
 };
 int resolve_timers(ibdgem_engine *e);

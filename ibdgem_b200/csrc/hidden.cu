@@ -43,27 +43,6 @@ __device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int be
 __device__ __forceinline__ bool near_tie(double c0, double c1, double c2, int best, int64_t i) {
     return near_tie(c0, c1, c2, best, tie_scale(i));
 }
-// One target state of one bin, branch-free: the three candidates, the reference's arg-max (strict '>', lowest index
-// wins, NaN never wins — src/hiddengem.c:91-99) and the near-tie test.  The tie test here is the cheaper superset
-// "ANY two candidates closer than the tolerance" (three subtractions and compares instead of fp64 min / max
-// networks): it can only flag more tables, never fewer.
-struct Step3 {
-    double v;
-    int k;
-    bool tie;
-};
-__device__ __forceinline__ Step3 step3(double c0, double c1, double c2, double scale) {
-    Step3 o;
-    const bool g1 = c1 > c0;
-    const double m01 = g1 ? c1 : c0;
-    const bool g2 = c2 > m01;
-    o.v = g2 ? c2 : m01;
-    o.k = g2 ? 2 : (g1 ? 1 : 0);
-    const double tol = fma(scale, fabs(o.v), 1e-12);  // |winner|: finite whenever any candidate is
-    o.tie = (fabs(c0 - c1) < tol) | (fabs(c0 - c2) < tol) | (fabs(c1 - c2) < tol);  // false for NaN and inf - inf
-    return o;
-}
-
 // a finite score below the smallest normal long double: the reference's product is a denormal (or zero) there
 __device__ __forceinline__ bool below_ldbl(double s0, double s1, double s2) {
     return (s0 < LN_LDBL_MIN && s0 > -INFINITY) || (s1 < LN_LDBL_MIN && s1 > -INFINITY) || (s2 < LN_LDBL_MIN && s2 > -INFINITY);

@@ -1291,10 +1291,10 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     for (size_t rk = 0; rk < range_end.size(); rk++) {
     const int w_hi = range_end[rk];
     if (ensure_table(e, range_sites(rk))) return 1;  // waits for the chunk, evaluates its per-site table
-    if (w_hi == w_lo) continue;
-    if (cache_windows(e, w_hi)) return 1;
-    {
-        // (a window shard still reports the bookkeeping of ALL windows: it is the same on every rank)
+    if (w_hi == w_lo && !(sharded && rk == 0)) continue;
+    if (w_hi > w_lo && cache_windows(e, w_hi)) return 1;
+    if (!sharded || rk == 0) {
+        // (a window shard still reports the bookkeeping of ALL windows: it is the same on every rank; once, with its first sub-range)
         LaunchScope ls(e, K_LD_WINDOWS);
         const int b_lo = sharded ? 0 : w_lo, b_hi = sharded ? nW : w_hi;
         const int64_t n = (int64_t)T * (b_hi - b_lo);
@@ -1306,6 +1306,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         e->book_ready = true;
     }
     IBD_CUDA(cudaGetLastError());
+    if (w_hi == w_lo) continue;  // (an empty shard: bookkeeping only)
     // windows are processed in batches so the expanded int8 operands stay within a fixed budget
     for (int w0 = w_lo; w0 < w_hi; w0 += nWb) {
         const int nw = std::min(nWb, w_hi - w0);

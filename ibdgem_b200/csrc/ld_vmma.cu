@@ -56,6 +56,10 @@ struct VCache {
     double *d_l0 = nullptr;         // [nblk * 1024] ln P(D | 00) of the slot's class
     uint32_t *d_tbits = nullptr;    // [nblk][H][32] haplotype-major bits over the K axis
     size_t b_slot = 0, b_n = 0, b_l0 = 0, b_tbits = 0;
+    // the column operand depends on the background only: it is expanded on a side stream while the engine stream builds
+    // the per-target window maps and the row tiles
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 __device__ __forceinline__ uint32_t vspread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
@@ -549,7 +553,7 @@ v_tw_kernel(int T, int mapW, int outW, const int32_t *__restrict__ targets, cons
             const uint64_t *__restrict__ pos, double alpha, double beta, double kappa, int32_t *__restrict__ tw_t, int32_t *__restrict__ tw_w,
             int32_t *__restrict__ tw_ks, int32_t *__restrict__ tw_ke, double *__restrict__ tw_C0, double *__restrict__ tw_R0,
             double *__restrict__ tw_R1, double *__restrict__ wll, int32_t *__restrict__ wn, uint64_t *__restrict__ ws, uint64_t *__restrict__ we,
-            int32_t *__restrict__ nwout) {
+            int32_t *__restrict__ nwout, const int32_t *__restrict__ ownT, int32_t *__restrict__ tw_own) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (gw >= (int64_t)T * mapW) return;
@@ -598,7 +602,7 @@ v_tw_kernel(int T, int mapW, int outW, const int32_t *__restrict__ targets, cons
         const int tw = twbase[t] + w;
         const double R0 = fma(alpha, (double)A0, beta * (double)(N0 - A0));
         const double R1 = fma(alpha, (double)A1, beta * (double)(N1 - A1));
-        tw_t[tw] = t; tw_w[tw] = w; tw_ks[tw] = k0; tw_ke[tw] = k1;
+        tw_t[tw] = t; tw_w[tw] = w; tw_ks[tw] = k0; tw_ke[tw] = k1; tw_own[tw] = ownT[t];
         tw_C0[tw] = c0; tw_R0[tw] = R0; tw_R1[tw] = R1;
         const int64_t o = (int64_t)t * outW + w;
         wll[o * 3 + 2] = ((c0 + R0) + R1) + kappa * (double)M;
@@ -617,7 +621,7 @@ v_tw_site_kernel(SiteView v, int T, int mapW, int outW, const int32_t *__restric
                  double beta, double kappa, int32_t *__restrict__ tw_t, int32_t *__restrict__ tw_w, int32_t *__restrict__ tw_ks,
                  int32_t *__restrict__ tw_ke, double *__restrict__ tw_C0, double *__restrict__ tw_R0, double *__restrict__ tw_R1,
                  double *__restrict__ wll, int32_t *__restrict__ wn, uint64_t *__restrict__ ws, uint64_t *__restrict__ we,
-                 int32_t *__restrict__ nwout) {
+                 int32_t *__restrict__ nwout, const int32_t *__restrict__ ownT, int32_t *__restrict__ tw_own) {
     const int lane = threadIdx.x & 31;
     const int64_t gw = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (gw >= (int64_t)T * mapW) return;
@@ -643,7 +647,7 @@ v_tw_site_kernel(SiteView v, int T, int mapW, int outW, const int32_t *__restric
     if (lane == 0) {
         const int tw = twbase[t] + w;
         const double R0 = fma(alpha, (double)A0, beta * (double)B0), R1 = fma(alpha, (double)A1, beta * (double)B1);
-        tw_t[tw] = t; tw_w[tw] = w; tw_ks[tw] = (int32_t)rank[s0]; tw_ke[tw] = (int32_t)rank[s1];
+        tw_t[tw] = t; tw_w[tw] = w; tw_ks[tw] = (int32_t)rank[s0]; tw_ke[tw] = (int32_t)rank[s1]; tw_own[tw] = ownT[t];
         tw_C0[tw] = c0; tw_R0[tw] = R0; tw_R1[tw] = R1;
         const int64_t o = (int64_t)t * outW + w;
         wll[o * 3 + 2] = ((c0 + R0) + R1) + kappa * (double)M;
@@ -865,6 +869,9 @@ void ld_vtensor_release(ibdgem_engine *e) {
     dev_free(e, c->d_nr, c->b_n);
     dev_free(e, c->d_l0, c->b_l0);
     dev_free(e, c->d_tbits, c->b_tbits);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     e->vc = nullptr;
 }
@@ -957,6 +964,44 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         lognb[t] = nb > 0 ? log((double)nb) : (double)NAN;
     }
 
+    // ---- background operand over the whole K axis, on the side stream ----------------------------
+    static const int vdebug = [] { const char *sb = getenv("IBDGEM_VMMA_DEBUG"); return sb ? atoi(sb) : 0; }();
+    const int nKB = c->nKB;
+    double *d_lnc, *d_lognb;
+    int32_t *d_bgU, *d_ownT;
+    if (scratch(e, SC_V_MISC, (size_t)NT * TILE_IND * 8 + (size_t)T * 8 + (size_t)nU * 4 + (size_t)T * 4 + 64, (void **)&d_lnc)) return 1;
+    d_lognb = d_lnc + (size_t)NT * TILE_IND;
+    d_bgU = reinterpret_cast<int32_t *>(d_lognb + T);
+    d_ownT = d_bgU + nU;
+    IBD_CUDA(cudaMemcpyAsync(d_lnc, lnc.data(), lnc.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_lognb, lognb.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_bgU, bgU.data(), (size_t)nU * 4, cudaMemcpyHostToDevice, e->stream));
+    IBD_CUDA(cudaMemcpyAsync(d_ownT, ownT.data(), (size_t)T * 4, cudaMemcpyHostToDevice, e->stream));
+    unsigned char *d_B;
+    const size_t b_bytes = (size_t)NT * 2 * nKB * B_SLAB;
+    if (scratch(e, SC_MMA_BG, b_bytes, (void **)&d_B)) return 1;
+    if (!c->side) {
+        IBD_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        IBD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        IBD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    IBD_CUDA(cudaEventRecord(c->ev_fork, e->stream));
+    IBD_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    {
+        LaunchScope ls(e, K_V_EXPAND_B, c->side);
+        v_expand_b_kernel<<<dim3((unsigned)nKB, (unsigned)(NT * 2)), 160, 0, c->side>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
+    }
+    IBD_CUDA(cudaEventRecord(c->ev_join, c->side));
+    // every way out of this function rejoins the side stream: the scratch it writes belongs to the engine stream's next call
+    struct Join {
+        ibdgem_engine *e;
+        VCache *c;
+        ~Join() { cudaStreamWaitEvent(e->stream, c->ev_join, 0); }
+    } join{e, c};
+    IBD_CUDA(cudaGetLastError());
+    CUtensorMap mapB;
+    if (make_slab_map(&mapB, d_B, BROWS, (int64_t)NT * 2 * nKB)) return 1;
+
     // ---- per-target window map -> (target, window) records -------------------------------------
     int32_t *d_ks, *d_ke, *d_nwin, *d_twbase;
     int64_t *d_ktot;
@@ -994,45 +1039,30 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         return 0;
     }
     const int n_tiles = (n_tw + TW_TILE - 1) / TW_TILE;
-    const int nKB = c->nKB;
 
-    int32_t *d_tw_t, *d_tw_w, *d_tw_ks, *d_tw_ke, *d_tw_own, *d_order, *d_hist, *d_tile_kb0, *d_tile_nkb, *d_bgU;
-    double *d_tw_C0, *d_tw_R0, *d_tw_R1, *d_lnc, *d_lognb;
+    int32_t *d_tw_t, *d_tw_w, *d_tw_ks, *d_tw_ke, *d_tw_own, *d_order, *d_hist, *d_tile_kb0, *d_tile_nkb;
+    double *d_tw_C0, *d_tw_R0, *d_tw_R1;
     int64_t *d_tile_slab;
     const size_t twn = (size_t)n_tiles * TW_TILE;
     if (scratch(e, SC_V_TWI, twn * 4 * 5, (void **)&d_tw_t) || scratch(e, SC_V_TWD, twn * 8 * 3, (void **)&d_tw_C0) ||
         scratch(e, SC_V_ORDER, twn * 4, (void **)&d_order) || scratch(e, SC_V_HIST, (size_t)(nKB + 2) * 4 * 2, (void **)&d_hist) ||
-        scratch(e, SC_V_TILES, (size_t)n_tiles * (4 + 4 + 8), (void **)&d_tile_slab) ||
-        scratch(e, SC_V_MISC, (size_t)NT * TILE_IND * 8 + (size_t)T * 8 + (size_t)nU * 4 + 64, (void **)&d_lnc))
+        scratch(e, SC_V_TILES, (size_t)n_tiles * (4 + 4 + 8), (void **)&d_tile_slab))
         return 1;
     d_tw_w = d_tw_t + twn; d_tw_ks = d_tw_w + twn; d_tw_ke = d_tw_ks + twn; d_tw_own = d_tw_ke + twn;
     d_tw_R0 = d_tw_C0 + twn; d_tw_R1 = d_tw_R0 + twn;
     d_tile_kb0 = reinterpret_cast<int32_t *>(d_tile_slab + n_tiles); d_tile_nkb = d_tile_kb0 + n_tiles;
-    d_lognb = d_lnc + (size_t)NT * TILE_IND;
-    d_bgU = reinterpret_cast<int32_t *>(d_lognb + T);
     int32_t *d_cursor = d_hist + (nKB + 2);
-    IBD_CUDA(cudaMemcpyAsync(d_lnc, lnc.data(), lnc.size() * 8, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_lognb, lognb.data(), (size_t)T * 8, cudaMemcpyHostToDevice, e->stream));
-    IBD_CUDA(cudaMemcpyAsync(d_bgU, bgU.data(), (size_t)nU * 4, cudaMemcpyHostToDevice, e->stream));
-    {
-        // own column of every (target, window): expanded on the host from the per-target table (n_tw ints)
-        std::vector<int32_t> own_tw((size_t)n_tw);
-        for (int t = 0; t < T; t++)
-            for (int i = h_twbase[(size_t)t]; i < h_twbase[(size_t)t + 1]; i++) own_tw[(size_t)i] = ownT[t];
-        IBD_CUDA(cudaMemcpyAsync(d_tw_own, own_tw.data(), (size_t)n_tw * 4, cudaMemcpyHostToDevice, e->stream));
-        IBD_CUDA(cudaStreamSynchronize(e->stream));  // own_tw goes out of scope
-    }
     {
         LaunchScope ls(e, K_V_TW);
         const int64_t warps = (int64_t)T * mapW;
         if (d_tgt_counts)
             v_tw_site_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
                 v, T, mapW, outW, d_targets, d_nwin, d_twbase, d_wf, d_wl, e->d_rank, e->d_lnP, e->C, e->d_pos, e->alpha, e->beta, e->kappa,
-                d_tw_t, d_tw_w, d_tw_ks, d_tw_ke, d_tw_C0, d_tw_R0, d_tw_R1, d_wll, d_wn, d_ws, d_we, d_nwout);
+                d_tw_t, d_tw_w, d_tw_ks, d_tw_ke, d_tw_C0, d_tw_R0, d_tw_R1, d_wll, d_wn, d_ws, d_we, d_nwout, d_ownT, d_tw_own);
         else
             v_tw_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
                 T, mapW, outW, d_targets, d_nwin, d_twbase, d_ks, d_ke, c->d_tbits, c->H, c->d_nr, c->d_nk, c->d_l0, c->d_slotsite, e->d_pos,
-                e->alpha, e->beta, e->kappa, d_tw_t, d_tw_w, d_tw_ks, d_tw_ke, d_tw_C0, d_tw_R0, d_tw_R1, d_wll, d_wn, d_ws, d_we, d_nwout);
+                e->alpha, e->beta, e->kappa, d_tw_t, d_tw_w, d_tw_ks, d_tw_ke, d_tw_C0, d_tw_R0, d_tw_R1, d_wll, d_wn, d_ws, d_we, d_nwout, d_ownT, d_tw_own);
     }
     {
         LaunchScope ls(e, K_V_SORT);
@@ -1047,19 +1077,6 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     std::vector<int32_t> h_nkb((size_t)n_tiles);
     IBD_CUDA(cudaMemcpyAsync(h_nkb.data(), d_tile_nkb, (size_t)n_tiles * 4, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
-
-    // ---- background operand over the whole K axis ------------------------------------------------
-    static const int vdebug = [] { const char *sb = getenv("IBDGEM_VMMA_DEBUG"); return sb ? atoi(sb) : 0; }();
-    unsigned char *d_B;
-    const size_t b_bytes = (size_t)NT * 2 * nKB * B_SLAB;
-    if (scratch(e, SC_MMA_BG, b_bytes, (void **)&d_B)) return 1;
-    {
-        LaunchScope ls(e, K_V_EXPAND_B);
-        v_expand_b_kernel<<<dim3((unsigned)nKB, (unsigned)(NT * 2)), 160, 0, e->stream>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
-    }
-    IBD_CUDA(cudaGetLastError());
-    CUtensorMap mapB;
-    if (make_slab_map(&mapB, d_B, BROWS, (int64_t)NT * 2 * nKB)) return 1;
 
     // ---- row tiles in batches under the A budget ---------------------------------------------------
     static const size_t a_budget = [] {
@@ -1120,6 +1137,7 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         p.debug = vdebug;
         IBD_CUDA(cudaMemsetAsync(d_unit, 0, 8, e->stream));
         p.unit_counter = d_unit;
+        if (bi == 0) IBD_CUDA(cudaStreamWaitEvent(e->stream, c->ev_join, 0));
         {
             LaunchScope ls(e, K_LD_VMMA);
             const int groups = std::max(1, std::min(p.n_units, e->sm_count / 2));

@@ -505,6 +505,36 @@ def test_window_shards_reassemble_the_unsharded_table():
         np.testing.assert_allclose(table[k, :nw], w["w_log"], rtol=0, atol=1e-9)
 
 
+def test_window_shard_without_windows_still_reports_the_bookkeeping():
+    """More shards than windows: a rank whose shard is empty scores nothing, writes no score column, and still reports
+    the window bookkeeping (the same on every rank)."""
+    import ibdgem_b200 as ib
+    ec = _engine()
+    case = _synth_case(85, 250, 20, 100, True, range(5), pu_idx=3)
+    pk = case.pk
+    want = ec.run_engine(case, expanded=False)
+    nW = want[0]["n_windows"]
+    count = nW + 3
+    seen = np.zeros(nW, bool)
+    with ib.Engine(ib.Params(window_size=100)) as e:
+        for idx in range(count):
+            e.set_window_shard(idx, count)
+            e.upload_sites(pk.pos, pk.n_ref, pk.n_alt, pk.host_keep, None)
+            e.upload_panel(ib.pack_bits(pk.hap), len(pk.names))
+            wb, we, _, _ = e.window_shard()
+            sc = e.score_ld(case.targets, case.bg, 3, max_windows=nW + 2)
+            for k, w in enumerate(want):
+                assert int(sc.n_windows[k]) == nW
+                np.testing.assert_array_equal(sc.w_nsites[k, :nW], w["w_nsites"])
+                np.testing.assert_array_equal(sc.w_start[k, :nW], w["w_start"])
+                np.testing.assert_array_equal(sc.w_end[k, :nW], w["w_end"])
+                assert np.isnan(sc.w_loglik[k, :wb]).all() and np.isnan(sc.w_loglik[k, we:]).all()
+                np.testing.assert_allclose(sc.w_loglik[k, wb:we], w["w_log"][wb:we], rtol=0, atol=1e-9)
+            assert not seen[wb:we].any()
+            seen[wb:we] = True
+    assert seen.all()
+
+
 # ---- per-target windows on the tensor cores (-v, -D): ld_vmma.cu, ld_path == 2 ------------------
 @pytest.mark.parametrize("window,S,N,T", [(10, 2500, 30, 7), (100, 9000, 40, 33), (1000, 30000, 100, 70), (37, 4000, 170, 90)])
 def test_ld_variable_sites_tensor_path_vs_oracle(window, S, N, T):
