@@ -1521,11 +1521,11 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     IBD_CUDA(cudaMemsetAsync(d_we, 0, nWT * 8, e->stream));
     const bool tensor = ld && !e->force_general && shared && ld_tensor_eligible(e, T, n_bg, tgt_counts);
     e->book_ready = false;
-    if (tensor && !e->copy_stream) {  // (a panel set in device memory never went through upload_panel)
+    if ((tensor || vtensor) && !e->copy_stream) {  // (a panel set in device memory never went through upload_panel)
         IBD_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
         IBD_CUDA(cudaEventCreateWithFlags(&e->ev_order, cudaEventDisableTiming));
     }
-    if (tensor && !e->ev_book) IBD_CUDA(cudaEventCreateWithFlags(&e->ev_book, cudaEventDisableTiming));
+    if ((tensor || vtensor) && !e->ev_book) IBD_CUDA(cudaEventCreateWithFlags(&e->ev_book, cudaEventDisableTiming));
     // everything but the tensor path reads the per-site table and the whole panel up front; the
     // tensor path asks for them window range by window range (upload / scoring overlap)
     if (!tensor) {

@@ -115,6 +115,7 @@ struct Params {
     const double *lnc;           // [NT * 80] ln(multiplicity) of each column individual, -inf = padding
     const double *lognb;         // [T] ln n_refpanel or NaN
     double *wll;                 // [T][outW][3]
+    double *wll_host;            // the caller's page-locked table (device alias) or nullptr: finished scores go there too
     int *unit_counter;
     int debug;
 };
@@ -290,9 +291,13 @@ ld_vmma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
                 l1 = (c0 + l1) - (lnb + 1.3862943611198906);  // ln(4 n_refpanel)
                 double l0 = (c0 + L[2]) - lnb;
                 if (!(lnb == lnb)) l0 = l1 = __longlong_as_double(0x7ff8000000000000LL);  // n_refpanel = 0: 0/0
-                double *o = p.wll + ((size_t)t * p.outW + w) * 3;
-                o[0] = l0;
-                o[1] = l1;
+                const size_t oi = ((size_t)t * p.outW + w) * 3;
+                p.wll[oi] = l0;
+                p.wll[oi + 1] = l1;
+                if (p.wll_host) {  // posted writes over PCIe, under the remaining tiles
+                    p.wll_host[oi] = l0;
+                    p.wll_host[oi + 1] = l1;
+                }
             }
         }
     } else if (warp >= EPI_WARP0) {
@@ -589,11 +594,23 @@ v_tw_kernel(int T, int mapW, int outW, const int32_t *__restrict__ targets, cons
         }
         uint32_t v = x0 | x1;
         cnt += __popc(v);
-        // (32 predicated loads per word measured slower than this walk over the ~10 set bits: 1.46 against 1.10 ms at C3)
+        // walk over the ~10 set bits, four at a time so that four loads are in flight before the first add needs its
+        // value (one bit at a time was a chain of L1 latencies; 32 predicated loads per word measured slower still)
+        const double *lw = l0 + (size_t)j * 32;
         while (v) {
-            const int b = __ffs((int)v) - 1;
+            const int b0 = __ffs((int)v) - 1;
             v &= v - 1u;
-            c0 += __ldg(l0 + (size_t)j * 32 + b);
+            const int b1 = __ffs((int)v) - 1;  // -1 when v is empty
+            v &= v - 1u;                       // (0 & anything stays 0)
+            const int b2 = __ffs((int)v) - 1;
+            v &= v - 1u;
+            const int b3 = __ffs((int)v) - 1;
+            v &= v - 1u;
+            const double q0 = __ldg(lw + b0);
+            const double q1 = b1 >= 0 ? __ldg(lw + b1) : 0.0;
+            const double q2 = b2 >= 0 ? __ldg(lw + b2) : 0.0;
+            const double q3 = b3 >= 0 ? __ldg(lw + b3) : 0.0;
+            c0 += (q0 + q1) + (q2 + q3);
         }
     }
     A0 = vwarp_sum(A0); N0 = vwarp_sum(N0); A1 = vwarp_sum(A1); N1 = vwarp_sum(N1); M = vwarp_sum(M); cnt = vwarp_sum(cnt);
@@ -801,31 +818,41 @@ v_expand_a_kernel(int unit0, const int32_t *__restrict__ tile_kb0, const int32_t
     }
 }
 
-// B slabs: block = (k-block, column tile half); thread = (individual of the half, 32-slot word).
-// Rows i, 40 + i, 80 + i of the slab: r0, r1, r0 & r1 of individual i as 0/1 bytes.
+// B slabs: block = (1,024-slot block = 8 k-blocks, column tile half); thread = (individual of the half, 32-slot word
+// of the k-block).  Rows i, 40 + i, 80 + i of the slab: r0, r1, r0 & r1 of individual i as 0/1 bytes.  All 16 loads of a
+// thread are issued before its first store.
 __global__ void __launch_bounds__(160)
 v_expand_b_kernel(int nKB, int nU, const int32_t *__restrict__ bgU, const uint32_t *__restrict__ tbits, int H, unsigned char *__restrict__ out) {
-    const int kb = blockIdx.x, half = blockIdx.y;  // half = n * 2 + rank
+    const int blk = blockIdx.x, half = blockIdx.y;  // half = n * 2 + rank
     const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
     const int u = half * vmma::IND_HALF + i;
-    uint32_t x0 = 0, x1 = 0;
+    uint32_t x0[8], x1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x0[j] = x1[j] = 0;
     if (u < nU) {
         const int ind = __ldg(bgU + u);
-        const int word = kb * 4 + part;
-        const size_t base = ((size_t)(word >> 5) * H) * 32 + (word & 31);
-        x0 = __ldg(tbits + base + (size_t)(2 * ind) * 32);
-        x1 = __ldg(tbits + base + (size_t)(2 * ind + 1) * 32);
+        const uint32_t *r0 = tbits + ((size_t)blk * H + (size_t)(2 * ind)) * 32 + part;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x0[j] = __ldg(r0 + 4 * j);
+            x1[j] = __ldg(r0 + 32 + 4 * j);
+        }
     }
-    const uint32_t xs[3] = {x0, x1, x0 & x1};
-    unsigned char *slab = out + ((size_t)half * nKB + kb) * vmma::B_SLAB;
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        uint32_t e[8];
+    for (int j = 0; j < 8; j++) {
+        const int kb = blk * 8 + j;
+        if (kb >= nKB) break;
+        const uint32_t xs[3] = {x0[j], x1[j], x0[j] & x1[j]};
+        unsigned char *slab = out + ((size_t)half * nKB + kb) * vmma::B_SLAB;
 #pragma unroll
-        for (int k = 0; k < 8; k++) e[k] = vspread4((xs[c] >> (4 * k)) & 15u);
-        uint4 *o = reinterpret_cast<uint4 *>(slab + (size_t)(c * vmma::IND_HALF + i) * 128 + part * 32);
-        __stcs(o, make_uint4(e[0], e[1], e[2], e[3]));
-        __stcs(o + 1, make_uint4(e[4], e[5], e[6], e[7]));
+        for (int c = 0; c < 3; c++) {
+            uint32_t e[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) e[k] = vspread4((xs[c] >> (4 * k)) & 15u);
+            uint4 *o = reinterpret_cast<uint4 *>(slab + (size_t)(c * vmma::IND_HALF + i) * 128 + part * 32);
+            __stcs(o, make_uint4(e[0], e[1], e[2], e[3]));
+            __stcs(o + 1, make_uint4(e[4], e[5], e[6], e[7]));
+        }
     }
 }
 
@@ -989,7 +1016,7 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
     IBD_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
     {
         LaunchScope ls(e, K_V_EXPAND_B, c->side);
-        v_expand_b_kernel<<<dim3((unsigned)nKB, (unsigned)(NT * 2)), 160, 0, c->side>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
+        v_expand_b_kernel<<<dim3((unsigned)((nKB + 7) / 8), (unsigned)(NT * 2)), 160, 0, c->side>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
     }
     IBD_CUDA(cudaEventRecord(c->ev_join, c->side));
     // every way out of this function rejoins the side stream: the scratch it writes belongs to the engine stream's next call
@@ -1064,6 +1091,36 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
                 T, mapW, outW, d_targets, d_nwin, d_twbase, d_ks, d_ke, c->d_tbits, c->H, c->d_nr, c->d_nk, c->d_l0, c->d_slotsite, e->d_pos,
                 e->alpha, e->beta, e->kappa, d_tw_t, d_tw_w, d_tw_ks, d_tw_ke, d_tw_C0, d_tw_R0, d_tw_R1, d_wll, d_wn, d_ws, d_we, d_nwout, d_ownT, d_tw_own);
     }
+    // The bookkeeping arrays and LIBD2 are final here: they leave for the host now, under the rest of the preparation
+    // and the GEMM (score_common copies the bookkeeping on the copy stream once ev_book has fired).  With a page-locked
+    // host table the whole device table goes out once — LIBD2 in place, NaN everywhere else — and the GEMM's merge warps
+    // then store LIBD0 / LIBD1 of every finished (target, window) into it themselves; the GEMM waits for that copy.
+    if (e->ev_book && e->copy_stream) {
+        IBD_CUDA(cudaEventRecord(e->ev_book, e->stream));
+        e->book_ready = true;
+    }
+    double *h_wll_mapped = nullptr;
+    static const int direct_env = [] { const char *sd = getenv("IBDGEM_LD_DIRECT_STORE"); return sd ? atoi(sd) : 1; }();
+    if (e->h_wll_out && direct_env) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, e->h_wll_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            h_wll_mapped = static_cast<double *>(attr.devicePointer);
+        else
+            cudaGetLastError();
+    }
+    if (h_wll_mapped) {
+        if (!e->d2h_stream) IBD_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+        while (e->range_ev.size() < 2) {
+            cudaEvent_t ev;
+            IBD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->range_ev.push_back(ev);
+        }
+        IBD_CUDA(cudaEventRecord(e->range_ev[0], e->stream));
+        IBD_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->range_ev[0], 0));
+        IBD_CUDA(cudaMemcpyAsync(e->h_wll_out, d_wll, (size_t)T * outW * 24, cudaMemcpyDeviceToHost, e->d2h_stream));
+        IBD_CUDA(cudaEventRecord(e->range_ev[1], e->d2h_stream));
+        e->wll_streamed = true;
+    }
     {
         LaunchScope ls(e, K_V_SORT);
         IBD_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)(nKB + 2) * 4, e->stream));
@@ -1134,10 +1191,14 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         p.tile_kb0 = d_tile_kb0; p.tile_nkb = d_tile_nkb; p.tile_slab = d_tile_slab; p.order = d_order;
         p.tw_t = d_tw_t; p.tw_w = d_tw_w; p.tw_own = d_tw_own; p.tw_C0 = d_tw_C0; p.tw_R0 = d_tw_R0; p.tw_R1 = d_tw_R1;
         p.lnc = d_lnc; p.lognb = d_lognb; p.wll = d_wll;
+        p.wll_host = h_wll_mapped;
         p.debug = vdebug;
         IBD_CUDA(cudaMemsetAsync(d_unit, 0, 8, e->stream));
         p.unit_counter = d_unit;
-        if (bi == 0) IBD_CUDA(cudaStreamWaitEvent(e->stream, c->ev_join, 0));
+        if (bi == 0) {
+            IBD_CUDA(cudaStreamWaitEvent(e->stream, c->ev_join, 0));
+            if (h_wll_mapped) IBD_CUDA(cudaStreamWaitEvent(e->stream, e->range_ev[1], 0));
+        }
         {
             LaunchScope ls(e, K_LD_VMMA);
             const int groups = std::max(1, std::min(p.n_units, e->sm_count / 2));
