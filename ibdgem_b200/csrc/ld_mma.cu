@@ -184,7 +184,7 @@ ld_expand_bg_kernel(int w0, int nU, int npadU, int ncols, int ncolpad, int H, in
                     const int32_t *__restrict__ bgU, const double *__restrict__ lnc, const uint32_t *__restrict__ tbits,
                     const uint8_t *__restrict__ nr, const uint8_t *__restrict__ nk, const double *__restrict__ C0,
                     double alpha, double beta, double kappa, double inv_abs_kappa, unsigned char *__restrict__ out,
-                    int32_t *__restrict__ akey, double *__restrict__ Rp, double *__restrict__ Qp) {
+                    int32_t *__restrict__ akey, double *__restrict__ Rp, double *__restrict__ Qp, double *__restrict__ Fp) {
     const int lane = threadIdx.x & 31;
     const int u = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int wl = blockIdx.y, w = w0 + wl;
@@ -193,6 +193,7 @@ ld_expand_bg_kernel(int w0, int nU, int npadU, int ncols, int ncolpad, int H, in
         if (lane < 2 && 2 * u + lane < ncolpad) {
             akey[(size_t)w * ncolpad + 2 * u + lane] = KEY_PAD;
             Rp[(size_t)w * ncolpad + 2 * u + lane] = -INFINITY;
+            Fp[(size_t)w * ncolpad + 2 * u + lane] = 0.0;
         }
         return;
     }
@@ -232,8 +233,12 @@ ld_expand_bg_kernel(int w0, int nU, int npadU, int ncols, int ncolpad, int H, in
         const double p0 = R0 + lc, p1 = R1 + lc;
         Rp[(size_t)w * ncolpad + 2 * u] = p0;
         Rp[(size_t)w * ncolpad + 2 * u + 1] = p1;
-        akey[(size_t)w * ncolpad + 2 * u] = (int32_t)rint(p0 * inv_abs_kappa);
-        akey[(size_t)w * ncolpad + 2 * u + 1] = (int32_t)rint(p1 * inv_abs_kappa);
+        const double k0 = rint(p0 * inv_abs_kappa), k1 = rint(p1 * inv_abs_kappa);
+        akey[(size_t)w * ncolpad + 2 * u] = (int32_t)k0;
+        akey[(size_t)w * ncolpad + 2 * u + 1] = (int32_t)k1;
+        // exp(R' - key |kappa|), the argument within |kappa| / 2 of zero (-inf -> 0 for a column of multiplicity 0)
+        Fp[(size_t)w * ncolpad + 2 * u] = p0 == -INFINITY ? 0.0 : exp(fma(k0, kappa, p0));
+        Fp[(size_t)w * ncolpad + 2 * u + 1] = p1 == -INFINITY ? 0.0 : exp(fma(k1, kappa, p1));
         Qp[(size_t)w * nU + u] = (((C0[w] + R0) + R1) + kappa * (double)M) + lc;
     }
 }
@@ -425,6 +430,7 @@ constexpr int A_SLAB = BM * KBYTES;   // 16 KB
 constexpr int B_SLAB = BN * KBYTES;   // 16 KB
 constexpr int EPI_WARP0 = 4;
 constexpr int NSETS = 4;              // epilogue warp sets of 4 warps (one warp per TMEM lane quarter)
+constexpr int ETAB_N = 512;           // entries of the exp(|kappa| d) table in shared memory
 // Units are handed out dynamically (an atomic counter): CTA pairs differ by ~15 % in speed (the two
 // dies), and pairs that pick up neighbouring units — the row blocks of one window — stream the same
 // background tiles at the same time, which is what lets L2 serve them.  The number travels to every
@@ -451,7 +457,8 @@ struct Cfg {
     static constexpr int NBAR = 2 * MAXKB + 2 * NSTAGE + 2 * NACC + URING;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int OFF_URING = OFF_TMEM + 16;                      // URING unit numbers handed out by the scheduler
-    static constexpr int SMEM_BYTES = OFF_URING + URING * 4 + 1024;      // + alignment slack
+    static constexpr int OFF_ETAB = OFF_URING + URING * 4;               // ETAB_N doubles: exp(|kappa| d) over the screen's reach
+    static constexpr int SMEM_BYTES = OFF_ETAB + ETAB_N * 8 + 1024;      // + alignment slack
     static constexpr uint32_t IDESC = (2u << 4) /* D = s32 */ | (0u << 7) /* A = u8 */ | (0u << 10) /* B = u8 */ |
                                       ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared memory limit");
@@ -468,6 +475,9 @@ struct Params {
     double kappa;
     const int32_t *akey;     // [nW][ncolpad]
     const double *Rp;        // [nW][ncolpad]
+    const double *Fp;        // [nW][ncolpad] exp(R' - key |kappa|): the part of a term the integer key does not carry
+    int tab_n, dpos;         // table mode (tab_n > 0): entries delta + dpos + 1 of exp(|kappa| (i - delta)); a row's
+                             // reference key may trail its running maximum by up to dpos
     const double *Rt;        // [nW][nrows] R_w of each target row
     const int32_t *row_own;  // [nrows] first excluded column of the row, or -1
     const double *C0;        // [nW]
@@ -530,6 +540,8 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
     }
     if (warp == 3)
         for (int i = lane; i < 2 * BM; i += 32) reinterpret_cast<int *>(smem + OFF_KMAX)[i] = KEY_INIT;
+    for (int i = threadIdx.x; i < p.tab_n; i += CF::THREADS)
+        reinterpret_cast<double *>(smem + CF::OFF_ETAB)[i] = exp(-p.kappa * (double)(i - p.delta));
     if (warp == 2) {
         if constexpr (CG == 1) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
@@ -753,7 +765,14 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             const bool row_ok = row < p.nrows;
             const int own0 = row_ok ? p.row_own[row] : -1;
             const int32_t *akw = p.akey + (size_t)w * p.ncolpad;
-            const double *rpw = p.Rp + (size_t)w * p.ncolpad;
+            // Table mode.  A term is exp(kappa M + R') = exp(|kappa| (key - M)) * F with F = exp(R' - key |kappa|): relative
+            // to a per-row reference key the first factor is a table entry and the term one fp64 FMA — no exp on the
+            // candidate path, which is what rows with many near-maximal columns (a pileup whose source is not in the
+            // background) spend their time on.  The row's partial is (|kappa| vref, s).
+            const bool tab = p.tab_n > 0;
+            const double *etab = reinterpret_cast<const double *>(smem + CF::OFF_ETAB);
+            const double *rpw = (tab ? p.Fp : p.Rp) + (size_t)w * p.ncolpad;
+            int vref = KEY_INIT;
             int kmax = row_ok ? KEY_INIT : (1 << 30);  // padding rows never reach the fp64 path
             // the sets see disjoint columns: they share the row's running maximum key through shared
             // memory (monotone, so a stale read only lets more elements through the screen)
@@ -850,6 +869,11 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         if (row_ok) atomicMax(skmax, cm);
                     }
                     const int thr = kmax - p.delta;
+                    if (tab && row_ok && cm > vref + p.dpos) {
+                        // rare: the row's first chunk, or a maximum far above the reference: move the reference
+                        s *= exp(p.kappa * (double)(kmax - vref));  // (kmax >= cm here; 0 stays 0)
+                        vref = kmax;
+                    }
                     // an element passes the screen only if the chunk maximum does: the per-element
                     // mask is built only when some row of the warp has a candidate in this chunk
                     uint32_t mask = 0;
@@ -869,9 +893,13 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
                         const int j = act ? __ffs((int)mk) - 1 : 0;
                         mk &= mk - 1u;
                         const int vj = pick32(v, j);
-                        const int M = skeys[c * 32 + j] - vj;  // v = key - M
                         const double rp = __shfl_sync(0xffffffffu, rp_cur[c], j);
-                        if (act) lse_add_fast(m, s, fma(p.kappa, (double)M, rp));
+                        if (tab) {
+                            if (act) s = fma(etab[vj - vref + p.delta], rp, s);  // thr < vj <= vref + dpos
+                        } else {
+                            const int M = skeys[c * 32 + j] - vj;  // v = key - M
+                            if (act) lse_add_fast(m, s, fma(p.kappa, (double)M, rp));
+                        }
                     }
                 }
                 tc_fence_before();
@@ -883,7 +911,7 @@ ld_mma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__
             if (set == 0) skmax_all[((it + 1) & 1) * BM + rloc] = KEY_INIT;  // next unit's slot (idle since unit it - 1)
             if (tr_role < 3) IBD_TRACE(tr_role, 4, g0);
             asm volatile("bar.sync 2, %0;" ::"n"(NSETS * 128 + 64) : "memory");  // previous unit's partials consumed
-            merge[set * BM + rloc] = make_double2(m, s);
+            merge[set * BM + rloc] = tab ? make_double2(-p.kappa * (double)vref, s) : make_double2(m, s);
             asm volatile("bar.arrive 1, %0;" ::"n"(NSETS * 128 + 64) : "memory");
             if (tr_role < 3) IBD_TRACE(tr_role, 7, g0);
         }
@@ -1216,13 +1244,13 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     }();
     const int nWb = (int)std::max<size_t>(1, std::min<size_t>({(size_t)nW, budget / per_window, (size_t)MAX_GRID_Y}));
     int32_t *d_bgU, *d_ownU, *d_rowown, *d_akey;
-    double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp, *d_Rt;
+    double *d_lnc, *d_lognb, *d_lognb4, *d_Rp, *d_Qp, *d_Rt, *d_Fp;
     unsigned char *d_A, *d_B;
     const size_t misc_i = (size_t)nU + T + 2 * (size_t)T;
     const size_t misc_d = (size_t)nU + 2 * (size_t)T;
     if (scratch(e, SC_MMA_MISC, misc_i * 4 + misc_d * 8 + 64, (void **)&d_lnc) ||
         scratch(e, SC_MMA_BGIDX, (size_t)nW * ncolpad * 4, (void **)&d_akey) ||
-        scratch(e, SC_MMA_ROWLSE, ((size_t)nW * ncolpad + (size_t)nW * nU + (size_t)nW * nrows) * 8, (void **)&d_Rp) ||
+        scratch(e, SC_MMA_ROWLSE, (2 * (size_t)nW * ncolpad + (size_t)nW * nU + (size_t)nW * nrows) * 8, (void **)&d_Rp) ||
         scratch(e, SC_MMA_TGT, (size_t)nWb * nrows * c->Wpad, (void **)&d_A) ||
         scratch(e, SC_MMA_BG, (size_t)nWb * ncols * c->Wpad, (void **)&d_B))
         return 1;
@@ -1231,7 +1259,8 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
     d_bgU = reinterpret_cast<int32_t *>(d_lognb4 + T);
     d_ownU = d_bgU + nU;
     d_rowown = d_ownU + T;
-    d_Qp = d_Rp + (size_t)nW * ncolpad;
+    d_Fp = d_Rp + (size_t)nW * ncolpad;
+    d_Qp = d_Fp + (size_t)nW * ncolpad;
     d_Rt = d_Qp + (size_t)nW * nU;
     {
         // the call's small tables go up in one piece from pinned memory, laid out like SC_MMA_MISC
@@ -1315,7 +1344,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
             const int npadU = ncolpad / 2;
             ld_expand_bg_kernel<<<dim3((unsigned)((npadU + 7) / 8), (unsigned)nw), 256, 0, e->stream>>>(
                 w0, nU, npadU, ncols, ncolpad, c->H, c->Wpad, c->WP32, d_bgU, d_lnc, c->d_tbits, c->d_nr, c->d_nk, c->d_C0,
-                e->alpha, e->beta, e->kappa, 1.0 / -e->kappa, d_B, d_akey, d_Rp, d_Qp);
+                e->alpha, e->beta, e->kappa, 1.0 / -e->kappa, d_B, d_akey, d_Rp, d_Qp, d_Fp);
         }
         {
             LaunchScope ls(e, K_LD_EXPAND_TGT);
@@ -1336,6 +1365,17 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         p.delta = (int)ceil(screen_nats(ncols) / -e->kappa) + 2;
         p.kappa = e->kappa;
         p.akey = d_akey; p.Rp = d_Rp; p.Rt = d_Rt;
+        p.Fp = d_Fp;
+        {
+            // table mode when the screen's reach plus the head-room above a row's reference key fits the shared-memory
+            // table and exp(|kappa| dpos) stays far from overflow; IBDGEM_MMA_TABLE=0 keeps the exp path (A/B)
+            static const int tab_env = [] { const char *st = getenv("IBDGEM_MMA_TABLE"); return st ? atoi(st) : 1; }();
+            const int dpos = (int)std::min(256.0, floor(600.0 / -e->kappa));
+            const int tab_n = p.delta + dpos + 1;
+            const bool tab = tab_env && dpos >= 8 && tab_n <= mma::ETAB_N;
+            p.tab_n = tab ? tab_n : 0;
+            p.dpos = dpos;
+        }
         p.row_own = d_rowown;
         p.C0 = c->d_C0; p.lognb4 = d_lognb4; p.wll = d_wll;
         p.wll_host = direct ? h_wll_mapped : nullptr;

@@ -1012,13 +1012,15 @@ int ld_vtensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, cons
         IBD_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         IBD_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     }
+    static const int use_side = [] { const char *sv = getenv("IBDGEM_V_SIDE"); return sv ? atoi(sv) : 1; }();  // 0: A/B, all on the engine stream
+    cudaStream_t bstream = use_side ? c->side : e->stream;
     IBD_CUDA(cudaEventRecord(c->ev_fork, e->stream));
-    IBD_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    IBD_CUDA(cudaStreamWaitEvent(bstream, c->ev_fork, 0));
     {
-        LaunchScope ls(e, K_V_EXPAND_B, c->side);
-        v_expand_b_kernel<<<dim3((unsigned)((nKB + 7) / 8), (unsigned)(NT * 2)), 160, 0, c->side>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
+        LaunchScope ls(e, K_V_EXPAND_B, bstream);
+        v_expand_b_kernel<<<dim3((unsigned)((nKB + 7) / 8), (unsigned)(NT * 2)), 160, 0, bstream>>>(nKB, nU, d_bgU, c->d_tbits, c->H, d_B);
     }
-    IBD_CUDA(cudaEventRecord(c->ev_join, c->side));
+    IBD_CUDA(cudaEventRecord(c->ev_join, bstream));
     // every way out of this function rejoins the side stream: the scratch it writes belongs to the engine stream's next call
     struct Join {
         ibdgem_engine *e;
