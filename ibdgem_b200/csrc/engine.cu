@@ -12,6 +12,7 @@
 
 #include "engine.h"
 #include "site_math.cuh"
+#include "tc_common.cuh"
 
 namespace ibdgem {
 
@@ -146,6 +147,71 @@ __global__ void fill_nan_kernel(double *p, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K_SITE_COUNT: ALT-allele count of every panel line (phase 1 of the site table) as a stream.  A line is
+// Wh words — 628 bytes at 2,504 individuals, not a multiple of 16 — so loads addressed line by line are
+// narrow and split sectors; R consecutive lines, R a multiple of 4, are one contiguous 16-byte-aligned span.
+// One thread moves spans into a ring of shared-memory stages with 1-D bulk copies (TMA); the warps
+// popcount the lines out of shared memory, a warp per line.  Persistent: one CTA per SM, CNT_STAGES spans
+// in flight each.
+constexpr int CNT_STAGES = 4, CNT_THREADS = 256, CNT_STAGE_BYTES = 40960;
+__global__ void __launch_bounds__(CNT_THREADS)
+site_count_kernel(int64_t s_begin, int64_t s_end, int64_t n_groups, int R, int H, int64_t Wh, const uint32_t *__restrict__ bits,
+                  int32_t *__restrict__ cnt) {
+    extern __shared__ __align__(128) unsigned char csm[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(csm), *empty = full + CNT_STAGES;
+    unsigned char *stages = csm + 128;
+    const uint32_t stage_bytes = (uint32_t)(R * Wh * 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CNT_STAGES; i++) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, CNT_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t g, int st) {
+        const int64_t r0 = s_begin + g * R;
+        const uint32_t bytes = (uint32_t)(min((int64_t)R, s_end - r0) * Wh * 4);  // (s_end - s_begin) % 4 == 0
+        mbar_expect_tx(full + st, bytes);
+        bulk_load_1d(stages + (size_t)st * stage_bytes, bits + r0 * Wh, bytes, full + st);
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < CNT_STAGES; k++) {
+            const int64_t g = blockIdx.x + (int64_t)k * gridDim.x;
+            if (g < n_groups) issue(g, k);
+        }
+    const int nfull = H >> 5, rem = H & 31;
+    int it = 0;
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
+        const int st = it % CNT_STAGES;
+        const uint32_t ph = (uint32_t)(it / CNT_STAGES) & 1u;
+        mbar_wait(full + st, ph);
+        const int64_t r0 = s_begin + g * R;
+        const int rg = (int)min((int64_t)R, s_end - r0);
+        const uint32_t *sp = reinterpret_cast<const uint32_t *>(stages + (size_t)st * stage_bytes);
+        for (int r = warp; r < rg; r += CNT_THREADS / 32) {
+            const uint32_t *row = sp + (size_t)r * Wh;
+            int c = 0;
+            for (int w = lane; w < nfull; w += 32) c += __popc(row[w]);
+            if (lane == 0 && rem) c += __popc(row[nfull] & ((1u << rem) - 1u));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) cnt[r0 + r] = c;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + st);
+        if (threadIdx.x == 0) {
+            const int64_t gn = g + (int64_t)CNT_STAGES * gridDim.x;
+            if (gn < n_groups) {
+                mbar_wait(empty + st, ph);
+                issue(gn, st);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K_SITE_TABLE: a warp takes 32 consecutive panel lines.  Phase 1 streams the packed rows with
 // 128-bit loads (four lanes per row) and popcounts them for the allele frequency (find_f_impute,
 // src/ibd-parse.c:91-99); lane r ends up with row r's count.  Phase 2 is lane-parallel, one site per
@@ -157,7 +223,7 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
                   const uint8_t *__restrict__ nalt, const double *__restrict__ afuser,
                   const double *__restrict__ Ptab, int C, double min_af, double max_af, int max_cov,
                   double *__restrict__ f_out, uint8_t *__restrict__ keep, uint8_t *__restrict__ status,
-                  double *__restrict__ lik7, double *__restrict__ lnlik7) {
+                  double *__restrict__ lik7, double *__restrict__ lnlik7, const int32_t *__restrict__ precnt) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -171,6 +237,9 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
         // shuffles to join the quarters, one to hand row r's count to lane r
         int mycnt = 0;
         const int j = lane >> 2, q = lane & 3;
+        if (precnt) {  // phase 1 was done by site_count_kernel
+            if (lane < rows) mycnt = __ldg(precnt + s0 + lane);
+        } else {
 #pragma unroll
         for (int it = 0; it < 4; it++) {
             const int r = it * 8 + j;
@@ -189,6 +258,7 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
             cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
             const int got = __shfl_sync(0xffffffffu, cnt, 4 * (lane & 7));
             if ((lane >> 3) == it) mycnt = got;
+        }
         }
         const int64_t s = s0 + lane;
         if (lane < rows) {
@@ -436,6 +506,7 @@ window_nonld_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ tar
 // in shared memory once per CTA; every thread then walks the sites with its target's genotype
 // bits, so the table is read from HBM once per window instead of once per target.
 constexpr int NONLD_TILE = 256;  // sites staged per pass
+template <int NONLD_BATCH>  // genotype loads in flight per thread
 __global__ void __launch_bounds__(128)
 window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ targets, int T,
                            const uint64_t *__restrict__ pos, const uint8_t *__restrict__ status,
@@ -480,14 +551,15 @@ window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restric
         for (int i = threadIdx.x; i < cnt * 7; i += blockDim.x) sl[i / 7][i % 7] = lnlik7[ssite[i / 7] * 7 + i % 7];
         __syncthreads();
         if (t < T) {
-            // genotype loads are issued eight at a time: one dependent global load per site made this loop
-            // a chain of L2 round trips (the kernel sat at 12 % of HBM)
-            for (int j0 = 0; j0 < cnt; j0 += 8) {
-                uint32_t pr[8];
+            // genotype loads are issued NONLD_BATCH at a time: one dependent global load per site made this loop a
+            // chain of L2 round trips (the kernel sat at 12 % of HBM); with 8 per batch a 100-site window was still
+            // 13 round trips long
+            for (int j0 = 0; j0 < cnt; j0 += NONLD_BATCH) {
+                uint32_t pr[NONLD_BATCH];
 #pragma unroll
-                for (int q = 0; q < 8; q++) pr[q] = (j0 + q < cnt) ? hap_pair(v.bits + ssite[j0 + q] * v.Wh, indiv) : 0u;
+                for (int q = 0; q < NONLD_BATCH; q++) pr[q] = (j0 + q < cnt) ? hap_pair(v.bits + ssite[j0 + q] * v.Wh, indiv) : 0u;
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
+                for (int q = 0; q < NONLD_BATCH; q++) {
                     if (j0 + q < cnt) {
                         const int g = (int)(pr[q] & 1u) + (int)(pr[q] >> 1);
                         a0 += sl[j0 + q][0];
@@ -807,10 +879,31 @@ int ensure_table(ibdgem_engine *e, int64_t s_end) {
     if (e->table_upto >= s_end) return 0;
     {
         LaunchScope ls(e, K_SITE_TABLE);
-        const int64_t n = s_end - e->table_upto;
-        site_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-            e->table_upto, s_end, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C,
-            e->prm.min_af, e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7, e->d_lnlik7);
+        auto table = [&](int64_t a, int64_t b, const int32_t *cnt) {
+            if (b <= a) return;
+            site_table_kernel<<<(unsigned)((b - a + 255) / 256), 256, 0, e->stream>>>(
+                a, b, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C, e->prm.min_af,
+                e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7, e->d_lnlik7, cnt);
+        };
+        // the allele counts of the 4-line-aligned middle of the range come from the streaming kernel (see
+        // site_count_kernel); the few lines around it, short ranges and odd buffers keep the fused kernel
+        static const int bulk_env = [] { const char *sb = getenv("IBDGEM_SITE_COUNT_BULK"); return sb ? atoi(sb) : 1; }();
+        const int64_t a = e->table_upto, a4 = (a + 3) & ~(int64_t)3, b4 = s_end & ~(int64_t)3;
+        const int R = (int)std::min<int64_t>(64, (CNT_STAGE_BYTES / (e->Wh * 4)) & ~(int64_t)3);
+        int32_t *d_cnt = nullptr;
+        if (bulk_env && R >= 4 && b4 - a4 >= 4096 && (reinterpret_cast<uintptr_t>(e->d_bits) & 15) == 0 &&
+            scratch(e, SC_SITE_CNT, (size_t)e->S * 4, (void **)&d_cnt) == 0) {
+            const int64_t n_groups = (b4 - a4 + R - 1) / R;
+            const size_t smem = 128 + (size_t)CNT_STAGES * R * e->Wh * 4;
+            IBD_CUDA(cudaFuncSetAttribute(site_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            site_count_kernel<<<(unsigned)std::min<int64_t>(n_groups, std::max(1, e->sm_count)), CNT_THREADS, smem, e->stream>>>(
+                a4, b4, n_groups, R, 2 * e->N, e->Wh, e->d_bits, d_cnt);
+            table(a, a4, nullptr);
+            table(a4, b4, d_cnt);
+            table(b4, s_end, nullptr);
+        } else {
+            table(a, s_end, nullptr);
+        }
     }
     IBD_CUDA(cudaGetLastError());
     e->table_upto = s_end;
@@ -1569,8 +1662,11 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         {
             LaunchScope ls(e, K_WINDOW_NONLD);
             if (shared) {
-                window_nonld_shared_kernel<<<dim3((unsigned)std::max(e->nW_shared, 1), (unsigned)((T + 127) / 128)), 128, 0, e->stream>>>(
-                    v, m, d_targets, T, e->d_pos, e->d_status, e->d_lnlik7, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
+                // IBDGEM_NONLD_BATCH: 8 / 16 / 32 genotype loads in flight per thread (A/B; more loads, fewer resident CTAs)
+                static const int batch = [] { const char *sb = getenv("IBDGEM_NONLD_BATCH"); return sb ? atoi(sb) : 16; }();
+                const dim3 grid((unsigned)std::max(e->nW_shared, 1), (unsigned)((T + 127) / 128));
+                auto kern = batch >= 32 ? window_nonld_shared_kernel<32> : (batch >= 16 ? window_nonld_shared_kernel<16> : window_nonld_shared_kernel<8>);
+                kern<<<grid, 128, 0, e->stream>>>(v, m, d_targets, T, e->d_pos, e->d_status, e->d_lnlik7, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
             } else {
                 const int64_t warps = (int64_t)nWT;
                 window_nonld_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, e->stream>>>(
