@@ -150,8 +150,8 @@ __global__ void fill_nan_kernel(double *p, int64_t n) {
 // K_SITE_COUNT: ALT-allele count of every panel line (phase 1 of the site table) as a stream.  A line is
 // Wh words — 628 bytes at 2,504 individuals, not a multiple of 16 — so loads addressed line by line are
 // narrow and split sectors; R consecutive lines, R a multiple of 4, are one contiguous 16-byte-aligned span.
-// One thread moves spans into a ring of shared-memory stages with 1-D bulk copies (TMA); the warps
-// popcount the lines out of shared memory, a warp per line.  Persistent: one CTA per SM, CNT_STAGES spans
+// One thread moves spans into a ring of shared-memory stages with 1-D bulk copies (TMA); the threads
+// popcount the lines out of shared memory, four lanes per line (R <= CNT_THREADS / 4).  Persistent: one CTA per SM, CNT_STAGES spans
 // in flight each.
 constexpr int CNT_STAGES = 4, CNT_THREADS = 256, CNT_STAGE_BYTES = 40960;
 __global__ void __launch_bounds__(CNT_THREADS)
@@ -161,7 +161,7 @@ site_count_kernel(int64_t s_begin, int64_t s_end, int64_t n_groups, int R, int H
     uint64_t *full = reinterpret_cast<uint64_t *>(csm), *empty = full + CNT_STAGES;
     unsigned char *stages = csm + 128;
     const uint32_t stage_bytes = (uint32_t)(R * Wh * 4);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < CNT_STAGES; i++) {
             mbar_init(full + i, 1);
@@ -190,14 +190,20 @@ site_count_kernel(int64_t s_begin, int64_t s_end, int64_t n_groups, int R, int H
         const int64_t r0 = s_begin + g * R;
         const int rg = (int)min((int64_t)R, s_end - r0);
         const uint32_t *sp = reinterpret_cast<const uint32_t *>(stages + (size_t)st * stage_bytes);
-        for (int r = warp; r < rg; r += CNT_THREADS / 32) {
-            const uint32_t *row = sp + (size_t)r * Wh;
+        {
+            // four lanes per line, 64 lines per pass: ~40 independent shared-memory loads per thread (a warp per line was
+            // a chain of five loads and five shuffles per line — latency-bound at eight warps per SM)
+            const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
             int c = 0;
-            for (int w = lane; w < nfull; w += 32) c += __popc(row[w]);
-            if (lane == 0 && rem) c += __popc(row[nfull] & ((1u << rem) - 1u));
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) cnt[r0 + r] = c;
+            if (r < rg) {
+                const uint32_t *row = sp + (size_t)r * Wh;
+#pragma unroll 8
+                for (int w = q; w < nfull; w += 4) c += __popc(row[w]);
+                if (q == 0 && rem) c += __popc(row[nfull] & ((1u << rem) - 1u));
+            }
+            c += __shfl_xor_sync(0xffffffffu, c, 1);
+            c += __shfl_xor_sync(0xffffffffu, c, 2);
+            if (q == 0 && r < rg) cnt[r0 + r] = c;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + st);
@@ -1662,8 +1668,8 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
         {
             LaunchScope ls(e, K_WINDOW_NONLD);
             if (shared) {
-                // IBDGEM_NONLD_BATCH: 8 / 16 / 32 genotype loads in flight per thread (A/B; more loads, fewer resident CTAs)
-                static const int batch = [] { const char *sb = getenv("IBDGEM_NONLD_BATCH"); return sb ? atoi(sb) : 16; }();
+                // IBDGEM_NONLD_BATCH: 8 / 16 / 32 genotype loads in flight per thread (A/B: measured 0.154 / 0.181 / 0.242 ms at C2 — more loads in flight cost more in resident CTAs than they save)
+                static const int batch = [] { const char *sb = getenv("IBDGEM_NONLD_BATCH"); return sb ? atoi(sb) : 8; }();
                 const dim3 grid((unsigned)std::max(e->nW_shared, 1), (unsigned)((T + 127) / 128));
                 auto kern = batch >= 32 ? window_nonld_shared_kernel<32> : (batch >= 16 ? window_nonld_shared_kernel<16> : window_nonld_shared_kernel<8>);
                 kern<<<grid, 128, 0, e->stream>>>(v, m, d_targets, T, e->d_pos, e->d_status, e->d_lnlik7, outW, d_wll, d_wn, d_ws, d_we, d_nwout);
