@@ -197,8 +197,17 @@ site_count_kernel(int64_t s_begin, int64_t s_end, int64_t n_groups, int R, int H
             int c = 0;
             if (r < rg) {
                 const uint32_t *row = sp + (size_t)r * Wh;
+                // every line starts its walk 4 words further on than the line before (wrapping around): with a line length
+                // that is a multiple of 32 words the eight lines of a warp would otherwise meet in the same banks
+                const int n4 = (nfull + 3) & ~3;
+                int w = q + 4 * (r & 7);
+                if (w >= n4) w %= n4;
 #pragma unroll 8
-                for (int w = q; w < nfull; w += 4) c += __popc(row[w]);
+                for (int k = 0; k < n4; k += 4) {
+                    if (w < nfull) c += __popc(row[w]);
+                    w += 4;
+                    if (w >= n4) w -= n4;
+                }
                 if (q == 0 && rem) c += __popc(row[nfull] & ((1u << rem) - 1u));
             }
             c += __shfl_xor_sync(0xffffffffu, c, 1);
@@ -229,7 +238,8 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
                   const uint8_t *__restrict__ nalt, const double *__restrict__ afuser,
                   const double *__restrict__ Ptab, int C, double min_af, double max_af, int max_cov,
                   double *__restrict__ f_out, uint8_t *__restrict__ keep, uint8_t *__restrict__ status,
-                  double *__restrict__ lik7, double *__restrict__ lnlik7, const int32_t *__restrict__ precnt) {
+                  double *__restrict__ lik7, double *__restrict__ lnlik7, const int32_t *__restrict__ precnt,
+                  const double *__restrict__ lnPtab) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -288,10 +298,13 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
                 v[3] = lik_ibd1(2, f, P0, P1, P2);
                 v[4] = P0; v[5] = P1; v[6] = P2;
             }
+            // ln P(D | g) comes from the engine's table (the long double logarithms every other path uses): three of the
+            // seven fp64 logarithms of a site
+            const double *lP = lnPtab + (k ? (size_t)(r * C + a) * 3 : 0);
 #pragma unroll
             for (int i = 0; i < 7; i++) {
                 lik7[s * 7 + i] = v[i];
-                lnlik7[s * 7 + i] = k ? log(v[i]) : v[i];
+                lnlik7[s * 7 + i] = k ? (i >= 4 ? lP[i - 4] : log(v[i])) : v[i];
             }
             f_out[s] = f;
             keep[s] = k ? 1 : 0;
@@ -510,7 +523,11 @@ window_nonld_kernel(SiteView v, WindowMapView m, const int32_t *__restrict__ tar
 // K_WINDOW_NONLD, shared window map (no -v, no -D): one CTA per window, one thread per target.
 // The window's rows of the per-site log table (56 bytes per site, target-independent) are staged
 // in shared memory once per CTA; every thread then walks the sites with its target's genotype
-// bits, so the table is read from HBM once per window instead of once per target.
+// bits, so the table is read from HBM once per window instead of once per target.  The kernel is
+// issue-bound (ncu: 68 % issue slots, 19 % L2), so the walk is kept short: the row offset of every
+// staged site is precomputed, ln IBD1 | g and ln IBD2 | g of a site sit side by side (one 16-byte
+// shared load per site and target), and LIBD0 — the same for every target — is summed once per CTA
+// from the values the threads stage.
 constexpr int NONLD_TILE = 256;  // sites staged per pass
 template <int NONLD_BATCH>  // genotype loads in flight per thread
 __global__ void __launch_bounds__(128)
@@ -519,9 +536,11 @@ window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restric
                            const double *__restrict__ lnlik7, int outW, double *__restrict__ wll,
                            int32_t *__restrict__ wn, uint64_t *__restrict__ ws, uint64_t *__restrict__ we,
                            int32_t *__restrict__ nwin_out) {
-    __shared__ double sl[NONLD_TILE][7];
-    __shared__ int64_t ssite[NONLD_TILE];
+    __shared__ double2 sl12[NONLD_TILE][3];  // [site][g] = (ln IBD1 | g, ln IBD2 | g)
+    __shared__ int64_t srow[NONLD_TILE];     // word offset of the site's panel line
+    __shared__ int32_t soff[NONLD_TILE];     // the site, relative to the window's first
     __shared__ int segcnt[NONLD_TILE / 32];
+    __shared__ double sa0[4];
     constexpr int PASSES = NONLD_TILE / 128;
     const int w = blockIdx.x;
     const int nw = m.nwin[0];
@@ -530,8 +549,10 @@ window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restric
     if (w >= nw || w >= m.maxW) return;
     const int64_t s0 = m.wfirst[w], s1 = m.wlast[w];
     const int indiv = t < T ? targets[t] : 0;
+    const uint32_t *tcol = v.bits + (indiv >> 4);
+    const int tsh = (indiv & 15) * 2;
     const int lane = threadIdx.x & 31;
-    double a0 = 0, a1 = 0, a2 = 0;
+    double a0p = 0, a1 = 0, a2 = 0;  // a0p: this thread's share of the window's LIBD0 terms
     int n = 0;
     for (int64_t sb = s0; sb <= s1; sb += NONLD_TILE) {
         __syncthreads();
@@ -550,34 +571,53 @@ window_nonld_shared_kernel(SiteView v, WindowMapView m, const int32_t *__restric
             const int seg = (q * 128 + (int)threadIdx.x) >> 5;
             int base = 0;
             for (int k = 0; k < seg; k++) base += segcnt[k];
-            if ((bal[q] >> lane) & 1u) ssite[base + __popc(bal[q] & ((1u << lane) - 1u))] = sb + q * 128 + threadIdx.x;
+            if ((bal[q] >> lane) & 1u) {
+                const int slot = base + __popc(bal[q] & ((1u << lane) - 1u));
+                const int64_t site = sb + q * 128 + threadIdx.x;
+                srow[slot] = site * v.Wh;
+                soff[slot] = (int32_t)(site - s0);
+            }
         }
         for (int k = 0; k < NONLD_TILE / 32; k++) cnt += segcnt[k];
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * 7; i += blockDim.x) sl[i / 7][i % 7] = lnlik7[ssite[i / 7] * 7 + i % 7];
+        for (int i = threadIdx.x; i < cnt * 7; i += blockDim.x) {
+            const int j = i / 7, c = i - j * 7;
+            const double x = lnlik7[(s0 + soff[j]) * 7 + c];
+            double *dst = reinterpret_cast<double *>(&sl12[j][0]);
+            if (c == 0)
+                a0p += x;
+            else if (c <= 3)
+                dst[(c - 1) * 2] = x;
+            else
+                dst[(c - 4) * 2 + 1] = x;
+        }
         __syncthreads();
         if (t < T) {
             // genotype loads are issued NONLD_BATCH at a time: one dependent global load per site made this loop a
-            // chain of L2 round trips (the kernel sat at 12 % of HBM); with 8 per batch a 100-site window was still
-            // 13 round trips long
+            // chain of L2 round trips
             for (int j0 = 0; j0 < cnt; j0 += NONLD_BATCH) {
                 uint32_t pr[NONLD_BATCH];
 #pragma unroll
-                for (int q = 0; q < NONLD_BATCH; q++) pr[q] = (j0 + q < cnt) ? hap_pair(v.bits + ssite[j0 + q] * v.Wh, indiv) : 0u;
+                for (int q = 0; q < NONLD_BATCH; q++) pr[q] = (j0 + q < cnt) ? __ldg(tcol + srow[j0 + q]) : 0u;
 #pragma unroll
                 for (int q = 0; q < NONLD_BATCH; q++) {
                     if (j0 + q < cnt) {
-                        const int g = (int)(pr[q] & 1u) + (int)(pr[q] >> 1);
-                        a0 += sl[j0 + q][0];
-                        a1 += sl[j0 + q][1 + g];
-                        a2 += sl[j0 + q][4 + g];
+                        const int g = __popc((pr[q] >> tsh) & 3u);
+                        const double2 l = sl12[j0 + q][g];
+                        a1 += l.x;
+                        a2 += l.y;
                     }
                 }
             }
             n += cnt;
         }
     }
+    // LIBD0 of the window: the threads' shares, joined once
+    a0p = warp_sum_d(a0p);
+    if (lane == 0) sa0[threadIdx.x >> 5] = a0p;
+    __syncthreads();
     if (t < T) {
+        const double a0 = (sa0[0] + sa0[1]) + (sa0[2] + sa0[3]);
         const int64_t o = (int64_t)t * outW + w;
         wll[o * 3 + 0] = a0;
         wll[o * 3 + 1] = a1;
@@ -889,7 +929,7 @@ int ensure_table(ibdgem_engine *e, int64_t s_end) {
             if (b <= a) return;
             site_table_kernel<<<(unsigned)((b - a + 255) / 256), 256, 0, e->stream>>>(
                 a, b, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C, e->prm.min_af,
-                e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7, e->d_lnlik7, cnt);
+                e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7, e->d_lnlik7, cnt, e->d_lnP);
         };
         // the allele counts of the 4-line-aligned middle of the range come from the streaming kernel (see
         // site_count_kernel); the few lines around it, short ranges and odd buffers keep the fused kernel
