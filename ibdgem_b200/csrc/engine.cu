@@ -12,7 +12,6 @@
 
 #include "engine.h"
 #include "site_math.cuh"
-#include "tc_common.cuh"
 
 namespace ibdgem {
 
@@ -147,86 +146,6 @@ __global__ void fill_nan_kernel(double *p, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K_SITE_COUNT: ALT-allele count of every panel line (phase 1 of the site table) as a stream.  A line is
-// Wh words — 628 bytes at 2,504 individuals, not a multiple of 16 — so loads addressed line by line are
-// narrow and split sectors; R consecutive lines, R a multiple of 4, are one contiguous 16-byte-aligned span.
-// One thread moves spans into a ring of shared-memory stages with 1-D bulk copies (TMA); the threads
-// popcount the lines out of shared memory, four lanes per line (R <= CNT_THREADS / 4).  Persistent: one CTA per SM, CNT_STAGES spans
-// in flight each.
-constexpr int CNT_STAGES = 4, CNT_THREADS = 256, CNT_STAGE_BYTES = 40960;
-__global__ void __launch_bounds__(CNT_THREADS)
-site_count_kernel(int64_t s_begin, int64_t s_end, int64_t n_groups, int R, int H, int64_t Wh, const uint32_t *__restrict__ bits,
-                  int32_t *__restrict__ cnt) {
-    extern __shared__ __align__(128) unsigned char csm[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(csm), *empty = full + CNT_STAGES;
-    unsigned char *stages = csm + 128;
-    const uint32_t stage_bytes = (uint32_t)(R * Wh * 4);
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < CNT_STAGES; i++) {
-            mbar_init(full + i, 1);
-            mbar_init(empty + i, CNT_THREADS / 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](int64_t g, int st) {
-        const int64_t r0 = s_begin + g * R;
-        const uint32_t bytes = (uint32_t)(min((int64_t)R, s_end - r0) * Wh * 4);  // (s_end - s_begin) % 4 == 0
-        mbar_expect_tx(full + st, bytes);
-        bulk_load_1d(stages + (size_t)st * stage_bytes, bits + r0 * Wh, bytes, full + st);
-    };
-    if (threadIdx.x == 0)
-        for (int k = 0; k < CNT_STAGES; k++) {
-            const int64_t g = blockIdx.x + (int64_t)k * gridDim.x;
-            if (g < n_groups) issue(g, k);
-        }
-    const int nfull = H >> 5, rem = H & 31;
-    int it = 0;
-    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
-        const int st = it % CNT_STAGES;
-        const uint32_t ph = (uint32_t)(it / CNT_STAGES) & 1u;
-        mbar_wait(full + st, ph);
-        const int64_t r0 = s_begin + g * R;
-        const int rg = (int)min((int64_t)R, s_end - r0);
-        const uint32_t *sp = reinterpret_cast<const uint32_t *>(stages + (size_t)st * stage_bytes);
-        {
-            // four lanes per line, 64 lines per pass: ~40 independent shared-memory loads per thread (a warp per line was
-            // a chain of five loads and five shuffles per line — latency-bound at eight warps per SM)
-            const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
-            int c = 0;
-            if (r < rg) {
-                const uint32_t *row = sp + (size_t)r * Wh;
-                // every line starts its walk 4 words further on than the line before (wrapping around): with a line length
-                // that is a multiple of 32 words the eight lines of a warp would otherwise meet in the same banks
-                const int n4 = (nfull + 3) & ~3;
-                int w = q + 4 * (r & 7);
-                if (w >= n4) w %= n4;
-#pragma unroll 8
-                for (int k = 0; k < n4; k += 4) {
-                    if (w < nfull) c += __popc(row[w]);
-                    w += 4;
-                    if (w >= n4) w -= n4;
-                }
-                if (q == 0 && rem) c += __popc(row[nfull] & ((1u << rem) - 1u));
-            }
-            c += __shfl_xor_sync(0xffffffffu, c, 1);
-            c += __shfl_xor_sync(0xffffffffu, c, 2);
-            if (q == 0 && r < rg) cnt[r0 + r] = c;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + st);
-        if (threadIdx.x == 0) {
-            const int64_t gn = g + (int64_t)CNT_STAGES * gridDim.x;
-            if (gn < n_groups) {
-                mbar_wait(empty + st, ph);
-                issue(gn, st);
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // K_SITE_TABLE: a warp takes 32 consecutive panel lines.  Phase 1 streams the packed rows with
 // 128-bit loads (four lanes per row) and popcounts them for the allele frequency (find_f_impute,
 // src/ibd-parse.c:91-99); lane r ends up with row r's count.  Phase 2 is lane-parallel, one site per
@@ -238,8 +157,8 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
                   const uint8_t *__restrict__ nalt, const double *__restrict__ afuser,
                   const double *__restrict__ Ptab, int C, double min_af, double max_af, int max_cov,
                   double *__restrict__ f_out, uint8_t *__restrict__ keep, uint8_t *__restrict__ status,
-                  double *__restrict__ lik7, double *__restrict__ lnlik7, const int32_t *__restrict__ precnt,
-                  const double *__restrict__ lnPtab) {
+                  double *__restrict__ lik7, double *__restrict__ lnlik7, const double *__restrict__ lnPtab) {
+    __shared__ double stage7[8][32 * 7];
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -253,9 +172,6 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
         // shuffles to join the quarters, one to hand row r's count to lane r
         int mycnt = 0;
         const int j = lane >> 2, q = lane & 3;
-        if (precnt) {  // phase 1 was done by site_count_kernel
-            if (lane < rows) mycnt = __ldg(precnt + s0 + lane);
-        } else {
 #pragma unroll
         for (int it = 0; it < 4; it++) {
             const int r = it * 8 + j;
@@ -275,8 +191,11 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
             const int got = __shfl_sync(0xffffffffu, cnt, 4 * (lane & 7));
             if ((lane >> 3) == it) mycnt = got;
         }
-        }
         const int64_t s = s0 + lane;
+        double v[7], lv[7];
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int i = 0; i < 7; i++) v[i] = lv[i] = nan;
         if (lane < rows) {
             double f = __ddiv_rn((double)mycnt, (double)H);
             if (afuser) {
@@ -285,10 +204,6 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
             }
             const int r = nref[s], a = nalt[s];
             const bool k = hostkeep[s] && !(f > max_af || f < min_af) && (r + a <= max_cov);
-            const double nan = __longlong_as_double(0x7ff8000000000000LL);
-            double v[7];
-#pragma unroll
-            for (int i = 0; i < 7; i++) v[i] = nan;
             if (k) {
                 const double *P = Ptab + (size_t)(r * C + a) * 3;
                 const double P0 = P[0], P1 = P[1], P2 = P[2];
@@ -302,13 +217,23 @@ site_table_kernel(int64_t s_begin, int64_t S, int32_t N, int64_t Wh, const uint3
             // seven fp64 logarithms of a site
             const double *lP = lnPtab + (k ? (size_t)(r * C + a) * 3 : 0);
 #pragma unroll
-            for (int i = 0; i < 7; i++) {
-                lik7[s * 7 + i] = v[i];
-                lnlik7[s * 7 + i] = k ? (i >= 4 ? lP[i - 4] : log(v[i])) : v[i];
-            }
+            for (int i = 0; i < 7; i++) lv[i] = k ? (i >= 4 ? lP[i - 4] : log(v[i])) : v[i];
             f_out[s] = f;
             keep[s] = k ? 1 : 0;
             status[s] = k ? ((r + a >= 1) ? 1 : 2) : 0;
+        }
+        // the warp's 32 x 7 values of each table are contiguous in memory: they pass through shared memory so that every
+        // store instruction writes 256 contiguous bytes (a lane storing its own seven doubles touched 14 lines per
+        // instruction — ncu: the table half of this kernel was bound by those stores)
+        double *stw = stage7[threadIdx.x >> 5];
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 7; i++) stw[lane * 7 + i] = pass ? lv[i] : v[i];
+            __syncwarp();
+            double *dst = (pass ? lnlik7 : lik7) + s0 * 7;
+            for (int i = lane; i < rows * 7; i += 32) dst[i] = stw[i];
         }
     }
 }
@@ -925,31 +850,10 @@ int ensure_table(ibdgem_engine *e, int64_t s_end) {
     if (e->table_upto >= s_end) return 0;
     {
         LaunchScope ls(e, K_SITE_TABLE);
-        auto table = [&](int64_t a, int64_t b, const int32_t *cnt) {
-            if (b <= a) return;
-            site_table_kernel<<<(unsigned)((b - a + 255) / 256), 256, 0, e->stream>>>(
-                a, b, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C, e->prm.min_af,
-                e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7, e->d_lnlik7, cnt, e->d_lnP);
-        };
-        // the allele counts of the 4-line-aligned middle of the range come from the streaming kernel (see
-        // site_count_kernel); the few lines around it, short ranges and odd buffers keep the fused kernel
-        static const int bulk_env = [] { const char *sb = getenv("IBDGEM_SITE_COUNT_BULK"); return sb ? atoi(sb) : 1; }();
-        const int64_t a = e->table_upto, a4 = (a + 3) & ~(int64_t)3, b4 = s_end & ~(int64_t)3;
-        const int R = (int)std::min<int64_t>(64, (CNT_STAGE_BYTES / (e->Wh * 4)) & ~(int64_t)3);
-        int32_t *d_cnt = nullptr;
-        if (bulk_env && R >= 4 && b4 - a4 >= 4096 && (reinterpret_cast<uintptr_t>(e->d_bits) & 15) == 0 &&
-            scratch(e, SC_SITE_CNT, (size_t)e->S * 4, (void **)&d_cnt) == 0) {
-            const int64_t n_groups = (b4 - a4 + R - 1) / R;
-            const size_t smem = 128 + (size_t)CNT_STAGES * R * e->Wh * 4;
-            IBD_CUDA(cudaFuncSetAttribute(site_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            site_count_kernel<<<(unsigned)std::min<int64_t>(n_groups, std::max(1, e->sm_count)), CNT_THREADS, smem, e->stream>>>(
-                a4, b4, n_groups, R, 2 * e->N, e->Wh, e->d_bits, d_cnt);
-            table(a, a4, nullptr);
-            table(a4, b4, d_cnt);
-            table(b4, s_end, nullptr);
-        } else {
-            table(a, s_end, nullptr);
-        }
+        const int64_t n = s_end - e->table_upto;
+        site_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+            e->table_upto, s_end, e->N, e->Wh, e->d_bits, e->d_hostkeep, e->d_nref, e->d_nalt, e->d_afuser, e->d_P, e->C,
+            e->prm.min_af, e->prm.max_af, (int)e->prm.max_cov, e->d_f, e->d_keep, e->d_status, e->d_lik7, e->d_lnlik7, e->d_lnP);
     }
     IBD_CUDA(cudaGetLastError());
     e->table_upto = s_end;
