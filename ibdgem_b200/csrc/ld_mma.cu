@@ -1195,7 +1195,7 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         window_shard_bounds(e, &shard_wb, &shard_we, nullptr, &shard_se);
         range_end.clear();
         // three sub-ranges when results go to the host and the shard is large: the copy of a sub-range's columns runs
-        // under the next sub-range's GEMM, so a third of it is left at the end
+        // under the next sub-range's GEMM, so only the last one's is left at the end
         const int span = shard_we - shard_wb;
         static const int parts_env = [] { const char *sp = getenv("IBDGEM_SHARD_PARTS"); return sp ? atoi(sp) : 3; }();
         // ... as long as every sub-range still keeps the persistent GEMM busy for >= 8 rounds of units (IBDGEM_SHARD_PARTS < 0
@@ -1204,7 +1204,13 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         int parts = 1;
         if (parts_env < 0) parts = std::min(span, -parts_env);
         else if (e->h_wll_out && parts_env > 1) parts = (int)std::max<int64_t>(1, std::min<int64_t>(parts_env, units / (8 * std::max(1, e->sm_count / 2))));
-        for (int k = 1; k <= parts; k++) range_end.push_back(shard_wb + (int)((int64_t)span * k / parts));
+        // sub-ranges shrink (parts : parts - 1 : ... : 1): what is left after the last GEMM is the copy of the smallest one
+        const int64_t wsum = (int64_t)parts * (parts + 1) / 2;
+        int64_t acc = 0;
+        for (int k = 0; k < parts; k++) {
+            acc += parts - k;
+            range_end.push_back(shard_wb + (int)((int64_t)span * acc / wsum));
+        }
         by_chunk = false;
     }
     auto range_sites = [&](size_t k) { return by_chunk ? e->chunk_end[k] : shard_se; };

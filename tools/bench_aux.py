@@ -305,7 +305,9 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
     o_nw = _pinned(torch, (T,), torch.int32)
     # the host score table of a window shard is compact and window-major: [this rank's windows][T][3]
     # (ibdgem_engine_set_shard_compact_output)
-    o_ll = _pinned(torch, ((S // W + world) // world + 1, T, 3), torch.float64)
+    # (one rank: no shard, the usual [T][maxW][3] table)
+    compact = world > 1
+    o_ll = _pinned(torch, ((S // W + world) // world + 1, T, 3) if compact else (T, maxW, 3), torch.float64)
     book = rank == 0  # the bookkeeping arrays are the same on every rank: only the root fetches them
     o_ws = _pinned(torch, (T, maxW), torch.int64) if book else None
     o_we = _pinned(torch, (T, maxW), torch.int64) if book else None
@@ -340,7 +342,7 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
     with ib.Engine(ib.Params(window_size=W, device=dev_i)) as e:
         e.set_stream(stream.cuda_stream)
         e.set_window_shard(rank, world)
-        e.set_shard_compact_output(True)
+        e.set_shard_compact_output(compact)
         e.upload_sites(pos, n_ref, n_alt, keep)
         e.upload_panel(bits, N)
         e.sync_uploads()
@@ -371,7 +373,8 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
         n2 = max(2, min(steps, 3))
         ms_e2e = timed(e2e, n2)
     nW = int(o_nw[0])
-    mine = o_ll.numpy()[: we - wb].transpose(1, 0, 2)  # compact, window-major: [we - wb][T][3] -> [T][we - wb][3]
+    # compact, window-major: [we - wb][T][3] -> [T][we - wb][3]
+    mine = o_ll.numpy()[: we - wb].transpose(1, 0, 2) if compact else o_ll.numpy()[:, wb:we]
     ok_cols = bool(np.isfinite(mine).all())
     gathered_ok = None
     if table.ok:
@@ -396,7 +399,8 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
             "e2e": {"ms_per_step": ms_e2e, "comparisons_per_s": comps / (ms_e2e * 1e-3),
                     "h2d_bytes_per_step_rank0": int(h2d[0] + pos.nbytes + n_ref.nbytes + n_alt.nbytes + keep.nbytes + targets.nbytes + bg.nbytes),
                     "d2h_bytes_per_step_rank0": int(T * (we - wb) * 24 + T * maxW * 20 + T * 4)},
-            "host_table": "compact, window-major [this rank's windows][T][3] per rank; contiguous copies, three sub-ranges"}
+            "host_table": ("compact, window-major [this rank's windows][T][3] per rank; contiguous copies, three shrinking sub-ranges"
+                           if compact else "[T][max_windows][3]")}
 
 
 def c5_inputs(torch, S, N, seed=5, src=None):
