@@ -321,6 +321,8 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
     d_panel = torch.empty((S, bits.shape[1]), dtype=torch.int32, device=dev)
     up_stream = torch.cuda.Stream(device=dev)
 
+    per_rank = []  # ms per step of every rank, one list per timed loop (the reported figure is the maximum)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -336,6 +338,9 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            per_rank.append([round(float(x.item()), 3) for x in every])
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
@@ -393,6 +398,7 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
             "columns stored into the root's HBM over NVLink (CUDA IPC peer stores%s)" % (world, nW, T, "" if table.ok else
             " UNAVAILABLE here: no gather was made"),
             "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "comparisons_per_s": comps / (ms * 1e-3),
+            "ms_per_step_by_rank": per_rank[0] if per_rank else [ms],
             "kernels_ms_rank0": st, "rank0_windows": [wb, we], "rank0_rows": [sb, se],
             "shard_columns_finite": ok_cols, "gathered_table_complete_and_equal": gathered_ok,
             "gather_bytes_per_rank": int(T) * (we - wb) * 24,
