@@ -1203,7 +1203,10 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         const int64_t units = (int64_t)span * ((2 * T + 255) / 256);
         int parts = 1;
         if (parts_env < 0) parts = std::min(span, -parts_env);
-        else if (e->h_wll_out && parts_env > 1) parts = (int)std::max<int64_t>(1, std::min<int64_t>(parts_env, units / (8 * std::max(1, e->sm_count / 2))));
+        else if (e->h_wll_out && parts_env > 1 && (size_t)T * span * 24 >= ((size_t)20 << 20))
+            // (a sub-range costs ~0.1 ms in launches and GEMM ramps: measured a loss below ~20 MB of shard table — C3 over
+            // 2 and 4 GPUs — and a gain above — C5 over 8)
+            parts = (int)std::max<int64_t>(1, std::min<int64_t>(parts_env, units / (8 * std::max(1, e->sm_count / 2))));
         // sub-ranges shrink (parts : parts - 1 : ... : 1): what is left after the last GEMM is the copy of the smallest one
         const int64_t wsum = (int64_t)parts * (parts + 1) / 2;
         int64_t acc = 0;
