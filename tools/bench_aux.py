@@ -344,10 +344,16 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # IBDGEM_TIMELINE_SHARDED=prefix: kernel timeline of the resident steps, one file per rank (prefix.T<targets>.<rank>)
+    tl = os.environ.get("IBDGEM_TIMELINE_SHARDED")
+    if tl:
+        os.environ["IBDGEM_TIMELINE"] = "%s.T%d.%d" % (tl, T, rank)
     with ib.Engine(ib.Params(window_size=W, device=dev_i)) as e:
         e.set_stream(stream.cuda_stream)
         e.set_window_shard(rank, world)
         e.set_shard_compact_output(compact)
+        if tl:
+            e.enable_timing(True)  # before the sites go up: that is where the timeline's zero is taken
         e.upload_sites(pos, n_ref, n_alt, keep)
         e.upload_panel(bits, N)
         e.sync_uploads()
@@ -377,6 +383,8 @@ def leg_window_sharded(torch, ib, world, rank, h_bits, pos, n_ref, n_alt, N, tar
             e2e()
         n2 = max(2, min(steps, 3))
         ms_e2e = timed(e2e, n2)
+    if tl:
+        os.environ.pop("IBDGEM_TIMELINE", None)
     nW = int(o_nw[0])
     # compact, window-major: [we - wb][T][3] -> [T][we - wb][3]
     mine = o_ll.numpy()[: we - wb].transpose(1, 0, 2) if compact else o_ll.numpy()[:, wb:we]
