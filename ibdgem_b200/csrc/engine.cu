@@ -59,6 +59,13 @@ LaunchScope::~LaunchScope() {
     cudaEventRecord(b, s);
     e->pending.push_back({id, a, b});
 }
+// End of an ABI call: the event pairs of its launches stay pending — they are read when somebody asks for the statistics
+// (kernel_stats / reset_stats), when a timeline is being written, or when many have piled up.  Reading them at the end of
+// every call cost ~0.3 ms of host time per call (two driver calls per launch), which the next call then started late by.
+int settle_timers(ibdgem_engine *e) {
+    if (e->t0_set || e->pending.size() > 4096) return resolve_timers(e);
+    return 0;
+}
 int resolve_timers(ibdgem_engine *e) {
     FILE *tl = e->timeline_path && e->t0_set && !e->pending.empty() ? fopen(e->timeline_path, "a") : nullptr;
     for (auto &p : e->pending) {
@@ -1433,7 +1440,7 @@ int ibdgem_engine_prepare(ibdgem_engine *e) {
     e->prepared = true;
     ld_tensor_invalidate(e);
     ld_vtensor_invalidate(e);
-    resolve_timers(e);
+    settle_timers(e);
     return 0;
 }
 
@@ -1746,7 +1753,7 @@ static int score_common(ibdgem_engine *e, int32_t T, const int32_t *targets, int
     if (e->book_ready) IBD_CUDA(cudaStreamSynchronize(e->copy_stream));
     if (e->wll_streamed || e->wll_dev_streamed) IBD_CUDA(cudaStreamSynchronize(e->d2h_stream));
     e->book_ready = false;
-    resolve_timers(e);
+    settle_timers(e);
     if (e->t0_set) {
         if (FILE *tl = fopen(e->timeline_path, "a")) {
             float ms = 0;

@@ -183,6 +183,7 @@ struct LaunchScope {
     ~LaunchScope();
 };
 int resolve_timers(ibdgem_engine *e);
+int settle_timers(ibdgem_engine *e);
 // Pinned host staging of at least `bytes`.  One buffer: a caller must have synchronised the stream
 // that reads or writes it before the next caller asks (every ABI call ends with such a sync).
 int pinned_stage(ibdgem_engine *e, size_t bytes, void **out);

@@ -742,7 +742,7 @@ extern "C" int hiddengem_viterbi_batch(ibdgem_engine *e, int32_t n_tables, const
     }
     if (rc) return 1;
     IBD_CUDA(cudaGetLastError());
-    resolve_timers(e);
+    settle_timers(e);
     // flagged tables: the reference's long double recurrence decides (tables are independent: a few host threads)
     std::vector<int> flagged;
     for (int t = 0; t < n_tables; t++) {
@@ -826,7 +826,7 @@ extern "C" int hiddengem_viterbi_batch_device(ibdgem_engine *e, int32_t n_tables
     std::vector<uint8_t> h_flag((size_t)n_tables);
     IBD_CUDA(cudaMemcpyAsync(h_flag.data(), d_flag, (size_t)n_tables, cudaMemcpyDeviceToHost, e->stream));
     IBD_CUDA(cudaStreamSynchronize(e->stream));
-    resolve_timers(e);
+    settle_timers(e);
     e->hg_flagged = 0;
     for (int t = 0; t < n_tables; t++) {
         if (!h_flag[(size_t)t]) continue;
