@@ -1339,8 +1339,11 @@ int ld_tensor_score(ibdgem_engine *e, int32_t T, const int32_t *h_targets, const
         ld_windows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
             b_lo, b_hi, T, nW, outW, c->W, c->K, e->d_wfirst, e->d_wlast, e->d_pos, d_wn, d_ws, d_we, d_nwout);
     }
-    if ((w_hi == nW || sharded) && e->ev_book) {  // START / END / NUM_SITES of every window are final: their copy to the
-        IBD_CUDA(cudaEventRecord(e->ev_book, e->stream));  // host can overlap the GEMM (score_common)
+    // START / END / NUM_SITES of every window are final: their copy to the host can overlap the GEMM (score_common).
+    // Recorded ONCE: the copy waits for the event's latest record, so a record per sub-range of a shard held the
+    // bookkeeping copy back until the last sub-range (200 MB at C5: it then outlasted the last GEMM on the root rank).
+    if (e->ev_book && !e->book_ready && (sharded ? rk == 0 : w_hi == nW)) {
+        IBD_CUDA(cudaEventRecord(e->ev_book, e->stream));
         e->book_ready = true;
     }
     IBD_CUDA(cudaGetLastError());
