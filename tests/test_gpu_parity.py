@@ -809,3 +809,89 @@ def test_window_shard_in_sub_ranges_with_compact_output():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_c2_full_size_spot_checks_against_oracle():
+    """BASELINE.json configs[1] at full size (1,000,000 sites x 2,504 samples x 100 targets, window 100, depth
+    Poisson(2): 13.5 % of the sites carry no read and belong to no window).  Windows are independent, so any window
+    of any target can be re-scored by the CPU oracle from the window's own panel lines; plus the size-independent
+    integer properties of the whole table."""
+    import ibdgem_b200 as ib
+    import oracle
+    from ibdgem_b200.synth import synth_panel_torch, unpack_rows
+    S, N, T, W = 1_000_000, 2504, 100, 100
+    d = synth_panel_torch(S, N, seed=1, device="cuda")
+    bits = d["bits"].numpy().view(np.uint32)
+    pos = d["pos"].numpy().view(np.uint64)
+    rng = np.random.default_rng(2)
+    g = (bits[:, 0] & 1) + ((bits[:, 0] >> 1) & 1)  # genotype of individual 0, the source of the reads
+    depth = np.minimum(rng.poisson(2.0, S), 20)
+    n_alt = rng.binomial(depth, np.where(g == 0, 0.02, np.where(g == 1, 0.5, 0.98))).astype(np.uint8)
+    n_ref = (depth - n_alt).astype(np.uint8)
+    keep = np.ones(S, np.uint8)
+    targets = np.arange(T, dtype=np.int32)
+    with ib.Engine(ib.Params(window_size=W)) as e:
+        e.upload_sites(pos, n_ref, n_alt, keep)
+        e.upload_panel(bits, N)
+        sc = e.score_nonld(targets)
+        assert e.kernel_stats()["window_nonld"][1] >= 1
+    idx = np.flatnonzero(depth >= 1)
+    nW = -(-len(idx) // W)
+    assert (sc.n_windows == nW).all()
+    assert (sc.w_nsites[:, :nW - 1] == W).all() and (sc.w_nsites[:, :nW].sum(axis=1) == len(idx)).all()
+    np.testing.assert_array_equal(sc.w_start[0, :nW], pos[idx[0::W]])
+    np.testing.assert_array_equal(sc.w_end[T - 1, :nW - 1], pos[idx[W - 1::W]][:nW - 1])
+    assert np.isfinite(sc.w_loglik[:, :nW]).all()
+    assert int(sc.processed[0]) + int(sc.skipped[0]) == S
+    # LIBD0 does not depend on the target's genotype
+    assert np.ptp(sc.w_loglik[:, :nW, 0], axis=0).max() == 0.0
+    prm = oracle.Params(window=W, ld_mode=0)
+    bg = np.arange(N, dtype=np.int32)
+    for w in (0, 4321, nW - 2):
+        rows = np.arange(idx[w * W], idx[(w + 1) * W - 1] + 1)
+        hap = unpack_rows(bits, 2 * N, rows)
+        for t in (0, 57, T - 1):
+            o = oracle.compare_target(prm, pos[rows], keep[rows], n_ref[rows], n_alt[rows], hap, int(t), bg)
+            assert o["n_windows"] == 1 and int(o["w_nsites"][0]) == W
+            np.testing.assert_allclose(sc.w_loglik[t, w], o["w_log"][0], rtol=0, atol=1e-8)
+
+
+def test_c4_full_size_spot_checks_against_oracle():
+    """BASELINE.json configs[3] at full size (10,000 tables x 10,000 bins of log-likelihoods, planted segments):
+    tables are independent, so any table can be decoded by the CPU oracle on its own (as far as the reference's
+    long double range reaches); plus size-independent properties of the whole batch (state counts of every table)."""
+    import torch
+    import ibdgem_b200 as ib
+    import oracle
+    n_tables, n_bins = 10_000, 10_000
+    nb = n_tables * n_bins
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    seg = torch.randint(0, 3, (nb // 200 + 1,), generator=gen, device=dev).repeat_interleave(200)[:nb]
+    ll = torch.randn((nb, 3), generator=gen, device=dev, dtype=torch.float64) * 10.0 - 150.0
+    ll[torch.arange(nb, device=dev), seg] += 8.0
+    h_ll = ll.cpu().numpy()
+    del ll, seg
+    torch.cuda.empty_cache()
+    off = np.arange(n_tables + 1, dtype=np.int64) * n_bins
+    with ib.Engine(ib.Params()) as e:
+        state, score, counts = e.viterbi_batch(h_ll, off, True)
+        assert e.kernel_stats()["viterbi_back"][1] > 0  # the batched kernels are the ones that ran
+    st2 = state.reshape(n_tables, n_bins)
+    assert int(st2.max()) <= 2 and (counts.sum(axis=1) == n_bins).all()
+    for k in range(3):
+        np.testing.assert_array_equal((st2 == k).sum(axis=1), counts[:, k])
+    # The reference's running long double products leave the normal range after ~5,700 of these bins (about -2 nats
+    # per bin) and every later state reads 0 there (SURVEY.md Appendix A; INTEGRATION.md 4): the log-space front-end
+    # keeps going, so the oracle is the judge up to that bin — forward scores exactly up to it, states up to one
+    # segment before it (the back-trace enters the valid part from whatever the tail decided and coalesces within bins).
+    tiny = np.finfo(np.longdouble).tiny
+    for t in (0, 4999, n_tables - 1):
+        sl = slice(t * n_bins, (t + 1) * n_bins)
+        st, sc, sc_ld = oracle.hiddengem(np.exp(h_ll[sl]))
+        bad = np.flatnonzero((sc_ld < tiny).any(axis=1))
+        n_ok = int(bad[0]) if len(bad) else n_bins
+        assert n_ok > 2000, n_ok
+        np.testing.assert_allclose(score[sl][:n_ok], sc[:n_ok], rtol=0, atol=1e-6)
+        np.testing.assert_array_equal(st2[t][: n_ok - 400], st[: n_ok - 400])
