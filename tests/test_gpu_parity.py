@@ -106,6 +106,22 @@ def test_ld_synthetic_vs_oracle(window, S, N, T, force_general):
         assert results[0]["ld_path"] == 1
 
 
+@pytest.mark.parametrize("eps", [0.001, 0.1, 0.3, 0.45])
+def test_ld_other_error_rates_vs_oracle(eps):
+    """The exp table of the ld_mma epilogue is sized from epsilon (kappa = ln 4 eps (1 - eps)): a dozen entries of
+    reach at 0.001, ~400 at 0.3, and at 0.45 (kappa = -0.01) the screen's reach does not fit the table and the
+    exp-based candidate path runs.  With the reads' source in the background (peaked rows) and without it (flat rows:
+    many columns within the screen's reach of the row maximum)."""
+    ec = _engine()
+    N = 40
+    for seed, bg, pu_idx in ((31, None, 2), (32, list(range(1, N)), -1)):
+        case = _synth_case(seed, 3000, N, 100, True, range(7), bg=bg, pu_idx=pu_idx, eps=eps)
+        results = ec.run_engine(case, expanded=False)
+        assert results[0]["ld_path"] == 1
+        for res, ora in zip(results, refcases.oracle_run(case)):
+            ec.assert_matches_oracle(res, ora)
+
+
 def test_ld_background_subsets_and_duplicates():
     ec = _engine()
     bg = [0, 3, 3, 5, 7, 8, 9, 11, 12, 20, 21, 22, 2]
